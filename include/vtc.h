@@ -1,0 +1,227 @@
+/*
+ * vtc.h -- C-ABI of libvtc.so: the B200 (sm_100a) ViT forward + CAM / attention-rollout hot path.
+ *
+ * The reference (Jingfeng-Tang/vision_transformer_cam) has no FFI: its "operator API" for this path is the
+ * Python surface of vit_model.py plus the inline post-processing of predict.py / validate.py.  This header
+ * is what a ctypes binding of that path binds (INTEGRATION.md shows the stub).  Each entry point cites the
+ * reference lines it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every function returns int: VTC_OK (0) or a negative VTC_ERR_*; `vtc_last_error()` (thread local)
+ *     describes the last failure.  Nothing throws, nothing prints.
+ *   - all tensor pointers are DEVICE pointers owned by the caller (torch allocations), dense row-major,
+ *     borrowed until the enqueued work has run.  The library never allocates or frees device memory and
+ *     never synchronises: work is enqueued on the `stream` argument (a cudaStream_t passed as void*).
+ *   - sm_100a only.  There is no CPU path and no other-architecture path: on anything else the first
+ *     enqueue returns VTC_ERR_ARCH.
+ *   - shapes: B images, N = 1 + (img/patch)^2 tokens, D embed_dim, H heads, hd = D/H, L depth, C classes,
+ *     P = N-1 patches, g = img/patch, K = topk (16).
+ */
+#ifndef VTC_H_
+#define VTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define VTC_API __attribute__((visibility("default")))
+#else
+#define VTC_API
+#endif
+
+enum {
+    VTC_OK = 0,
+    VTC_ERR_ARG = -1,       /* null pointer / bad enum / inconsistent option */
+    VTC_ERR_SHAPE = -2,     /* unsupported shape (e.g. embed_dim not a multiple of 128) */
+    VTC_ERR_ARCH = -3,      /* device is not compute capability 10.x */
+    VTC_ERR_CUDA = -4,      /* a CUDA runtime / driver call failed */
+    VTC_ERR_WORKSPACE = -5  /* workspace or packed-weight buffer too small / misaligned */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * Model description: VisionTransformer.__init__ arguments (vit_model.py:215-219) that shape the forward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vtc_config {
+    int32_t img_size;            /* 224 | 384 | 448 ... (square, vit_model.py:53-56) */
+    int32_t patch_size;          /* 16 */
+    int32_t in_c;                /* 3 */
+    int32_t num_classes;         /* C */
+    int32_t embed_dim;           /* D, multiple of 128, head_dim must be 64 */
+    int32_t depth;               /* L */
+    int32_t num_heads;           /* H */
+    int32_t mlp_hidden;          /* int(D * mlp_ratio), multiple of 256 */
+    int32_t representation_size; /* 0 = pre_logits is Identity (vit_model.py:267-276) */
+    int32_t mask_from;           /* 4: first layer whose CLS attention builds a mask (vit_model.py:118,325) */
+    float   mask_thresh;         /* 0.25 (vit_model.py:339) */
+    int32_t topk;                /* 16 (vit_model.py:377) */
+    float   ln_eps;              /* 1e-6 (vit_model.py:244) */
+} vtc_config;
+
+/* fp32 parameters, state_dict names in comments.  Device pointers. */
+typedef struct vtc_layer_weights {
+    const float* norm1_w; const float* norm1_b;   /* blocks.i.norm1.{weight,bias}      [D] */
+    const float* qkv_w;   const float* qkv_b;     /* blocks.i.attn.qkv.{weight,bias}   [3D,D],[3D] */
+    const float* proj_w;  const float* proj_b;    /* blocks.i.attn.proj.{weight,bias}  [D,D],[D] */
+    const float* norm2_w; const float* norm2_b;   /* blocks.i.norm2.{weight,bias}      [D] */
+    const float* fc1_w;   const float* fc1_b;     /* blocks.i.mlp.fc1.{weight,bias}    [4D,D],[4D] */
+    const float* fc2_w;   const float* fc2_b;     /* blocks.i.mlp.fc2.{weight,bias}    [D,4D],[D] */
+} vtc_layer_weights;
+
+typedef struct vtc_weights {
+    const float* cls_token;                        /* cls_token  [1,1,D] */
+    const float* pos_embed;                        /* pos_embed  [1,N,D] */
+    const float* patch_w; const float* patch_b;    /* patch_embed.proj.{weight,bias} [D,in_c,p,p],[D] */
+    const float* norm_w;  const float* norm_b;     /* norm.{weight,bias} [D] */
+    const float* pre_w;   const float* pre_b;      /* pre_logits.fc.{weight,bias} [R,D],[R] or NULL */
+    const float* head_w;  const float* head_b;     /* head.{weight,bias}  [C,R or D],[C] */
+    const float* head1_w; const float* head1_b;    /* head1.{weight,bias} [C,R or D],[C] */
+    const vtc_layer_weights* layers;               /* host array of `num_layers` entries */
+    int32_t num_layers;
+} vtc_weights;
+
+/* forward flags */
+enum {
+    VTC_FWD_MASK_NORM_IMAGE = 1 << 0, /* normalise the CLS map per image instead of the reference's batch-global
+                                         max (vit_model.py:335,372) */
+    VTC_FWD_FP32_SPLIT      = 1 << 1  /* reserved: split-bf16 (3x) GEMMs for the 1e-4 "fp32 mode" */
+};
+
+/* Optional teacher forcing of the discrete decisions (tests only; NULL = compute them). */
+typedef struct vtc_forcing {
+    const uint8_t* bg;       /* [L,B,P] background vectors; used for layers with bg_layer_mask bit set */
+    uint32_t bg_layer_mask;  /* bit l set -> layer l's bg vector is taken from `bg` */
+    const int32_t* topk_idx; /* [B,K] or NULL */
+} vtc_forcing;
+
+/* Forward outputs.  NULL = not requested (except logits / hwp_logits / hwp_tokens which are required). */
+typedef struct vtc_outputs {
+    float*   logits;      /* [B,C]       head(norm(x)[:,0])                       vit_model.py:402-422 */
+    float*   hwp_logits;  /* [B,C]       head1(mean of the K high-weight tokens)  vit_model.py:391-393 */
+    float*   hwp_tokens;  /* [B,K,D]     ori_allbs_hw_p_ts                        vit_model.py:381-390 */
+    int32_t* topk_idx;    /* [B,K]       patch indices, descending attention      vit_model.py:377 */
+    float*   tokens;      /* [Lt,B,N,D]  block outputs X_l (attn_matrix)          vit_model.py:324 */
+    int32_t  tokens_layers; /* Lt: how many trailing layers to keep: 1 (last only) .. L */
+    float*   cls_rows;    /* [L,B,H,N]   P_l[:,:,0,:]  (CLS query row per head)   vit_model.py:329-334 */
+    float*   attn;        /* [La,B,H,N,N] full softmax P_l (attn_weights)         vit_model.py:126-128,323 */
+    int32_t  attn_layers; /* La trailing layers kept in `attn` (0 = none) */
+    float*   attn_mean;   /* [L,B,N,N]   head-mean P_l (what rollout consumes)    predict.py:189-190 */
+    uint8_t* bg;          /* [L,B,P]     background vector built after layer l (0 for l < mask_from) :337-342 */
+    float*   cls_map;     /* [L,B,P]     renormalised head-mean CLS row (before /max)  vit_model.py:329-334 */
+} vtc_outputs;
+
+typedef struct vtc_model vtc_model;   /* host-side handle: config, packed-weight pointers, TMA descriptors */
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+VTC_API int vtc_version(void);
+VTC_API const char* vtc_last_error(void);
+/* VTC_OK iff the current CUDA device is sm_100 class (compute capability 10.x). */
+VTC_API int vtc_check_device(void);
+
+/* replaces VisionTransformer.__init__ shape bookkeeping (vit_model.py:215-301) */
+VTC_API int vtc_model_create(const vtc_config* cfg, vtc_model** out);
+VTC_API int vtc_model_destroy(vtc_model* m);
+/* bytes of the packed (bf16, K-major) GEMM weight buffer the caller must provide */
+VTC_API size_t vtc_model_packed_bytes(const vtc_model* m);
+/* fp32 state_dict tensors -> packed bf16 buffer (enqueued on stream); the fp32 vectors (biases, LayerNorm,
+ * cls_token, pos_embed, heads) are referenced in place and must outlive the handle's use.
+ * Replaces nothing in the reference (it feeds fp32 nn.Linear weights to ATen); call again after any
+ * in-place weight update (load_state_dict). */
+VTC_API int vtc_model_pack_weights(vtc_model* m, const vtc_weights* w, void* packed, size_t packed_bytes, void* stream);
+/* workspace bytes for a batch of B images (depends on which outputs are requested: pass the same struct) */
+VTC_API size_t vtc_workspace_bytes(const vtc_model* m, int32_t batch, const vtc_outputs* outs);
+
+/* ---- the fused path ---------------------------------------------------------------------------
+ * VisionTransformer.forward (vit_model.py:303-424): patch embed, L pre-norm blocks with the layer>4
+ * background mask, high-weight-patch head, final norm + head.  x: [B,in_c,S,S] fp32 NCHW. */
+VTC_API int vtc_forward(vtc_model* m, const float* x, int32_t batch, const vtc_outputs* outs, const vtc_forcing* forcing,
+                void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* ---- per-kernel entry points (unit parity; the model forward is built from these) -------------- */
+enum { VTC_EPI_BIAS = 0, VTC_EPI_BIAS_GELU = 1, VTC_EPI_BIAS_RESIDUAL = 2, VTC_EPI_PATCH_EMBED = 3 };
+/* out[M,Nout] = A[M,K] (bf16) . W[Nout,K]^T (bf16) + bias (+ epilogue).  nn.Linear: vit_model.py:110,138,158,161;
+ * conv-as-GEMM: vit_model.py:64,76.
+ *   VTC_EPI_BIAS / _GELU : out is bf16 [M,Nout]
+ *   VTC_EPI_BIAS_RESIDUAL: out is fp32 [M,Nout] = residual + A.W^T + bias (out may alias residual)
+ *   VTC_EPI_PATCH_EMBED  : A rows are (b,p) patches; out is the fp32 token buffer [B,tokens,Nout], row b*tokens+1+p,
+ *                          plus pos_embed[1+p] (pos = [tokens,Nout] fp32); vit_model.py:79,308-314
+ * Requires K % 64 == 0, Nout % 256 == 0. */
+VTC_API int vtc_gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos,
+                  void* out, int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream);
+
+/* fp32 -> bf16 (weight packing, also used by tests) */
+VTC_API int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream);
+/* NCHW fp32 image -> bf16 patch matrix [B*P, in_c*p*p] (k = c*p*p + kh*p + kw), the im2col of the k=s=p conv
+ * (vit_model.py:64,76-79) */
+VTC_API int vtc_patchify(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream);
+/* tokens[b,0,:] = cls_token + pos_embed[0] (vit_model.py:308-314) */
+VTC_API int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int32_t batch, int32_t n_tokens,
+                       int32_t dim, void* stream);
+/* nn.LayerNorm over the last dim (vit_model.py:193,198,402): x fp32 [rows,D] -> y bf16 [rows,D] */
+VTC_API int vtc_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim,
+                       float eps, void* stream);
+/* Attention core (vit_model.py:113-137): qkv bf16 [B,N,3,H,64] -> out bf16 [B,N,H*64];
+ * key_bias [B,N] additive logit bias per key (0 / -100, pre-multiplied by nothing) or NULL (vit_model.py:118-124);
+ * cls_rows [B,H,N] fp32 (P[b,h,0,:]) or NULL; attn [B,H,N,N] fp32 full P or NULL. */
+VTC_API int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
+                  int32_t n_tokens, int32_t heads, float scale, void* stream);
+/* head mean of P: attn [B,H,N,N] -> mean [B,N,N] (predict.py:189-190) */
+VTC_API int vtc_head_mean(const float* attn, float* mean, int32_t batch, int32_t heads, int32_t n_tokens, void* stream);
+/* CLS-row statistic (vit_model.py:329-335): cls_rows [B,H,N] -> cls_map [B,P] = ((mean_h + e0)/rowsum)[1:], and
+ * gmax[0] = max(gmax[0], max cls_map) (caller zeroes gmax).  */
+VTC_API int vtc_cls_stat(const float* cls_rows, float* cls_map, float* gmax, int32_t batch, int32_t heads, int32_t n_tokens,
+                 void* stream);
+/* background mask (vit_model.py:335-361): bg[b,p] = cls_map[b,p]/max < thresh (max = gmax[0], or the row max when
+ * per_image); key_bias[b,0] = 0, key_bias[b,1+p] = -100*bg.  forced_bg [B,P] overrides the decision when non-NULL. */
+VTC_API int vtc_cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image,
+                 uint8_t* bg, float* key_bias, int32_t batch, int32_t n_tokens, void* stream);
+/* high-weight-patch head + final norm + head (vit_model.py:374-422). tokens [B,N,D] fp32 (block-L output). */
+VTC_API int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const int32_t* forced_topk,
+                   float* logits, float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int32_t batch, void* stream);
+
+/* ---- CAM / rollout / pseudo-label post-processing ----------------------------------------------
+ * attention rollout (predict.py:215-232): attn_mean [L,B,N,N] -> row [B,P] = (e0^T A_{L-1} ... A_0)[1:] with
+ * A_l = (mean_l + I)/rowsum, evaluated as a reverse vector-matrix chain. */
+VTC_API int vtc_rollout(const float* attn_mean, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream);
+/* per-layer CLS maps / bg map (predict.py:261-266, validate.py:225-237): cls_rows [L,B,H,N] ->
+ * maps [B,P]: mean over layers [first,last) and heads, + identity on the CLS entry, / rowsum, patches, / max. */
+VTC_API int vtc_cls_layer_map(const float* cls_rows, float* map, int32_t layers, int32_t first, int32_t last, int32_t batch,
+                      int32_t heads, int32_t n_tokens, void* stream);
+/* classic CAM (t.py:55-75, utils.py:80-88, vit_model.py:297): tokens [B,N,D] fp32, w [C,D] ->
+ * cam [B,C,g,g] = minmax(relu(F.w^T)) per (b,c) map, eps added to the max. */
+VTC_API int vtc_cam_project(const float* tokens, const float* w, float* cam, int32_t batch, int32_t n_tokens, int32_t dim,
+                    int32_t classes, int32_t relu, float eps, void* stream);
+/* row-wise divide by the row max: maps [rows,P] in place (predict.py:247,266) */
+VTC_API int vtc_normalize_max(float* maps, int32_t rows, int32_t p, void* stream);
+/* bilinear, align_corners=False (validate.py:177,239; cv2.resize predict.py:247): in [n,g,g] -> out [n,H,W] fp32 */
+VTC_API int vtc_upsample_bilinear(const float* in, float* out, int32_t n, int32_t g, int32_t out_h, int32_t out_w, void* stream);
+/* same, then *255 and truncate to uint8 (predict.py:266-269) */
+VTC_API int vtc_upsample_bilinear_u8(const float* in, uint8_t* out, int32_t n, int32_t g, int32_t out_h, int32_t out_w,
+                             void* stream);
+/* CAM pseudo label (utils.py:100-108 convention): label[b,y,x] = argmax([bg_thresh, up(cam[b,c]) for labelled c]),
+ * 0 = background, c+1 otherwise.  cam [B,C,g,g], labels [B,C] u8 -> out [B,H,W] u8.  Fused upsample + argmax. */
+VTC_API int vtc_cam_label(const float* cam, const uint8_t* labels, float bg_thresh, uint8_t* out, int32_t batch,
+                  int32_t classes, int32_t g, int32_t out_h, int32_t out_w, void* stream);
+/* high-weight-patch class vote + cosine maps (validate.py:132-175): per image
+ *   patch_to_cls[k] = mode{argmax_c W1'[c,d] : argmax_k ori[k,d] = k}, W1' rows of classes with sigmoid(hwp)<sig set to -10
+ *   cos[k,p] = <ori[k]/|ori[k]|, F[p]/|F[p]|>
+ * outputs patch_to_cls [B,K] int32 (class 0..C-1, or -1 when the patch owns no feature) and cos [B,K,g,g]. */
+VTC_API int vtc_hwp_cos_vote(const float* hwp_logits, const float* head1_w, const float* hwp_tokens, const float* tokens,
+                     float sig_thresh, int32_t* patch_to_cls, float* cos, int32_t batch, int32_t n_tokens, int32_t dim,
+                     int32_t classes, int32_t k, void* stream);
+/* validate.py:177-258 fused: seg[b,y,x] = (patch_to_cls[argmax_k up(cos[b,k])] + 1) * [max_k >= cos_thresh] *
+ * [up(bg_map[b]) >= bg_thresh]; patches voting -1 count as background. out [B,H,W] u8. */
+VTC_API int vtc_hwp_seg(const float* cos, const int32_t* patch_to_cls, const float* bg_map, float cos_thresh, float bg_thresh,
+                uint8_t* out, int32_t batch, int32_t k, int32_t g, int32_t out_h, int32_t out_w, void* stream);
+/* ConfusionMatrix.update (utils.py:35-45): mat [n,n] int64 += bincount(n*gt + pred) over gt in [0,n). */
+VTC_API int vtc_confmat_update(const uint8_t* gt, const uint8_t* pred, size_t count, int32_t n, int64_t* mat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTC_H_ */

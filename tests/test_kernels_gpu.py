@@ -1,0 +1,271 @@
+"""Per-kernel parity on the B200: each libvtc kernel (called through the C-ABI) against a plain fp32 torch expression
+of the same op on the same seeded inputs.  Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib_built):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from vision_transformer_cam_b200 import _lib
+    _lib.load()
+    _lib.check(_lib.load().vtc_check_device(), "vtc_check_device")
+    return torch.device("cuda:0")
+
+
+def _rand(shape, seed, dev, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 128), (300, 768, 768), (1000, 2304, 768),
+                                   (197, 3072, 768), (394, 768, 3072), (50432, 768, 768)])
+def test_gemm_bias(dev, M, N, K):
+    from vision_transformer_cam_b200 import ops, _lib
+    a = _rand((M, K), 1, dev).bfloat16()
+    w = _rand((N, K), 2, dev, 0.05).bfloat16()
+    bias = _rand((N,), 3, dev)
+    out = ops.gemm_bf16(a, w, bias, _lib.EPI_BIAS)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    # bf16 output rounding (2^-9 relative) + fp32 accumulation order: 1e-2 of the output scale
+    assert relerr(out.float(), ref) < 1e-2, relerr(out.float(), ref)
+    assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 4e-3
+
+
+def test_gemm_gelu(dev):
+    from vision_transformer_cam_b200 import ops, _lib
+    M, N, K = 777, 3072, 768
+    a = _rand((M, K), 4, dev).bfloat16()
+    w = _rand((N, K), 5, dev, 0.05).bfloat16()
+    bias = _rand((N,), 6, dev)
+    out = ops.gemm_bf16(a, w, bias, _lib.EPI_BIAS_GELU)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    assert relerr(out.float(), ref) < 1e-2
+    # the erf approximation itself (A&S 7.1.26) must be far below bf16 resolution: check where |x| is small
+    assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 4e-3
+
+
+def test_gemm_residual_inplace(dev):
+    from vision_transformer_cam_b200 import ops, _lib
+    M, N, K = 1000, 768, 3072
+    a = _rand((M, K), 7, dev).bfloat16()
+    w = _rand((N, K), 8, dev, 0.02).bfloat16()
+    bias = _rand((N,), 9, dev)
+    res = _rand((M, N), 10, dev)
+    ref = res + a.float() @ w.float().t() + bias
+    buf = res.clone()
+    out = ops.gemm_bf16(a, w, bias, _lib.EPI_BIAS_RESIDUAL, residual=buf, out=buf)
+    assert out.data_ptr() == buf.data_ptr()
+    # fp32 output: only accumulation order differs -> 1e-5 of scale
+    assert relerr(out, ref) < 2e-5, relerr(out, ref)
+    out2 = ops.gemm_bf16(a, w, bias, _lib.EPI_BIAS_RESIDUAL, residual=res)
+    assert relerr(out2, ref) < 2e-5
+
+
+def test_gemm_patch_embed(dev):
+    from vision_transformer_cam_b200 import ops, _lib
+    B, P, D, K = 3, 196, 768, 768
+    N = P + 1
+    a = _rand((B * P, K), 11, dev).bfloat16()
+    w = _rand((D, K), 12, dev, 0.05).bfloat16()
+    bias = _rand((D,), 13, dev)
+    pos = _rand((N, D), 14, dev)
+    tokens = torch.full((B, N, D), 123.0, device=dev)
+    ops.gemm_bf16(a, w, bias, _lib.EPI_PATCH_EMBED, pos=pos, out=tokens, tokens=N)
+    ref = (a.float() @ w.float().t() + bias).view(B, P, D) + pos[1:]
+    assert relerr(tokens[:, 1:], ref) < 2e-5
+    assert bool((tokens[:, 0] == 123.0).all())          # CLS rows untouched
+
+
+def test_gemm_rejects_bad_shapes(dev):
+    from vision_transformer_cam_b200 import ops, _lib
+    a = torch.zeros((128, 100), device=dev, dtype=torch.bfloat16)
+    w = torch.zeros((256, 100), device=dev, dtype=torch.bfloat16)
+    with pytest.raises(_lib.VtcError):
+        ops.gemm_bf16(a, w, torch.zeros(256, device=dev))
+
+
+# ---------------------------------------------------------------------------------------- elementwise
+def test_cast_patchify_cls_rows(dev):
+    from vision_transformer_cam_b200 import ops
+    x = _rand((2, 3, 224, 224), 20, dev)
+    p = ops.patchify(x, 16)
+    ref = F.unfold(x, kernel_size=16, stride=16).transpose(1, 2).reshape(2 * 196, 768)   # k = c*256 + kh*16 + kw
+    assert torch.equal(p, ref.bfloat16())
+    v = _rand((1000003,), 21, dev)
+    assert torch.equal(ops.cast_bf16(v), v.bfloat16())
+    tokens = torch.zeros((2, 197, 768), device=dev)
+    cls, pos = _rand((1, 1, 768), 22, dev), _rand((1, 197, 768), 23, dev)
+    ops.cls_token_rows(cls, pos, tokens)
+    assert torch.equal(tokens[:, 0], (cls[0, 0] + pos[0, 0]).expand(2, -1))
+    assert float(tokens[:, 1:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D,rows", [(768, 1), (768, 50432), (1024, 577 * 3), (256, 100)])
+def test_layernorm(dev, D, rows):
+    from vision_transformer_cam_b200 import ops
+    x = _rand((rows, D), 30, dev, 3.0) + 0.5
+    g, b = _rand((D,), 31, dev), _rand((D,), 32, dev)
+    y = ops.layernorm_bf16(x, g, b, 1e-6)
+    ref = F.layer_norm(x, (D,), g, b, 1e-6)
+    # fp32 statistics; only the final bf16 rounding differs: 2^-8 relative per element
+    assert float((y.float() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max()) + 1e-6
+    assert float((y.float() - ref.bfloat16().float()).abs().mean()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, H, scale, kb):
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    q, k, v = qkv.float().view(B, N, 3, H, D // H).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) * scale
+    if kb is not None:
+        s = s + kb[:, None, None, :]
+    p = s.softmax(-1)
+    o = (p @ v).transpose(1, 2).reshape(B, N, D)
+    return o, p
+
+
+@pytest.mark.parametrize("B,N,H,masked", [(2, 197, 12, False), (3, 197, 12, True), (1, 50, 12, True), (2, 256, 4, False), (5, 129, 2, True)])
+def test_attention(dev, B, N, H, masked):
+    from vision_transformer_cam_b200 import ops
+    qkv = _rand((B, N, 3 * H * 64), 40, dev, 1.5).bfloat16()
+    kb = None
+    if masked:
+        g = torch.Generator().manual_seed(41)
+        kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+        kb[:, 0] = 0
+        kb = kb.to(dev)
+    out, cls, attn = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=True)
+    ref_o, ref_p = _attn_ref(qkv, H, 0.125, kb)
+    # P is fp32 softmax of an fp32-accumulated bf16 product: exp2/ex2.approx vs exp -> 2e-6 absolute on probabilities
+    assert float((attn - ref_p).abs().max()) < 5e-6, float((attn - ref_p).abs().max())
+    assert float((cls - ref_p[:, :, 0, :]).abs().max()) < 5e-6
+    assert float((attn.sum(-1) - 1).abs().max()) < 1e-5
+    # O: P rounded to bf16 before the second MMA + bf16 output: 1e-2 of scale
+    assert relerr(out.float(), ref_o) < 1e-2, relerr(out.float(), ref_o)
+    out2, cls2, _ = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
+    assert torch.equal(out2, out) and torch.equal(cls2, cls)
+    hm = ops.head_mean(attn)
+    assert float((hm - attn.mean(1)).abs().max()) < 1e-6
+
+
+def test_attention_too_long_is_an_error(dev):
+    from vision_transformer_cam_b200 import ops, _lib
+    qkv = torch.zeros((1, 577, 3 * 64), device=dev, dtype=torch.bfloat16)
+    with pytest.raises(_lib.VtcError):
+        ops.attention(qkv, 1, 0.125)
+
+
+# -------------------------------------------------------------------------------------------- CLS ops
+def test_cls_stat_and_mask(dev):
+    from vision_transformer_cam_b200 import ops
+    from oracle.vit_forward import cls_row_stat
+    B, H, N = 5, 12, 197
+    P = torch.rand((B, H, N, N), generator=torch.Generator().manual_seed(50)).softmax(-1)
+    P[:, :, 0, 5:40] *= 8
+    P = P / P.sum(-1, keepdim=True)
+    ref = cls_row_stat(P)                                  # vit_model.py:329-334 on the full matrix
+    cmap, gmax = ops.cls_stat(P[:, :, 0, :].contiguous().to(dev))
+    assert float((cmap.cpu() - ref).abs().max()) < 1e-7
+    assert abs(float(gmax) - float(ref.max())) < 1e-7
+    bg, kb = ops.cls_mask(cmap, gmax, 0.25, per_image=False)
+    ref_bg = torch.lt(ref / ref.max(), 0.25)
+    assert float((bg.cpu().bool() != ref_bg).float().mean()) < 1e-3      # ties at the threshold only
+    assert torch.equal(kb[:, 1:].cpu(), bg.cpu().float() * -100.0) and float(kb[:, 0].abs().max()) == 0
+    bg_i, _ = ops.cls_mask(cmap, gmax, 0.25, per_image=True)
+    ref_i = torch.lt(ref / ref.max(dim=1, keepdim=True).values, 0.25)
+    assert float((bg_i.cpu().bool() != ref_i).float().mean()) < 1e-3
+    forced = (torch.arange(B * (N - 1)).reshape(B, N - 1) % 3 == 0).to(torch.uint8).to(dev)
+    bg_f, kb_f = ops.cls_mask(cmap, gmax, 0.25, forced_bg=forced)
+    assert torch.equal(bg_f, forced)
+
+
+# ------------------------------------------------------------------------------------------- postproc
+def test_rollout_and_layer_maps(dev):
+    from vision_transformer_cam_b200 import ops
+    from oracle import postproc as PP
+    L, B, H, N = 12, 3, 12, 197
+    g = torch.Generator().manual_seed(60)
+    P_list = [(torch.randn((B, H, N, N), generator=g) * 2).softmax(-1) for _ in range(L)]
+    mean = PP.head_mean(P_list)
+    row = ops.rollout(mean.to(dev))
+    ref = PP.rollout_dense(P_list)
+    assert relerr(row.cpu(), ref) < 1e-5
+    cls_rows = torch.stack([p[:, :, 0, :] for p in P_list]).contiguous().to(dev)
+    bgm = ops.cls_layer_map(cls_rows, 5, L)
+    assert float((bgm.cpu() - PP.bg_map(cls_rows.cpu())).abs().max()) < 1e-6
+    lm = torch.stack([ops.cls_layer_map(cls_rows, l, l + 1) for l in range(L)])
+    assert float((lm.cpu().view(L, B, 14, 14) - PP.layer_maps(P_list)).abs().max()) < 1e-6
+
+
+def test_cam_project_upsample_label(dev):
+    from vision_transformer_cam_b200 import ops
+    from oracle import postproc as PP
+    B, N, D, Ccls = 4, 197, 768, 20
+    X = _rand((B, N, D), 70, dev)
+    W = _rand((Ccls, D), 71, dev, 0.1)
+    cam = ops.cam_project(X, W)
+    ref = PP.classic_cam(X.cpu(), W.cpu())
+    assert float((cam.cpu() - ref).abs().max()) < 1e-5
+    for hw in [(224, 224), (375, 500), (333, 401)]:
+        up = ops.upsample_bilinear(cam, hw)
+        ref_up = F.interpolate(ref, size=hw, mode="bilinear", align_corners=False)
+        assert float((up.cpu() - ref_up).abs().max()) < 1e-5
+        u8 = ops.upsample_bilinear(cam, hw, as_u8=True)
+        ref_u8 = (ref_up * 255).to(torch.uint8)
+        assert int((u8.cpu().int() - ref_u8.int()).abs().max()) <= 1
+        labels = (torch.rand((B, Ccls), generator=torch.Generator().manual_seed(72)) < 0.15)
+        labels[0] = False
+        lab = ops.cam_label(cam, labels.to(dev), hw, 0.25)
+        ref_lab = PP.cam_pseudo_label(ref, labels.float(), hw, 0.25)
+        assert float((lab.cpu() == ref_lab).float().mean()) >= 0.9995      # argmax ties / 1e-6 interpolation noise
+    m = cam.clone().view(B * Ccls, 196) + 0.1
+    ops.normalize_max_(m)
+    assert float((m.max(dim=1).values - 1).abs().max()) == 0.0
+
+
+def test_hwp_vote_seg_confmat(dev):
+    from vision_transformer_cam_b200 import ops
+    from oracle import postproc as PP
+    import numpy as np
+    B, N, D, Ccls, K = 3, 197, 768, 20, 16
+    X = _rand((B, N, D), 80, dev)
+    W1 = _rand((Ccls, D), 81, dev, 0.3)
+    idx = torch.stack([torch.randperm(196, generator=torch.Generator().manual_seed(82 + b))[:K] for b in range(B)])
+    ori = torch.stack([X[b, 1 + idx[b].to(dev)] for b in range(B)]).contiguous()
+    hwp = _rand((B, Ccls), 83, dev, 3.0)
+    cls_rows = torch.rand((12, B, 12, N), generator=torch.Generator().manual_seed(84)).to(dev)
+    cls_rows = cls_rows / cls_rows.sum(-1, keepdim=True)
+    p2c, cos = ops.hwp_cos_vote(hwp, W1, ori, X)
+    for b in range(B):
+        ref_p2c = PP.hwp_patch_classes(hwp[b].cpu(), W1.cpu(), ori[b].cpu())
+        mine = p2c[b].cpu().long()
+        ok = (mine == ref_p2c) | ((mine < 0) & (ref_p2c >= 21))
+        assert bool(ok.all()), (mine, ref_p2c)
+        assert float((cos[b].cpu() - PP.hwp_cos_maps(X[b].cpu(), ori[b].cpu())).abs().max()) < 1e-5
+    bgm = ops.cls_layer_map(cls_rows, 5, 12)
+    hw = (375, 500)
+    seg = ops.hwp_seg(cos, p2c, bgm, hw)
+    ref_seg = PP.hwp_pseudo_seg(hwp.cpu(), W1.cpu(), ori.cpu(), X.cpu(), cls_rows.cpu(), hw, clamp_sentinel=True)
+    assert float((seg.cpu() == ref_seg).float().mean()) >= 0.9995
+    gt = torch.randint(0, 22, (B, *hw), generator=torch.Generator().manual_seed(85)).to(torch.uint8)
+    gt[gt == 21] = 255
+    mat = torch.zeros((21, 21), dtype=torch.int64, device=dev)
+    ops.confmat_update(mat, gt.to(dev), seg)
+    ref_mat = PP.confmat_update(None, gt.numpy(), seg.cpu().numpy())
+    assert np.array_equal(mat.cpu().numpy(), ref_mat)            # integer counters: bit exact
+    ops.confmat_update(mat, gt.to(dev), seg)
+    assert np.array_equal(mat.cpu().numpy(), 2 * ref_mat)

@@ -1,0 +1,132 @@
+"""CAM / attention-rollout / pseudo-label extraction: the math that the reference runs inline in predict.py and
+validate.py after the forward, as callable functions over the libvtc kernels.
+
+The reference has no API for this layer (it is script code), so this module defines one; every function cites the
+reference lines whose result it reproduces.  Inputs are `CamForward` fields (vit_model.forward_cam) or the entries of
+the reference 6-tuple; everything stays on the GPU."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .vit_model import CamForward
+
+
+# ---- attention rollout (predict.py:189-247) --------------------------------------------------------------------
+def head_mean(attn_weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    """predict.py:189-190 for a batch: list of L [B,H,N,N] -> [L,B,N,N]."""
+    return torch.stack([ops.head_mean(p.contiguous()) for p in attn_weights])
+
+
+def rollout_row(attn_mean: torch.Tensor) -> torch.Tensor:
+    """predict.py:215-232: CLS row of prod_l (mean_l + I)/rowsum, patch columns, un-normalised.  [L,B,N,N] -> [B,P]."""
+    return ops.rollout(attn_mean.contiguous())
+
+
+def rollout_map(attn_mean: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """predict.py:229-247: rollout row / max, g x g, bilinear (cv2.resize == align_corners=False) to (H,W)."""
+    row = ops.normalize_max_(rollout_row(attn_mean))
+    B, P = row.shape
+    g = int(round(P ** 0.5))
+    m = row.view(B, g, g)
+    return m if out_hw is None else ops.upsample_bilinear(m, out_hw)
+
+
+def layer_maps(cls_rows: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None, as_u8: bool = False) -> torch.Tensor:
+    """predict.py:261-269: per layer (mean_h P + I)/rowsum, CLS row, / max -> [L,B,g,g] (or resized, optionally *255 u8)."""
+    L, B, H, N = cls_rows.shape
+    g = int(round((N - 1) ** 0.5))
+    m = torch.stack([ops.cls_layer_map(cls_rows, l, l + 1) for l in range(L)]).view(L, B, g, g)
+    if out_hw is None:
+        return m
+    return ops.upsample_bilinear(m, out_hw, as_u8=as_u8)
+
+
+# ---- classic CAM (t.py:55-75, utils.py:80-129) -------------------------------------------------------------------
+def classic_cam(tokens_last: torch.Tensor, head1_weight: torch.Tensor, relu: bool = True, eps: float = 1e-5) -> torch.Tensor:
+    """cam[b,c] = minmax(relu(F_b . W_c)) on the block-L patch tokens -> [B,C,g,g] in [0,1]."""
+    return ops.cam_project(tokens_last.contiguous(), head1_weight.contiguous(), relu, eps)
+
+
+def cam_pseudo_label(cam: torch.Tensor, labels: torch.Tensor, out_hw: Tuple[int, int], bg_thresh: float = 0.25) -> torch.Tensor:
+    """utils.py:100-108 convention: upsample, keep the image's classes, argmax against a constant background score.
+    Fused upsample+argmax: writes 1 byte per pixel.  -> uint8 [B,H,W] (0 = background, c+1)."""
+    return ops.cam_label(cam.contiguous(), labels, out_hw, bg_thresh)
+
+
+def cam_upsampled(cam: torch.Tensor, out_hw: Tuple[int, int], as_u8: bool = False) -> torch.Tensor:
+    """Full-resolution maps on request (utils.py:86,113: uint8(255*cam) resized)."""
+    return ops.upsample_bilinear(cam.contiguous(), out_hw, as_u8=as_u8)
+
+
+# ---- validate.py:132-258 pseudo segmentation ---------------------------------------------------------------------
+def bg_map(cls_rows: torch.Tensor, first_layer: int = 5) -> torch.Tensor:
+    """validate.py:225-237: mean CLS attention over layers[first_layer:] and heads, + identity, renormalised, / max."""
+    return ops.cls_layer_map(cls_rows, first_layer, cls_rows.shape[0])
+
+
+def hwp_pseudo_seg(fwd: CamForward, head1_weight: torch.Tensor, out_hw: Tuple[int, int], sig_thresh: float = 0.9,
+                   cos_thresh: float = 0.5, bg_thresh: float = 0.05, return_parts: bool = False):
+    """validate.py:132-258 for a batch -> uint8 [B,H,W].  'Patch owns no feature' (the reference's sentinel >= 21, which
+    overflows its confusion matrix) is mapped to background."""
+    p2c, cos = ops.hwp_cos_vote(fwd.hwp_logits, head1_weight.contiguous(), fwd.hwp_tokens, fwd.tokens_last.contiguous(), sig_thresh)
+    bgm = bg_map(fwd.cls_rows)
+    seg = ops.hwp_seg(cos, p2c, bgm, out_hw, cos_thresh, bg_thresh)
+    return (seg, p2c, bgm) if return_parts else seg
+
+
+# ---- metrics (utils.py:30-77, 248-262) -----------------------------------------------------------------------------
+class ConfusionMatrix:
+    """utils.py:30-77 with the counters on the GPU (int64 [n,n], n = num_classes + 1)."""
+
+    def __init__(self, num_classes: int, device="cuda"):
+        self.num_classes = num_classes
+        self.n = num_classes + 1
+        self.mat = torch.zeros((self.n, self.n), dtype=torch.int64, device=device)
+
+    def update(self, gt: torch.Tensor, pred: torch.Tensor) -> None:
+        """gt / pred: uint8 label maps of equal size; gt >= n (255) is ignored (utils.py:42)."""
+        ops.confmat_update(self.mat, gt.to(torch.uint8).contiguous().view(-1), pred.to(torch.uint8).contiguous().view(-1))
+
+    def reset(self) -> None:
+        self.mat.zero_()
+
+    def compute(self):
+        h = self.mat.float()
+        acc_global = torch.diag(h).sum() / h.sum()
+        acc = torch.diag(h) / h.sum(1)
+        iu = torch.diag(h) / (h.sum(1) + h.sum(0) - torch.diag(h))
+        return acc_global, acc, iu
+
+    def reduce_from_all_processes(self) -> None:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(self.mat)
+
+    def __str__(self):
+        acc_global, acc, iu = self.compute()
+        return ("global correct: {:.1f}\naverage row correct: {}\nIoU: {}\nmean IoU: {:.1f}").format(
+            acc_global.item() * 100, ["{:.1f}".format(i) for i in (acc * 100).tolist()],
+            ["{:.1f}".format(i) for i in (iu * 100).tolist()], iu.nanmean().item() * 100)
+
+
+def average_precision(y_true: np.ndarray, y_score: np.ndarray) -> float:
+    """sklearn.metrics.average_precision_score for one binary row (called per image by utils.py:258): host-side, 20 values."""
+    y_true = np.asarray(y_true, dtype=np.float64)
+    y_score = np.asarray(y_score, dtype=np.float64)
+    order = np.argsort(-y_score, kind="mergesort")
+    y_true, y_score = y_true[order], y_score[order]
+    idx = np.r_[np.where(np.diff(y_score))[0], y_true.size - 1]
+    tps = np.cumsum(y_true)[idx]
+    precision = tps / (1.0 + idx)
+    recall = tps / tps[-1]
+    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+
+def compute_mAP(labels: torch.Tensor, outputs: torch.Tensor) -> List[float]:
+    """utils.py:248-262: per-image AP over the class scores, for images with at least one positive label."""
+    y_true, y_pred = labels.detach().cpu().numpy(), outputs.detach().cpu().numpy()
+    return [average_precision(y_true[i], y_pred[i]) for i in range(y_true.shape[0]) if y_true[i].sum() > 0]

@@ -1,0 +1,323 @@
+// Fused multi-head attention for the ViT blocks (vit_model.py:113-137): per (image, head)
+//   S = Q K^T * scale (+ per-key bias of the layer>4 background mask), P = softmax(S), O = P V
+// with both contractions on tcgen05 (S and O accumulate in TMEM) and the softmax in fp32 registers.  Besides O the
+// kernel emits what the reference reads back from the full P tensor: the CLS query row P[b,h,0,:] (mask builder,
+// top-k head, per-layer maps) and, on request, the whole P (the 6-tuple's attn_weights / the rollout's head mean).
+//
+// Single-pass variant: all keys of one head fit one TMEM accumulator (N <= 256 tokens, head_dim 64).
+//   warps 0-3 : softmax + epilogue of query rows   0..127   (TMEM lane quarter = warp)
+//   warps 4-7 : softmax + epilogue of query rows 128..255
+//   warp  8   : TMEM allocation, TMA loads (Q,K,V as 256x64 boxes of the [B,N,3,H,64] qkv tensor; rows >= N are
+//               zero-filled by TMA), tcgen05.mma issue.
+// P is handed to the second MMA through shared memory as bf16 in the canonical K-major 128-byte-swizzle layout;
+// V is consumed MN-major straight from the TMA tile (no transpose anywhere).
+#include "common.cuh"
+#include "ops.h"
+#include "tma_host.h"
+
+namespace vtc {
+
+namespace attn {
+constexpr int HD = 64;
+constexpr int MAXN = 256;
+constexpr int TILE_BYTES = MAXN * HD * 2;            // 32 KB: one 256x64 bf16 box
+constexpr int P_KBLOCK_BYTES = 128 * 128;            // 128 rows x 64 keys bf16
+constexpr int P_TILE_BYTES = 4 * P_KBLOCK_BYTES;     // 256 keys
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = TILE_BYTES;
+constexpr int OFF_V = 2 * TILE_BYTES;
+constexpr int OFF_P = 3 * TILE_BYTES;
+constexpr int OFF_BAR = OFF_P + 2 * P_TILE_BYTES;    // 229376
+constexpr int OFF_KB = OFF_BAR + 128;                // key bias (log2 domain) [256] floats
+constexpr int OFF_CLS = OFF_KB + MAXN * 4;           // CLS row staging [256] floats
+constexpr int SMEM_BYTES = OFF_CLS + MAXN * 4;       // no alignment slack: the dynamic smem base is checked instead
+constexpr int THREADS = 288;
+static_assert(SMEM_BYTES <= 232448, "attention smem budget");
+}  // namespace attn
+
+struct AttnParams {
+    const float* key_bias;   // [B,N] or null
+    __nv_bfloat16* out;      // [B,N,H*64]
+    float* cls_rows;         // [B,H,N] or null
+    float* attn;             // [B,H,N,N] or null
+    int B, N, H;
+    float scale_log2;
+};
+
+__global__ void __launch_bounds__(attn::THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+    using namespace attn;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* bar_qk = bars + 0;
+    uint64_t* bar_v = bars + 1;
+    uint64_t* s_full = bars + 2;    // [2]
+    uint64_t* p_full = bars + 4;    // [2]
+    uint64_t* o_full = bars + 6;    // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    float* kb_s = reinterpret_cast<float*>(smem + OFF_KB);
+    float* cls_s = reinterpret_cast<float*>(smem + OFF_CLS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.H;
+    const int h = blockIdx.x - b * p.H;
+    const int N = p.N;
+    const int NP = (N + 15) & ~15;
+    const int ntiles = (N + 127) >> 7;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQKV);
+            mbar_init(bar_qk, 1);
+            mbar_init(bar_v, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&s_full[i], 1);
+                mbar_init(&p_full[i], 128);
+                mbar_init(&o_full[i], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+    } else {
+        // stage the key bias (log2 domain) while the control warp sets up
+        for (int j = threadIdx.x; j < MAXN; j += 256) {
+            float v = 0.f;
+            if (p.key_bias != nullptr && j < N) v = p.key_bias[static_cast<size_t>(b) * N + j] * 1.4426950408889634f;
+            kb_s[j] = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // ---- loads: coordinates (column, token, image) in the [B, N, 3*H*64] view
+            const int D = p.H * HD;
+            mbar_arrive_expect_tx(bar_qk, 2 * TILE_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(smem + OFF_Q)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(bar_qk)), "r"(h * HD), "r"(0), "r"(b)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(smem + OFF_K)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(bar_qk)), "r"(D + h * HD), "r"(0), "r"(b)
+                : "memory");
+            mbar_arrive_expect_tx(bar_v, TILE_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(smem + OFF_V)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(bar_v)), "r"(2 * D + h * HD), "r"(0), "r"(b)
+                : "memory");
+
+            // ---- S_i = Q_i K^T
+            mbar_wait(bar_qk, 0);
+            tc_fence_after();
+            const uint32_t idesc_s = make_idesc_bf16(128, NP, 0, 0);
+            const uint32_t q_addr = smem_u32(smem + OFF_Q);
+            const uint32_t k_addr = smem_u32(smem + OFF_K);
+            for (int i = 0; i < ntiles; ++i) {
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint64_t da = make_smem_desc_sw128(q_addr + i * (128 * 128) + k * 32, 1024, 16);
+                    const uint64_t db = make_smem_desc_sw128(k_addr + k * 32, 1024, 16);
+                    umma_bf16(tmem_base + i * 256, da, db, idesc_s, k != 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[i]);
+            }
+            // ---- O_i = P_i V   (O_i aliases the first 64 columns of S_i: S_i is dead once P_i is in smem)
+            mbar_wait(bar_v, 0);
+            const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
+            const uint32_t v_addr = smem_u32(smem + OFF_V);
+            const uint32_t p_addr = smem_u32(smem + OFF_P);
+            const int ksteps = NP / 16;
+            for (int i = 0; i < ntiles; ++i) {
+                mbar_wait(&p_full[i], 0);
+                tc_fence_after();
+                for (int j = 0; j < ksteps; ++j) {
+                    const uint64_t da = make_smem_desc_sw128(p_addr + i * P_TILE_BYTES + (j >> 2) * P_KBLOCK_BYTES + (j & 3) * 32, 1024, 16);
+                    const uint64_t db = make_smem_desc_sw128(v_addr + j * 2048, 1024, 1024);
+                    umma_bf16(tmem_base + i * 256, da, db, idesc_o, j != 0 ? 1u : 0u);
+                }
+                umma_commit(&o_full[i]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int tile = warp >> 2;
+        if (tile < ntiles) {
+            const int quarter = warp & 3;
+            const int r_local = quarter * 32 + lane;
+            const int row = tile * 128 + r_local;
+            const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * 256;
+            const int nchunks = (N + 31) >> 5;
+            const float sc = p.scale_log2;
+
+            mbar_wait(&s_full[tile], 0);
+            tc_fence_after();
+            // pass 1: row max
+            float m = -INFINITY;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_s + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = c * 32 + j;
+                    const float x = fmaf(__uint_as_float(r[j]), sc, kb_s[col]);
+                    if (col < N) m = fmaxf(m, x);
+                }
+            }
+            // pass 2: exponentials, row sum, bf16 P tile in smem (K-major, 128-byte swizzle)
+            float sum = 0.f;
+            uint8_t* p_tile = smem + OFF_P + tile * P_TILE_BYTES + r_local * 128;
+            const bool is_cls = (row == 0) && (p.cls_rows != nullptr);
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_s + c * 32, r);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int col = c * 32 + j;
+                    float e0 = exp2f(fmaf(__uint_as_float(r[j]), sc, kb_s[col]) - m);
+                    float e1 = exp2f(fmaf(__uint_as_float(r[j + 1]), sc, kb_s[col + 1]) - m);
+                    if (col >= N) e0 = 0.f;
+                    if (col + 1 >= N) e1 = 0.f;
+                    sum += e0 + e1;
+                    if (is_cls) { cls_s[col] = e0; cls_s[col + 1] = e1; }
+                    pk[j >> 1] = pack_bf16x2(e0, e1);
+                }
+                uint8_t* kblk = p_tile + (c >> 1) * P_KBLOCK_BYTES;
+                const int g0 = (c & 1) * 4;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int gs = (g0 + g) ^ (r_local & 7);
+                    st_u4(kblk + gs * 16, make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+                }
+            }
+            const float inv = 1.0f / sum;
+            if (p.attn != nullptr) {
+                // pass 3 (on request): normalised fp32 P row, re-read from TMEM before S is overwritten by O.
+                // The branch is CTA-uniform; only the stores are predicated (tcgen05.ld is .sync.aligned).
+                const bool wr = row < N;
+                float* dst = p.attn + ((static_cast<size_t>(b) * p.H + h) * N + (wr ? row : 0)) * N;
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_s + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        if (wr && col < N) dst[col] = exp2f(fmaf(__uint_as_float(r[j]), sc, kb_s[col]) - m) * inv;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[tile]);
+
+            if (warp == 0 && p.cls_rows != nullptr) {
+                const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
+                __syncwarp();
+                float* dst = p.cls_rows + (static_cast<size_t>(b) * p.H + h) * N;
+                for (int j = lane; j < N; j += 32) dst[j] = cls_s[j] * inv0;
+            }
+
+            // epilogue: O / rowsum -> bf16 [B,N,H*64]
+            mbar_wait(&o_full[tile], 0);
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32b_x32(t_s, o0);
+            tmem_ld_32x32b_x32(t_s + 32, o1);
+            tmem_ld_wait();
+            if (row < N) {
+                __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * (p.H * HD) + h * HD;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    st_u4(dst + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
+                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
+                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
+                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv)));
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    st_u4(dst + 32 + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv)));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_out, int batch, int n_tokens, int heads,
+              float scale, cudaStream_t stream) {
+    VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
+    VTC_REQUIRE(n_tokens <= attn::MAXN, VTC_ERR_SHAPE,
+                "attention: %d tokens > %d: the KV-blocked long-sequence kernel is not built yet", n_tokens, attn::MAXN);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int D = heads * attn::HD;
+    CUtensorMap tm;
+    uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)n_tokens, (uint64_t)batch};
+    uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)n_tokens * 3 * D * 2};
+    uint32_t box[3] = {attn::HD, attn::MAXN, 1};
+    rc = make_tmap_bf16(&tm, qkv, 3, dims, strides, box);
+    if (rc != VTC_OK) return rc;
+    static bool configured = false;
+    if (!configured) {
+        VTC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+        configured = true;
+    }
+    AttnParams p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale * 1.4426950408889634f};
+    attention_kernel<<<batch * heads, attn::THREADS, attn::SMEM_BYTES, stream>>>(tm, p);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- head mean of the full P (predict.py:189-190) -------------------------------------------------------
+__global__ void head_mean_kernel(const float* __restrict__ attn, float* __restrict__ mean, int H, size_t nn, size_t total) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const float inv = 1.0f / H;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t b = i / nn, e = i - b * nn;
+        const float* src = attn + b * H * nn + e;
+        float s = 0.f;
+        for (int hh = 0; hh < H; ++hh) s += __ldg(src + hh * nn);
+        mean[i] = s * inv;
+    }
+}
+
+int head_mean(const float* attn_in, float* mean, int batch, int heads, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(attn_in && mean, VTC_ERR_ARG, "head_mean: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "head_mean: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t nn = static_cast<size_t>(n_tokens) * n_tokens;
+    const size_t total = nn * batch;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    head_mean_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(attn_in, mean, heads, nn, total);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+}  // namespace vtc
+
+extern "C" {
+int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch, int32_t n_tokens,
+                  int32_t heads, float scale, void* stream) {
+    return vtc::attention(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream));
+}
+int vtc_head_mean(const float* attn, float* mean, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
+    return vtc::head_mean(attn, mean, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,214 @@
+// Small latency-bound kernels around the CLS attention row:
+//   cls_stat    head-mean CLS row -> renormalised patch map + batch-global max   (vit_model.py:329-335, 366-372)
+//   cls_mask    background decision + additive key bias for the next block     (vit_model.py:335-361)
+//   topk_heads  top-16 patches, token gather, head1, final LayerNorm on the CLS row, head  (vit_model.py:374-422)
+// None of them materialises a [B,N,N] tensor; everything is fp32.
+#include "common.cuh"
+#include "ops.h"
+
+namespace vtc {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < (blockDim.x >> 5)) ? red[lane] : 0.f;
+    return warp_sum(t);
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < (blockDim.x >> 5)) ? red[lane] : -INFINITY;
+    return warp_max(t);
+}
+
+// grid = B, block = 256
+__global__ void cls_stat_kernel(const float* __restrict__ cls_rows, float* __restrict__ cls_map, float* __restrict__ gmax, int H, int N) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const float* src = cls_rows + static_cast<size_t>(b) * H * N;
+    const float invH = 1.0f / H;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float s = 0.f;
+        for (int h = 0; h < H; ++h) s += src[h * N + j];
+        part += s * invH;
+    }
+    const float rowsum = block_sum(part, red) + 1.0f;    // + identity on the CLS diagonal (vit_model.py:331-333)
+    float mx = 0.f;
+    for (int j = threadIdx.x + 1; j < N; j += blockDim.x) {
+        float s = 0.f;
+        for (int h = 0; h < H; ++h) s += src[h * N + j];
+        const float v = (s * invH) / rowsum;
+        cls_map[static_cast<size_t>(b) * (N - 1) + (j - 1)] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    if (threadIdx.x == 0 && gmax != nullptr) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));   // values are >= 0
+}
+
+int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(cls_rows && cls_map, VTC_ERR_ARG, "cls_stat: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 1, VTC_ERR_SHAPE, "cls_stat: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    cls_stat_kernel<<<batch, 256, 0, stream>>>(cls_rows, cls_map, gmax, heads, n_tokens);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// grid = B, block = 256
+__global__ void cls_mask_kernel(const float* __restrict__ cls_map, const float* __restrict__ gmax, const uint8_t* __restrict__ forced,
+                                float thresh, int per_image, uint8_t* __restrict__ bg, float* __restrict__ key_bias, int N) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int P = N - 1;
+    const float* m = cls_map + static_cast<size_t>(b) * P;
+    float mx;
+    if (per_image) {
+        float v = 0.f;
+        for (int j = threadIdx.x; j < P; j += blockDim.x) v = fmaxf(v, m[j]);
+        mx = block_max(v, red);
+    } else {
+        mx = *gmax;
+    }
+    if (threadIdx.x == 0 && key_bias != nullptr) key_bias[static_cast<size_t>(b) * N] = 0.f;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+        uint8_t isbg;
+        if (forced != nullptr) isbg = forced[static_cast<size_t>(b) * P + j] != 0;
+        else isbg = (m[j] / mx) < thresh;                         // torch.lt(mask_14 / max, 0.25)
+        if (bg != nullptr) bg[static_cast<size_t>(b) * P + j] = isbg;
+        if (key_bias != nullptr) key_bias[static_cast<size_t>(b) * N + 1 + j] = isbg ? -100.0f : 0.0f;
+    }
+}
+
+int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
+             float* key_bias, int batch, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(cls_map && (per_image || gmax), VTC_ERR_ARG, "cls_mask: null pointer");
+    VTC_REQUIRE(batch > 0 && n_tokens > 1, VTC_ERR_SHAPE, "cls_mask: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    cls_mask_kernel<<<batch, 256, 0, stream>>>(cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, n_tokens);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// grid = B, block = 256.  Dynamic smem: [P] map copy + [D] mean token + [D] normalised CLS row + [R] pre-logits.
+__global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__ tokens, const float* __restrict__ cls_map,
+                                  const int32_t* __restrict__ forced_topk, float* __restrict__ logits, float* __restrict__ hwp_logits,
+                                  float* __restrict__ hwp_tokens, int32_t* __restrict__ topk_idx) {
+    extern __shared__ float sm[];
+    __shared__ float red[32];
+    __shared__ int idx_s[64];
+    const int b = blockIdx.x;
+    const int N = hp.n_tokens, P = N - 1, D = hp.dim, K = hp.topk, C = hp.classes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* mapv = sm;            // [P]
+    float* meanv = mapv + P;     // [D]
+    float* xn = meanv + D;       // [D]
+    float* feat = xn + D;        // [R] (only with pre_logits)
+
+    for (int j = threadIdx.x; j < P; j += blockDim.x) mapv[j] = cls_map[static_cast<size_t>(b) * P + j];
+    __syncthreads();
+    if (forced_topk != nullptr) {
+        if (threadIdx.x < K) idx_s[threadIdx.x] = forced_topk[b * K + threadIdx.x];
+    } else if (warp == 0) {
+        // K rounds of warp arg-max, descending, ties to the smaller index (torch.topk, vit_model.py:377)
+        for (int k = 0; k < K; ++k) {
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int j = lane; j < P; j += 32) {
+                const float v = mapv[j];
+                if (v > best) { best = v; bi = j; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { idx_s[k] = bi; mapv[bi] = -INFINITY; }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (topk_idx != nullptr && threadIdx.x < K) topk_idx[b * K + threadIdx.x] = idx_s[threadIdx.x];
+
+    // gather the K tokens (block-L output, pre final norm) and their mean
+    const float* tok = tokens + static_cast<size_t>(b) * N * D;
+    const float invK = 1.0f / K;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float v = tok[static_cast<size_t>(1 + idx_s[k]) * D + d];
+            hwp_tokens[(static_cast<size_t>(b) * K + k) * D + d] = v;
+            s += v;
+        }
+        meanv[d] = s * invK;
+    }
+    // final LayerNorm of the CLS row only (vit_model.py:402 normalises all rows; only row 0 is consumed :406)
+    float part = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) part += tok[d];
+    const float mean = block_sum(part, red) / D;
+    part = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { const float t = tok[d] - mean; part += t * t; }
+    const float rstd = rsqrtf(block_sum(part, red) / D + hp.eps);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) xn[d] = (tok[d] - mean) * rstd * hp.norm_w[d] + hp.norm_b[d];
+    __syncthreads();
+
+    const float* fin = xn;
+    int F = D;
+    if (hp.pre_w != nullptr) {   // pre_logits = tanh(fc(x)) (vit_model.py:267-273)
+        for (int r = warp; r < hp.rep; r += nwarps) {
+            float s = 0.f;
+            for (int d = lane; d < D; d += 32) s += hp.pre_w[static_cast<size_t>(r) * D + d] * xn[d];
+            s = warp_sum(s);
+            if (lane == 0) feat[r] = tanhf(s + hp.pre_b[r]);
+        }
+        __syncthreads();
+        fin = feat;
+        F = hp.rep;
+    }
+    for (int c = warp; c < C; c += nwarps) {
+        float s = 0.f, s1 = 0.f;
+        for (int d = lane; d < F; d += 32) s += hp.head_w[static_cast<size_t>(c) * F + d] * fin[d];
+        for (int d = lane; d < D; d += 32) s1 += hp.head1_w[static_cast<size_t>(c) * D + d] * meanv[d];
+        s = warp_sum(s);
+        s1 = warp_sum(s1);
+        if (lane == 0) {
+            logits[b * C + c] = s + hp.head_b[c];
+            hwp_logits[b * C + c] = s1 + hp.head1_b[c];
+        }
+    }
+}
+
+int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,
+               float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int batch, cudaStream_t stream) {
+    VTC_REQUIRE(tokens && cls_map && logits && hwp_logits && hwp_tokens, VTC_ERR_ARG, "topk_heads: null pointer");
+    VTC_REQUIRE(hp.norm_w && hp.norm_b && hp.head_w && hp.head_b && hp.head1_w && hp.head1_b, VTC_ERR_ARG, "topk_heads: missing weights");
+    VTC_REQUIRE(hp.topk > 0 && hp.topk <= 64 && hp.topk <= hp.n_tokens - 1, VTC_ERR_SHAPE, "topk_heads: topk=%d", hp.topk);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(hp.n_tokens - 1) + 2 * hp.dim + (hp.pre_w ? hp.rep : 0));
+    VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "topk_heads: %zu bytes of smem", smem);
+    topk_heads_kernel<<<batch, 256, smem, stream>>>(hp, tokens, cls_map, forced_topk, logits, hwp_logits, hwp_tokens, topk_idx);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+}  // namespace vtc
+
+extern "C" {
+int vtc_cls_stat(const float* cls_rows, float* cls_map, float* gmax, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
+    return vtc::cls_stat(cls_rows, cls_map, gmax, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));
+}
+int vtc_cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image, uint8_t* bg,
+                 float* key_bias, int32_t batch, int32_t n_tokens, void* stream) {
+    return vtc::cls_mask(cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, batch, n_tokens, static_cast<cudaStream_t>(stream));
+}
+}

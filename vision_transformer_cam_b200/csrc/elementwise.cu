@@ -1,0 +1,178 @@
+// Bandwidth-bound kernels of the forward: fp32->bf16 cast, patchify (im2col of the k=s=p conv), CLS token rows,
+// LayerNorm.  All use 16-byte vector accesses and are coalesced on the side that moves the most bytes.
+#include "common.cuh"
+#include "ops.h"
+
+namespace vtc {
+
+// ---- cast ------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    const size_t n8 = n / 8;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const float4 a = ld_stream_f4(src + i * 8);
+        const float4 b = ld_stream_f4(src + i * 8 + 4);
+        st_u4(dst + i * 8, make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - n8 * 8) dst[n8 * 8 + threadIdx.x] = __float2bfloat16_rn(src[n8 * 8 + threadIdx.x]);
+}
+
+int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream) {
+    VTC_REQUIRE(src && dst, VTC_ERR_ARG, "cast: null pointer");
+    if (n == 0) return VTC_OK;
+    VTC_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, VTC_ERR_ARG,
+                "cast: pointers must be 16-byte aligned");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t n8 = n / 8;
+    size_t blocks = (n8 + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    cast_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- patchify --------------------------------------------------------------------------------------
+// One thread moves 8 consecutive pixels of one image row: reads are fully coalesced along x (the fp32 side is
+// 2/3 of the bytes); each 16-byte bf16 store lands in patch row (b,py,px) at k = c*p*p + kh*p + kw.
+__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int in_c, int S, int p, size_t total8) {
+    const int g = S / p;
+    const int kdim = in_c * p * p;
+    const int xg_per_row = S / 8;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8; i += stride) {
+        const int xg = static_cast<int>(i % xg_per_row);
+        size_t r = i / xg_per_row;
+        const int y = static_cast<int>(r % S);
+        r /= S;
+        const int c = static_cast<int>(r % in_c);
+        const size_t b = r / in_c;
+        const float4 a0 = ld_stream_f4(x + i * 8);
+        const float4 a1 = ld_stream_f4(x + i * 8 + 4);
+        const int x0 = xg * 8;
+        const int py = y / p, kh = y - py * p;
+        const int px = x0 / p, kw = x0 - px * p;
+        const size_t row = (b * g + py) * g + px;
+        __nv_bfloat16* dst = out + row * kdim + (c * p + kh) * p + kw;
+        st_u4(dst, make_uint4(pack_bf16x2(a0.x, a0.y), pack_bf16x2(a0.z, a0.w), pack_bf16x2(a1.x, a1.y), pack_bf16x2(a1.z, a1.w)));
+    }
+}
+
+int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream) {
+    VTC_REQUIRE(x && patches, VTC_ERR_ARG, "patchify: null pointer");
+    VTC_REQUIRE(batch > 0 && in_c > 0 && img > 0 && patch > 0, VTC_ERR_SHAPE, "patchify: bad shape");
+    VTC_REQUIRE(img % patch == 0 && patch % 8 == 0, VTC_ERR_SHAPE, "patchify: img %d / patch %d unsupported (patch %% 8 == 0 required)", img, patch);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t total8 = static_cast<size_t>(batch) * in_c * img * img / 8;
+    size_t blocks = (total8 + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    patchify_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, total8);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- CLS token rows ---------------------------------------------------------------------------------
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ tokens,
+                                int n_tokens, int dim) {
+    float* dst = tokens + static_cast<size_t>(blockIdx.x) * n_tokens * dim;
+    for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
+        const float4 a = ldg_f4(cls + 4 * i);
+        const float4 b = ldg_f4(pos + 4 * i);
+        st_f4(dst + 4 * i, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+    }
+}
+
+int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int batch, int n_tokens, int dim, cudaStream_t stream) {
+    VTC_REQUIRE(cls_token && pos_embed && tokens, VTC_ERR_ARG, "cls_token_rows: null pointer");
+    VTC_REQUIRE(batch > 0 && dim % 4 == 0, VTC_ERR_SHAPE, "cls_token_rows: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    cls_rows_kernel<<<batch, 256, 0, stream>>>(cls_token, pos_embed, tokens, n_tokens, dim);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- LayerNorm ---------------------------------------------------------------------------------------
+// One warp per row, the row lives in registers (NV float4 per lane), two-pass mean / variance in fp32 exactly
+// like ATen's (sum of squared deviations), bf16 output.  8 rows per 256-thread CTA.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows,
+                                                        float eps) {
+    constexpr int D = NV * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* src = x + static_cast<size_t>(row) * D;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (lane + 32 * i) * 4);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    __nv_bfloat16* dst = y + static_cast<size_t>(row) * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 g = ldg_f4(gamma + c);
+        const float4 b = ldg_f4(beta + c);
+        const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+        const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+        const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+        *reinterpret_cast<uint2*>(dst + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+}
+
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream) {
+    VTC_REQUIRE(x && gamma && beta && y, VTC_ERR_ARG, "layernorm: null pointer");
+    VTC_REQUIRE(rows > 0, VTC_ERR_SHAPE, "layernorm: rows=%d", rows);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int grid = cdiv(rows, 8);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
+    switch (dim) {
+        case 256: layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        case 384: layernorm_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        case 512: layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        case 768: layernorm_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        case 1024: layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        case 1280: layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        default:
+            set_last_error("layernorm: dim %d unsupported (256/384/512/768/1024/1280)", dim);
+            return VTC_ERR_SHAPE;
+    }
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+}  // namespace vtc
+
+extern "C" {
+int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
+    return vtc::cast_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+int vtc_patchify(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream) {
+    return vtc::patchify(x, patches, batch, in_c, img, patch, static_cast<cudaStream_t>(stream));
+}
+int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int32_t batch, int32_t n_tokens, int32_t dim,
+                       void* stream) {
+    return vtc::cls_token_rows(cls_token, pos_embed, tokens, batch, n_tokens, dim, static_cast<cudaStream_t>(stream));
+}
+int vtc_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim, float eps,
+                       void* stream) {
+    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,237 @@
+// Model handle + the fused forward: VisionTransformer.forward of the reference (vit_model.py:303-424) as a fixed
+// sequence of kernel launches on one stream.  Host-only state; no device allocation, no synchronisation.
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "ops.h"
+
+struct vtc_model {
+    vtc_config cfg;
+    int N, P, D, H, L, C, HID, KP, R;
+    vtc_weights w;
+    std::vector<vtc_layer_weights> lw;
+    // packed bf16 GEMM weights (inside the caller's packed buffer)
+    const __nv_bfloat16* patch_w = nullptr;
+    struct LayerPacked { const __nv_bfloat16 *qkv, *proj, *fc1, *fc2; };
+    std::vector<LayerPacked> lp;
+    bool packed = false;
+};
+
+namespace vtc {
+
+static size_t seg(size_t elems, size_t elem_bytes) { return align_up(elems * elem_bytes, 256); }
+
+static size_t packed_bytes(const vtc_model* m) {
+    const size_t D = m->D, HID = m->HID;
+    return seg(D * m->KP, 2) + m->L * (seg(3 * D * D, 2) + seg(D * D, 2) + 2 * seg(HID * D, 2));
+}
+
+struct Workspace {
+    __nv_bfloat16 *hbuf, *patches, *y, *qkv, *ao;
+    float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp;
+    size_t bytes;
+};
+
+static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t* base) {
+    Workspace ws{};
+    const size_t M = static_cast<size_t>(B) * m->N, D = m->D, N = m->N;
+    size_t off = 0;
+    auto take = [&](size_t elems, size_t eb) { uint8_t* p = base ? base + off : nullptr; off += seg(elems, eb); return p; };
+    size_t hb = M * m->HID;
+    const size_t pb = static_cast<size_t>(B) * m->P * m->KP;
+    if (pb > hb) hb = pb;
+    ws.hbuf = reinterpret_cast<__nv_bfloat16*>(take(hb, 2));
+    ws.patches = ws.hbuf;   // the patch matrix is dead before the first fc1 writes hbuf
+    ws.y = reinterpret_cast<__nv_bfloat16*>(take(M * D, 2));
+    ws.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D, 2));
+    ws.ao = reinterpret_cast<__nv_bfloat16*>(take(M * D, 2));
+    const bool all_tokens = o && o->tokens && o->tokens_layers >= m->L;
+    ws.tok = reinterpret_cast<float*>(take(M * D, 4));    // embedding output / running residual stream
+    (void)all_tokens;
+    ws.cls_rows = (o && o->cls_rows) ? nullptr : reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N, 4));
+    ws.cls_map = (o && o->cls_map) ? nullptr : reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->P, 4));
+    ws.key_bias = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N, 4));
+    ws.gmax = reinterpret_cast<float*>(take(m->L, 4));
+    const bool need_tmp = o && o->attn_mean && !(o->attn && o->attn_layers >= m->L);
+    ws.attn_tmp = need_tmp ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N * N, 4)) : nullptr;
+    ws.bytes = off;
+    return ws;
+}
+
+static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, const vtc_forcing* f, void* workspace, size_t ws_bytes,
+                   uint32_t flags, cudaStream_t st) {
+    VTC_REQUIRE(m && x && o && workspace, VTC_ERR_ARG, "forward: null pointer");
+    VTC_REQUIRE(m->packed, VTC_ERR_ARG, "forward: vtc_model_pack_weights has not been called");
+    VTC_REQUIRE(B > 0, VTC_ERR_SHAPE, "forward: batch %d", B);
+    VTC_REQUIRE(o->logits && o->hwp_logits && o->hwp_tokens, VTC_ERR_ARG, "forward: logits / hwp_logits / hwp_tokens are required outputs");
+    VTC_REQUIRE(!(flags & VTC_FWD_FP32_SPLIT), VTC_ERR_ARG, "forward: the split-bf16 fp32 mode is not built yet");
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VTC_ERR_WORKSPACE, "forward: workspace must be 256-byte aligned");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    Workspace ws = carve(m, B, o, static_cast<uint8_t*>(workspace));
+    VTC_REQUIRE(ws.bytes <= ws_bytes, VTC_ERR_WORKSPACE, "forward: workspace %zu bytes < required %zu", ws_bytes, ws.bytes);
+
+    const int N = m->N, D = m->D, H = m->H, L = m->L, P = m->P, HID = m->HID;
+    const int M = B * N;
+    const size_t tok_elems = static_cast<size_t>(M) * D;
+    const int Lt = o->tokens ? o->tokens_layers : 0;
+    const int La = o->attn ? o->attn_layers : 0;
+    VTC_REQUIRE(Lt >= 0 && Lt <= L && La >= 0 && La <= L, VTC_ERR_ARG, "forward: tokens_layers / attn_layers out of range");
+    VTC_REQUIRE(!o->tokens || Lt >= 1, VTC_ERR_ARG, "forward: tokens requested with tokens_layers == 0");
+    const float scale = 1.0f / sqrtf(static_cast<float>(D / H));          // vit_model.py:97
+    const int per_image = (flags & VTC_FWD_MASK_NORM_IMAGE) ? 1 : 0;
+
+    // ---- patch embedding + token assembly (vit_model.py:306-314)
+    float* t_cur = ws.tok;
+    if ((rc = patchify(x, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st)) != VTC_OK) return rc;
+    if ((rc = cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st)) != VTC_OK) return rc;
+    if ((rc = gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st)) != VTC_OK)
+        return rc;
+    VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * L, st));
+    if (o->bg) VTC_CUDA(cudaMemsetAsync(o->bg, 0, static_cast<size_t>(L) * B * P, st));
+
+    bool have_bias = false;
+    float* last_map = nullptr;
+    for (int l = 0; l < L; ++l) {
+        const vtc_layer_weights& w = m->lw[l];
+        const vtc_model::LayerPacked& pw = m->lp[l];
+        float* t_in = t_cur;
+        float* t_out = t_cur;
+        if (o->tokens && l >= L - Lt) t_out = o->tokens + static_cast<size_t>(l - (L - Lt)) * tok_elems;
+        const bool want_map = (l >= m->cfg.mask_from) || (l == L - 1) || (o->cls_map != nullptr);
+        float* cls_l = o->cls_rows ? o->cls_rows + static_cast<size_t>(l) * B * H * N : (want_map ? ws.cls_rows : nullptr);
+        float* attn_l = nullptr;
+        if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
+        else if (o->attn_mean) attn_l = ws.attn_tmp;
+
+        if ((rc = layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st)) != VTC_OK) return rc;
+        if ((rc = gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st)) != VTC_OK) return rc;
+        const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
+        if ((rc = attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st)) != VTC_OK) return rc;
+        if ((rc = gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st)) != VTC_OK) return rc;
+        if ((rc = layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st)) != VTC_OK) return rc;
+        if ((rc = gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st)) != VTC_OK) return rc;
+        if ((rc = gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st)) != VTC_OK) return rc;
+        t_cur = t_out;
+
+        if (o->attn_mean && (rc = head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st)) != VTC_OK) return rc;
+        if (want_map) {
+            float* map_l = o->cls_map ? o->cls_map + static_cast<size_t>(l) * B * P : ws.cls_map;
+            if ((rc = cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st)) != VTC_OK) return rc;
+            last_map = map_l;
+            if (l >= m->cfg.mask_from) {                                                                        // vit_model.py:325
+                const uint8_t* forced = (f && f->bg && (f->bg_layer_mask >> l & 1u)) ? f->bg + static_cast<size_t>(l) * B * P : nullptr;
+                uint8_t* bg_l = o->bg ? o->bg + static_cast<size_t>(l) * B * P : nullptr;
+                if ((rc = cls_mask(map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, B, N, st)) != VTC_OK) return rc;
+                have_bias = true;
+            }
+        }
+    }
+    HeadParams hp{m->w.norm_w, m->w.norm_b, m->w.pre_w, m->w.pre_b, m->w.head_w, m->w.head_b, m->w.head1_w, m->w.head1_b,
+                  D, m->R, m->C, m->cfg.topk, N, m->cfg.ln_eps};
+    return topk_heads(hp, t_cur, last_map, f ? f->topk_idx : nullptr, o->logits, o->hwp_logits, o->hwp_tokens, o->topk_idx, B, st);
+}
+
+}  // namespace vtc
+
+extern "C" {
+
+int vtc_model_create(const vtc_config* cfg, vtc_model** out) {
+    using namespace vtc;
+    VTC_REQUIRE(cfg && out, VTC_ERR_ARG, "model_create: null pointer");
+    VTC_REQUIRE(cfg->img_size > 0 && cfg->patch_size > 0 && cfg->img_size % cfg->patch_size == 0, VTC_ERR_SHAPE,
+                "model_create: img_size %d / patch_size %d", cfg->img_size, cfg->patch_size);
+    VTC_REQUIRE(cfg->patch_size % 8 == 0, VTC_ERR_SHAPE, "model_create: patch_size %d must be a multiple of 8", cfg->patch_size);
+    VTC_REQUIRE(cfg->embed_dim > 0 && cfg->num_heads > 0 && cfg->embed_dim == cfg->num_heads * 64, VTC_ERR_SHAPE,
+                "model_create: head_dim must be 64 (embed_dim %d, heads %d)", cfg->embed_dim, cfg->num_heads);
+    VTC_REQUIRE(cfg->embed_dim % 256 == 0 && cfg->mlp_hidden % 256 == 0, VTC_ERR_SHAPE,
+                "model_create: embed_dim %d and mlp_hidden %d must be multiples of 256", cfg->embed_dim, cfg->mlp_hidden);
+    VTC_REQUIRE((cfg->in_c * cfg->patch_size * cfg->patch_size) % 64 == 0, VTC_ERR_SHAPE, "model_create: in_c*patch^2 must be a multiple of 64");
+    VTC_REQUIRE(cfg->depth > 0 && cfg->depth <= 32 && cfg->num_classes > 0, VTC_ERR_SHAPE, "model_create: depth %d classes %d", cfg->depth, cfg->num_classes);
+    VTC_REQUIRE(cfg->representation_size == 0 || cfg->representation_size == cfg->embed_dim, VTC_ERR_SHAPE,
+                "model_create: representation_size must be 0 or embed_dim (head1 consumes embed_dim features, vit_model.py:295,393)");
+    const int g = cfg->img_size / cfg->patch_size;
+    VTC_REQUIRE(cfg->topk > 0 && cfg->topk <= 64 && cfg->topk <= g * g, VTC_ERR_SHAPE, "model_create: topk %d", cfg->topk);
+    vtc_model* m = new (std::nothrow) vtc_model();
+    VTC_REQUIRE(m != nullptr, VTC_ERR_ARG, "model_create: out of host memory");
+    m->cfg = *cfg;
+    m->P = g * g;
+    m->N = m->P + 1;
+    m->D = cfg->embed_dim;
+    m->H = cfg->num_heads;
+    m->L = cfg->depth;
+    m->C = cfg->num_classes;
+    m->HID = cfg->mlp_hidden;
+    m->KP = cfg->in_c * cfg->patch_size * cfg->patch_size;
+    m->R = cfg->representation_size;
+    *out = m;
+    return VTC_OK;
+}
+
+int vtc_model_destroy(vtc_model* m) {
+    delete m;
+    return VTC_OK;
+}
+
+size_t vtc_model_packed_bytes(const vtc_model* m) { return m ? vtc::packed_bytes(m) : 0; }
+
+int vtc_model_pack_weights(vtc_model* m, const vtc_weights* w, void* packed, size_t bytes, void* stream) {
+    using namespace vtc;
+    VTC_REQUIRE(m && w && packed, VTC_ERR_ARG, "pack_weights: null pointer");
+    VTC_REQUIRE(w->num_layers == m->L && w->layers, VTC_ERR_ARG, "pack_weights: %d layers given, model has %d", w->num_layers, m->L);
+    VTC_REQUIRE(bytes >= packed_bytes(m), VTC_ERR_WORKSPACE, "pack_weights: buffer %zu < %zu", bytes, packed_bytes(m));
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, VTC_ERR_WORKSPACE, "pack_weights: buffer must be 256-byte aligned");
+    VTC_REQUIRE(w->cls_token && w->pos_embed && w->patch_w && w->patch_b && w->norm_w && w->norm_b && w->head_w && w->head_b &&
+                    w->head1_w && w->head1_b, VTC_ERR_ARG, "pack_weights: missing top-level parameter");
+    VTC_REQUIRE((m->R == 0) == (w->pre_w == nullptr), VTC_ERR_ARG, "pack_weights: pre_logits weights do not match representation_size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    m->w = *w;
+    m->lw.assign(w->layers, w->layers + w->num_layers);
+    m->w.layers = m->lw.data();
+    m->lp.resize(m->L);
+    uint8_t* base = static_cast<uint8_t*>(packed);
+    size_t off = 0;
+    const size_t D = m->D, HID = m->HID;
+    int rc;
+    auto pack = [&](const float* src, size_t elems, const __nv_bfloat16** dst) -> int {
+        VTC_REQUIRE(src != nullptr, VTC_ERR_ARG, "pack_weights: missing GEMM weight");
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(base + off);
+        off += seg(elems, 2);
+        *dst = d;
+        return cast_bf16(src, d, elems, st);
+    };
+    if ((rc = pack(w->patch_w, D * m->KP, &m->patch_w)) != VTC_OK) return rc;
+    for (int l = 0; l < m->L; ++l) {
+        const vtc_layer_weights& lw = m->lw[l];
+        VTC_REQUIRE(lw.norm1_w && lw.norm1_b && lw.norm2_w && lw.norm2_b && lw.qkv_b && lw.proj_b && lw.fc1_b && lw.fc2_b, VTC_ERR_ARG,
+                    "pack_weights: layer %d misses a vector parameter", l);
+        if ((rc = pack(lw.qkv_w, 3 * D * D, &m->lp[l].qkv)) != VTC_OK) return rc;
+        if ((rc = pack(lw.proj_w, D * D, &m->lp[l].proj)) != VTC_OK) return rc;
+        if ((rc = pack(lw.fc1_w, HID * D, &m->lp[l].fc1)) != VTC_OK) return rc;
+        if ((rc = pack(lw.fc2_w, D * HID, &m->lp[l].fc2)) != VTC_OK) return rc;
+    }
+    m->packed = true;
+    return VTC_OK;
+}
+
+size_t vtc_workspace_bytes(const vtc_model* m, int32_t batch, const vtc_outputs* outs) {
+    if (!m || batch <= 0) return 0;
+    return vtc::carve(m, batch, outs, nullptr).bytes;
+}
+
+int vtc_forward(vtc_model* m, const float* x, int32_t batch, const vtc_outputs* outs, const vtc_forcing* forcing, void* workspace,
+                size_t workspace_bytes, uint32_t flags, void* stream) {
+    return vtc::forward(m, x, batch, outs, forcing, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
+}
+
+int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,
+                   float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int32_t batch, void* stream) {
+    using namespace vtc;
+    VTC_REQUIRE(m && m->packed, VTC_ERR_ARG, "topk_heads: model without weights");
+    HeadParams hp{m->w.norm_w, m->w.norm_b, m->w.pre_w, m->w.pre_b, m->w.head_w, m->w.head_b, m->w.head1_w, m->w.head1_b,
+                  m->D, m->R, m->C, m->cfg.topk, m->N, m->cfg.ln_eps};
+    return topk_heads(hp, tokens, cls_map, forced_topk, logits, hwp_logits, hwp_tokens, topk_idx, batch, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// Internal C++ entry points of the kernels (the extern "C" wrappers in each .cu and the model forward call these).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vtc {
+
+int gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out, int M,
+              int N, int K, int epilogue, int tokens, cudaStream_t stream);
+int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
+int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream);
+int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int batch, int n_tokens, int dim, cudaStream_t stream);
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream);
+int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
+              float scale, cudaStream_t stream);
+int head_mean(const float* attn, float* mean, int batch, int heads, int n_tokens, cudaStream_t stream);
+int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream);
+int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
+             float* key_bias, int batch, int n_tokens, cudaStream_t stream);
+
+struct HeadParams {
+    const float* norm_w; const float* norm_b;
+    const float* pre_w;  const float* pre_b;
+    const float* head_w; const float* head_b;
+    const float* head1_w; const float* head1_b;
+    int dim, rep, classes, topk, n_tokens;
+    float eps;
+};
+int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,
+               float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int batch, cudaStream_t stream);
+
+}  // namespace vtc

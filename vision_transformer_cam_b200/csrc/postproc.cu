@@ -1,0 +1,507 @@
+// CAM / attention-rollout / pseudo-label post-processing: the math predict.py:189-269 and
+// validate.py:132-276 run after the forward, as bandwidth-oriented kernels (coalesced row reads, warp-shuffle
+// reductions, fused upsample + argmax so that only 1 byte per output pixel reaches HBM).
+#include "common.cuh"
+#include "ops.h"
+
+namespace vtc {
+
+static int grid_cap(size_t blocks, int per_sm) {
+    const size_t cap = static_cast<size_t>(device_sm_count()) * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+// ---- attention rollout ----------------------------------------------------------------------------------------
+// r <- r . A_l for l = L-1 .. 0, A_l = (Pbar_l + I) / rowsum(Pbar_l + I): only the CLS row of the product is consumed
+// (predict.py:229-232), so the dense N^3 chain collapses to a vector-matrix chain.  One CTA per image; each warp
+// streams whole rows (coalesced), gets the row sum by shuffle, and accumulates w_i * row into its private column
+// accumulators in shared memory; the matrix is read exactly once.
+constexpr int ROLL_WARPS = 8;
+__global__ void __launch_bounds__(ROLL_WARPS * 32) rollout_kernel(const float* __restrict__ pbar, float* __restrict__ out, int L, int B, int N) {
+    extern __shared__ float sm[];
+    float* r = sm;                  // [N]
+    float* acc = sm + N;            // [ROLL_WARPS][N]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) r[j] = (j == 0) ? 1.0f : 0.0f;
+    __syncthreads();
+    for (int l = L - 1; l >= 0; --l) {
+        const float* A = pbar + (static_cast<size_t>(l) * B + b) * N * N;
+        float* my = acc + warp * N;
+        for (int j = lane; j < N; j += 32) my[j] = 0.f;
+        for (int i = warp; i < N; i += ROLL_WARPS) {
+            const float ri = r[i];
+            if (ri == 0.0f) continue;            // exact zeros only (the first step has a single non-zero row)
+            const float* row = A + static_cast<size_t>(i) * N;
+            float s = 0.f;
+            for (int j = lane; j < N; j += 32) s += row[j];
+            const float w = ri / (warp_sum(s) + 1.0f);
+            for (int j = lane; j < N; j += 32) my[j] += w * row[j] + (j == i ? w : 0.f);   // second touch hits L1; + identity
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < ROLL_WARPS; ++w) s += acc[w * N + j];
+            r[j] = s;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x + 1; j < N; j += blockDim.x) out[static_cast<size_t>(b) * (N - 1) + j - 1] = r[j];
+}
+
+int rollout(const float* attn_mean, float* row, int layers, int batch, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(attn_mean && row, VTC_ERR_ARG, "rollout: null pointer");
+    VTC_REQUIRE(layers > 0 && batch > 0 && n_tokens > 1, VTC_ERR_SHAPE, "rollout: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t smem = sizeof(float) * static_cast<size_t>(n_tokens) * (ROLL_WARPS + 1);
+    VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "rollout: %d tokens need %zu bytes of smem", n_tokens, smem);
+    rollout_kernel<<<batch, ROLL_WARPS * 32, smem, stream>>>(attn_mean, row, layers, batch, n_tokens);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- CLS-row maps (per-layer maps predict.py:261-266; layers-6..12 bg map validate.py:225-237) -----------------
+__global__ void cls_layer_map_kernel(const float* __restrict__ cls_rows, float* __restrict__ map, int first, int last, int B, int H, int N) {
+    extern __shared__ float rowv[];      // [N]
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const float inv = 1.0f / (static_cast<float>(last - first) * H);
+    float part = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float s = 0.f;
+        for (int l = first; l < last; ++l) {
+            const float* src = cls_rows + ((static_cast<size_t>(l) * B + b) * H) * N + j;
+            for (int h = 0; h < H; ++h) s += src[static_cast<size_t>(h) * N];
+        }
+        s *= inv;
+        if (j == 0) s += 1.0f;
+        rowv[j] = s;
+        part += s;
+    }
+    // block reductions (sum, then max of the patch part)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    float tot = (lane < (blockDim.x >> 5)) ? red[lane] : 0.f;
+    tot = warp_sum(tot);
+    __syncthreads();
+    float mx = 0.f;
+    for (int j = threadIdx.x + 1; j < N; j += blockDim.x) {
+        const float v = rowv[j] / tot;
+        rowv[j] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    float gm = (lane < (blockDim.x >> 5)) ? red[lane] : 0.f;
+    gm = warp_max(gm);
+    for (int j = threadIdx.x + 1; j < N; j += blockDim.x) map[static_cast<size_t>(b) * (N - 1) + j - 1] = rowv[j] / gm;
+}
+
+int cls_layer_map(const float* cls_rows, float* map, int layers, int first, int last, int batch, int heads, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(cls_rows && map, VTC_ERR_ARG, "cls_layer_map: null pointer");
+    VTC_REQUIRE(0 <= first && first < last && last <= layers && batch > 0 && heads > 0 && n_tokens > 1, VTC_ERR_SHAPE, "cls_layer_map: bad range [%d,%d) of %d", first, last, layers);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    cls_layer_map_kernel<<<batch, 256, sizeof(float) * n_tokens, stream>>>(cls_rows, map, first, last, batch, heads, n_tokens);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- classic CAM ---------------------------------------------------------------------------------------------------
+// cam[b,c,p] = <W[c,:], F[b,p,:]> on the block-L patch tokens, ReLU, per-map min-max (t.py:66-70, utils.py:84-85).
+// One CTA per image: W staged once in shared memory, each warp streams patch rows with float4 loads, C running dot
+// products per lane, shuffle reduction, raw maps kept in shared memory for the normalisation pass.
+constexpr int CAM_MAXC = 32;
+__global__ void __launch_bounds__(256) cam_project_kernel(const float* __restrict__ tokens, const float* __restrict__ w, float* __restrict__ cam,
+                                                          int N, int D, int C, int relu, float eps) {
+    extern __shared__ float sm[];
+    float* ws = sm;                 // [C][D]
+    float* raw = sm + C * D;        // [C][P]
+    const int P = N - 1;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < C * D / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = ldg_f4(w + 4 * i);
+    __syncthreads();
+    const float* F = tokens + (static_cast<size_t>(b) * N + 1) * D;
+    const int nv = D / 128;         // float4 per lane
+    for (int p = warp; p < P; p += 8) {
+        float acc[CAM_MAXC];
+#pragma unroll
+        for (int c = 0; c < CAM_MAXC; ++c) acc[c] = 0.f;
+        const float* row = F + static_cast<size_t>(p) * D;
+        for (int i = 0; i < nv; ++i) {
+            const int d = (lane + 32 * i) * 4;
+            const float4 f = ld_stream_f4(row + d);
+#pragma unroll
+            for (int c = 0; c < CAM_MAXC; ++c) {
+                if (c < C) {
+                    const float4 wv = *reinterpret_cast<const float4*>(ws + c * D + d);
+                    acc[c] = fmaf(f.x, wv.x, fmaf(f.y, wv.y, fmaf(f.z, wv.z, fmaf(f.w, wv.w, acc[c]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CAM_MAXC; ++c) {
+            if (c < C) {
+                const float s = warp_sum(acc[c]);
+                if (lane == 0) raw[c * P + p] = relu ? fmaxf(s, 0.f) : s;
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += 8) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int p = lane; p < P; p += 32) { const float v = raw[c * P + p]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        const float den = (mx - mn) + eps;
+        float* dst = cam + (static_cast<size_t>(b) * C + c) * P;
+        for (int p = lane; p < P; p += 32) dst[p] = (raw[c * P + p] - mn) / den;
+    }
+}
+
+int cam_project(const float* tokens, const float* w, float* cam, int batch, int n_tokens, int dim, int classes, int relu, float eps, cudaStream_t stream) {
+    VTC_REQUIRE(tokens && w && cam, VTC_ERR_ARG, "cam_project: null pointer");
+    VTC_REQUIRE(batch > 0 && n_tokens > 1 && dim % 128 == 0 && classes > 0 && classes <= CAM_MAXC, VTC_ERR_SHAPE,
+                "cam_project: dim %d (multiple of 128) classes %d (<= %d)", dim, classes, CAM_MAXC);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(classes) * dim + static_cast<size_t>(classes) * (n_tokens - 1));
+    VTC_REQUIRE(smem <= 200 * 1024, VTC_ERR_SHAPE, "cam_project: %zu bytes of smem", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        VTC_CUDA(cudaFuncSetAttribute(cam_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    cam_project_kernel<<<batch, 256, smem, stream>>>(tokens, w, cam, n_tokens, dim, classes, relu, eps);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- row-wise / max -------------------------------------------------------------------------------------------------
+__global__ void normalize_max_kernel(float* __restrict__ maps, int rows, int P) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* m = maps + static_cast<size_t>(row) * P;
+    float mx = -INFINITY;
+    for (int j = lane; j < P; j += 32) mx = fmaxf(mx, m[j]);
+    mx = warp_max(mx);
+    for (int j = lane; j < P; j += 32) m[j] = m[j] / mx;
+}
+
+int normalize_max(float* maps, int rows, int p, cudaStream_t stream) {
+    VTC_REQUIRE(maps, VTC_ERR_ARG, "normalize_max: null pointer");
+    VTC_REQUIRE(rows > 0 && p > 0, VTC_ERR_SHAPE, "normalize_max: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    normalize_max_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(maps, rows, p);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- bilinear upsampling, align_corners=False (F.interpolate validate.py:177,239 == cv2.resize INTER_LINEAR) ----------
+struct Lerp { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
+    float src = (dst + 0.5f) * scale - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int i0 = static_cast<int>(src);
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    const int i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    const float l1 = src - i0;
+    return Lerp{i0, i1, 1.0f - l1, l1};
+}
+__device__ __forceinline__ float bilerp(const float* m, int g, const Lerp& y, const Lerp& x) {
+    return y.w0 * (x.w0 * m[y.i0 * g + x.i0] + x.w1 * m[y.i0 * g + x.i1]) + y.w1 * (x.w0 * m[y.i1 * g + x.i0] + x.w1 * m[y.i1 * g + x.i1]);
+}
+
+template <bool U8>
+__global__ void upsample_kernel(const float* __restrict__ in, void* __restrict__ out, int g, int H, int W) {
+    extern __shared__ float m[];      // [g*g]
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < g * g; i += blockDim.x) m[i] = in[static_cast<size_t>(n) * g * g + i];
+    __syncthreads();
+    const float sy = static_cast<float>(g) / H, sx = static_cast<float>(g) / W;
+    const size_t hw = static_cast<size_t>(H) * W;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<size_t>(y) * W);
+        const float v = bilerp(m, g, lerp_coord(y, sy, g), lerp_coord(x, sx, g));
+        if (U8) static_cast<uint8_t*>(out)[n * hw + i] = static_cast<uint8_t>(v * 255.0f);     // .astype("uint8") truncation, predict.py:269
+        else static_cast<float*>(out)[n * hw + i] = v;
+    }
+}
+
+template <bool U8>
+static int upsample(const float* in, void* out, int n, int g, int H, int W, cudaStream_t stream) {
+    VTC_REQUIRE(in && out, VTC_ERR_ARG, "upsample: null pointer");
+    VTC_REQUIRE(n > 0 && g > 0 && H > 0 && W > 0 && g * g * 4 <= 48 * 1024 && n <= 65535, VTC_ERR_SHAPE, "upsample: bad shape n=%d g=%d", n, g);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    int bx = cdiv(H * W, 256 * 4);
+    if (bx < 1) bx = 1;
+    upsample_kernel<U8><<<dim3(bx, n), 256, sizeof(float) * g * g, stream>>>(in, out, g, H, W);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- CAM pseudo label: fused upsample + argmax over [bg_thresh, labelled classes] -----------------------------------
+__global__ void cam_label_kernel(const float* __restrict__ cam, const uint8_t* __restrict__ labels, float bg_thresh, uint8_t* __restrict__ out,
+                                 int C, int g, int H, int W) {
+    extern __shared__ float m[];      // [C][g*g]
+    __shared__ int active[64];
+    __shared__ int nactive;
+    const int b = blockIdx.y;
+    const int gg = g * g;
+    for (int i = threadIdx.x; i < C * gg; i += blockDim.x) m[i] = cam[static_cast<size_t>(b) * C * gg + i];
+    if (threadIdx.x == 0) {
+        int k = 0;
+        for (int c = 0; c < C; ++c)
+            if (labels[b * C + c]) active[k++] = c;
+        nactive = k;
+    }
+    __syncthreads();
+    const float sy = static_cast<float>(g) / H, sx = static_cast<float>(g) / W;
+    const size_t hw = static_cast<size_t>(H) * W;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<size_t>(y) * W);
+        const Lerp ly = lerp_coord(y, sy, g), lx = lerp_coord(x, sx, g);
+        float best = bg_thresh;
+        int lab = 0;
+        for (int k = 0; k < nactive; ++k) {
+            const int c = active[k];
+            const float v = bilerp(m + c * gg, g, ly, lx);
+            if (v > best) { best = v; lab = c + 1; }       // strict: ties keep the earlier entry like torch.argmax
+        }
+        out[b * hw + i] = static_cast<uint8_t>(lab);
+    }
+}
+
+int cam_label(const float* cam, const uint8_t* labels, float bg_thresh, uint8_t* out, int batch, int classes, int g, int H, int W, cudaStream_t stream) {
+    VTC_REQUIRE(cam && labels && out, VTC_ERR_ARG, "cam_label: null pointer");
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && classes > 0 && classes <= 64 && g > 0 && H > 0 && W > 0, VTC_ERR_SHAPE, "cam_label: bad shape");
+    const size_t smem = sizeof(float) * classes * g * g;
+    VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "cam_label: %zu bytes of smem", smem);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    int bx = cdiv(H * W, 256 * 4);
+    if (bx < 1) bx = 1;
+    cam_label_kernel<<<dim3(bx, batch), 256, smem, stream>>>(cam, labels, bg_thresh, out, classes, g, H, W);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- high-weight-patch class vote + cosine maps (validate.py:132-175) -------------------------------------------------
+constexpr int HWP_MAXK = 16;
+__global__ void __launch_bounds__(256) hwp_cos_vote_kernel(const float* __restrict__ hwp_logits, const float* __restrict__ w1,
+                                                           const float* __restrict__ ori, const float* __restrict__ tokens, float sig_thresh,
+                                                           int32_t* __restrict__ p2c, float* __restrict__ cosm, int N, int D, int C, int K) {
+    extern __shared__ float sm[];
+    float* os = sm;                       // [K][D] hw tokens
+    float* onorm = os + K * D;            // [K]
+    int* votes = reinterpret_cast<int*>(onorm + HWP_MAXK);   // [K][C]
+    __shared__ int pred[64];
+    const int b = blockIdx.x, P = N - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* ob = ori + static_cast<size_t>(b) * K * D;
+    for (int i = threadIdx.x; i < K * D / 4; i += blockDim.x) reinterpret_cast<float4*>(os)[i] = ldg_f4(ob + 4 * i);
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) votes[i] = 0;
+    if (threadIdx.x < C) pred[threadIdx.x] = (1.0f / (1.0f + expf(-hwp_logits[b * C + threadIdx.x]))) >= sig_thresh;   // validate.py:132-134
+    __syncthreads();
+    for (int k = warp; k < K; k += 8) {
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s += os[k * D + d] * os[k * D + d];
+        s = warp_sum(s);
+        if (lane == 0) onorm[k] = fmaxf(sqrtf(s), 1e-12f);                        // F.normalize eps
+    }
+    // feature vote: class of feature d (argmax over predicted classes' head1 rows) goes to the hw patch owning d
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float bw = -INFINITY;
+        int bc = 0;
+        for (int c = 0; c < C; ++c) {
+            const float v = pred[c] ? __ldg(w1 + static_cast<size_t>(c) * D + d) : -10.0f;     // validate.py:138-143
+            if (v > bw) { bw = v; bc = c; }
+        }
+        float bo = -INFINITY;
+        int bk = 0;
+        for (int k = 0; k < K; ++k) {
+            const float v = os[k * D + d];
+            if (v > bo) { bo = v; bk = k; }                                       // validate.py:148
+        }
+        atomicAdd(&votes[bk * C + bc], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        int best = 0, bc = -1;
+        for (int c = 0; c < C; ++c)
+            if (votes[threadIdx.x * C + c] > best) { best = votes[threadIdx.x * C + c]; bc = c; }   // mode, ties -> smallest class
+        p2c[b * K + threadIdx.x] = bc;                                            // -1: patch owns no feature
+    }
+    // cosine maps
+    const float* F = tokens + (static_cast<size_t>(b) * N + 1) * D;
+    const int nv = D / 128;
+    for (int p = warp; p < P; p += 8) {
+        float acc[HWP_MAXK];
+#pragma unroll
+        for (int k = 0; k < HWP_MAXK; ++k) acc[k] = 0.f;
+        float nn = 0.f;
+        const float* row = F + static_cast<size_t>(p) * D;
+        for (int i = 0; i < nv; ++i) {
+            const int d = (lane + 32 * i) * 4;
+            const float4 f = ld_stream_f4(row + d);
+            nn = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, nn))));
+#pragma unroll
+            for (int k = 0; k < HWP_MAXK; ++k) {
+                if (k < K) {
+                    const float4 o = *reinterpret_cast<const float4*>(os + k * D + d);
+                    acc[k] = fmaf(f.x, o.x, fmaf(f.y, o.y, fmaf(f.z, o.z, fmaf(f.w, o.w, acc[k]))));
+                }
+            }
+        }
+        nn = fmaxf(sqrtf(warp_sum(nn)), 1e-12f);
+#pragma unroll
+        for (int k = 0; k < HWP_MAXK; ++k) {
+            if (k < K) {
+                const float s = warp_sum(acc[k]);
+                if (lane == 0) cosm[(static_cast<size_t>(b) * K + k) * P + p] = s / (nn * onorm[k]);
+            }
+        }
+    }
+}
+
+int hwp_cos_vote(const float* hwp_logits, const float* head1_w, const float* hwp_tokens, const float* tokens, float sig_thresh,
+                 int32_t* patch_to_cls, float* cosm, int batch, int n_tokens, int dim, int classes, int k, cudaStream_t stream) {
+    VTC_REQUIRE(hwp_logits && head1_w && hwp_tokens && tokens && patch_to_cls && cosm, VTC_ERR_ARG, "hwp_cos_vote: null pointer");
+    VTC_REQUIRE(batch > 0 && n_tokens > 1 && dim % 128 == 0 && classes > 0 && classes <= 64 && k > 0 && k <= HWP_MAXK, VTC_ERR_SHAPE,
+                "hwp_cos_vote: dim %d classes %d k %d", dim, classes, k);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(k) * dim + HWP_MAXK) + sizeof(int) * k * classes;
+    VTC_REQUIRE(smem <= 200 * 1024, VTC_ERR_SHAPE, "hwp_cos_vote: %zu bytes of smem", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        VTC_CUDA(cudaFuncSetAttribute(hwp_cos_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    hwp_cos_vote_kernel<<<batch, 256, smem, stream>>>(hwp_logits, head1_w, hwp_tokens, tokens, sig_thresh, patch_to_cls, cosm, n_tokens, dim, classes, k);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- validate.py:177-258 fused: upsample K cosine maps + argmax + fg/bg thresholds -> uint8 label map ------------------
+__global__ void hwp_seg_kernel(const float* __restrict__ cosm, const int32_t* __restrict__ p2c, const float* __restrict__ bg_map, float cos_thresh,
+                               float bg_thresh, uint8_t* __restrict__ out, int K, int g, int H, int W) {
+    extern __shared__ float m[];      // [K][g*g] + [g*g]
+    __shared__ int cls_s[HWP_MAXK];
+    const int b = blockIdx.y;
+    const int gg = g * g;
+    for (int i = threadIdx.x; i < K * gg; i += blockDim.x) m[i] = cosm[static_cast<size_t>(b) * K * gg + i];
+    for (int i = threadIdx.x; i < gg; i += blockDim.x) m[K * gg + i] = bg_map[static_cast<size_t>(b) * gg + i];
+    if (threadIdx.x < K) cls_s[threadIdx.x] = p2c[b * K + threadIdx.x];
+    __syncthreads();
+    const float sy = static_cast<float>(g) / H, sx = static_cast<float>(g) / W;
+    const size_t hw = static_cast<size_t>(H) * W;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<size_t>(y) * W);
+        const Lerp ly = lerp_coord(y, sy, g), lx = lerp_coord(x, sx, g);
+        float best = -INFINITY;
+        int bk = 0;
+        for (int k = 0; k < K; ++k) {
+            const float v = bilerp(m + k * gg, g, ly, lx);
+            if (v > best) { best = v; bk = k; }                                   // validate.py:179-180
+        }
+        const bool fg = best >= cos_thresh;                                       // validate.py:183-186
+        const bool keep = bilerp(m + K * gg, g, ly, lx) >= bg_thresh;             // validate.py:239-246
+        const int c = cls_s[bk];
+        out[b * hw + i] = (fg && keep && c >= 0) ? static_cast<uint8_t>(c + 1) : 0;   // validate.py:190-258
+    }
+}
+
+int hwp_seg(const float* cosm, const int32_t* p2c, const float* bg_map, float cos_thresh, float bg_thresh, uint8_t* out, int batch, int k, int g,
+            int H, int W, cudaStream_t stream) {
+    VTC_REQUIRE(cosm && p2c && bg_map && out, VTC_ERR_ARG, "hwp_seg: null pointer");
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && k > 0 && k <= HWP_MAXK && g > 0 && H > 0 && W > 0, VTC_ERR_SHAPE, "hwp_seg: bad shape");
+    const size_t smem = sizeof(float) * (k + 1) * g * g;
+    VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "hwp_seg: %zu bytes of smem", smem);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    int bx = cdiv(H * W, 256 * 4);
+    if (bx < 1) bx = 1;
+    hwp_seg_kernel<<<dim3(bx, batch), 256, smem, stream>>>(cosm, p2c, bg_map, cos_thresh, bg_thresh, out, k, g, H, W);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- confusion matrix (utils.py:35-45) -------------------------------------------------------------------------------------
+__global__ void confmat_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred, size_t count, int n, unsigned long long* __restrict__ mat) {
+    extern __shared__ unsigned int hist[];    // [n*n]
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const int a = gt[i], p = pred[i];
+        if (a < n && p < n) atomicAdd(&hist[a * n + p], 1u);      // k = (a >= 0) & (a < n): 255 = ignore
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x)
+        if (hist[i]) atomicAdd(&mat[i], static_cast<unsigned long long>(hist[i]));
+}
+
+int confmat_update(const uint8_t* gt, const uint8_t* pred, size_t count, int n, int64_t* mat, cudaStream_t stream) {
+    VTC_REQUIRE(gt && pred && mat, VTC_ERR_ARG, "confmat: null pointer");
+    VTC_REQUIRE(n > 0 && n <= 64, VTC_ERR_SHAPE, "confmat: n=%d", n);
+    if (count == 0) return VTC_OK;
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int grid = grid_cap((count + 256 * 16 - 1) / (256 * 16), 8);
+    confmat_kernel<<<grid, 256, sizeof(unsigned int) * n * n, stream>>>(gt, pred, count, n, reinterpret_cast<unsigned long long*>(mat));
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+}  // namespace vtc
+
+extern "C" {
+int vtc_rollout(const float* attn_mean, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream) {
+    return vtc::rollout(attn_mean, row, layers, batch, n_tokens, static_cast<cudaStream_t>(stream));
+}
+int vtc_cls_layer_map(const float* cls_rows, float* map, int32_t layers, int32_t first, int32_t last, int32_t batch, int32_t heads,
+                      int32_t n_tokens, void* stream) {
+    return vtc::cls_layer_map(cls_rows, map, layers, first, last, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));
+}
+int vtc_cam_project(const float* tokens, const float* w, float* cam, int32_t batch, int32_t n_tokens, int32_t dim, int32_t classes,
+                    int32_t relu, float eps, void* stream) {
+    return vtc::cam_project(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, static_cast<cudaStream_t>(stream));
+}
+int vtc_normalize_max(float* maps, int32_t rows, int32_t p, void* stream) {
+    return vtc::normalize_max(maps, rows, p, static_cast<cudaStream_t>(stream));
+}
+int vtc_upsample_bilinear(const float* in, float* out, int32_t n, int32_t g, int32_t out_h, int32_t out_w, void* stream) {
+    return vtc::upsample<false>(in, out, n, g, out_h, out_w, static_cast<cudaStream_t>(stream));
+}
+int vtc_upsample_bilinear_u8(const float* in, uint8_t* out, int32_t n, int32_t g, int32_t out_h, int32_t out_w, void* stream) {
+    return vtc::upsample<true>(in, out, n, g, out_h, out_w, static_cast<cudaStream_t>(stream));
+}
+int vtc_cam_label(const float* cam, const uint8_t* labels, float bg_thresh, uint8_t* out, int32_t batch, int32_t classes, int32_t g,
+                  int32_t out_h, int32_t out_w, void* stream) {
+    return vtc::cam_label(cam, labels, bg_thresh, out, batch, classes, g, out_h, out_w, static_cast<cudaStream_t>(stream));
+}
+int vtc_hwp_cos_vote(const float* hwp_logits, const float* head1_w, const float* hwp_tokens, const float* tokens, float sig_thresh,
+                     int32_t* patch_to_cls, float* cos, int32_t batch, int32_t n_tokens, int32_t dim, int32_t classes, int32_t k, void* stream) {
+    return vtc::hwp_cos_vote(hwp_logits, head1_w, hwp_tokens, tokens, sig_thresh, patch_to_cls, cos, batch, n_tokens, dim, classes, k,
+                             static_cast<cudaStream_t>(stream));
+}
+int vtc_hwp_seg(const float* cos, const int32_t* patch_to_cls, const float* bg_map, float cos_thresh, float bg_thresh, uint8_t* out,
+                int32_t batch, int32_t k, int32_t g, int32_t out_h, int32_t out_w, void* stream) {
+    return vtc::hwp_seg(cos, patch_to_cls, bg_map, cos_thresh, bg_thresh, out, batch, k, g, out_h, out_w, static_cast<cudaStream_t>(stream));
+}
+int vtc_confmat_update(const uint8_t* gt, const uint8_t* pred, size_t count, int32_t n, int64_t* mat, void* stream) {
+    return vtc::confmat_update(gt, pred, count, n, mat, static_cast<cudaStream_t>(stream));
+}
+}

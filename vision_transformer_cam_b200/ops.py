@@ -1,0 +1,194 @@
+"""Tensor-level wrappers over the C-ABI kernels (one function per `vtc_*` entry point).
+
+PyTorch is plumbing here: it owns device memory and the stream; every computation is a libvtc kernel.  All
+wrappers validate device / dtype / contiguity and raise (never fall back) when something is off."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (libvtc has no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _lib.call("vtc_cast_bf16", _ptr(src, torch.float32, "src"), _ptr(out), src.numel(), _stream())
+    return out
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int = _lib.EPI_BIAS,
+              residual: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, tokens: int = 0) -> torch.Tensor:
+    """a [M,K] bf16, w [N,K] bf16 (nn.Linear layout), bias [N] fp32."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        if epilogue in (_lib.EPI_BIAS, _lib.EPI_BIAS_GELU):
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        elif epilogue == _lib.EPI_BIAS_RESIDUAL:
+            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        else:
+            raise RuntimeError("patch-embed epilogue needs an explicit token buffer `out`")
+    _lib.call("vtc_gemm_bf16", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32, "bias"),
+              _ptr(residual, torch.float32, "residual"), _ptr(pos, torch.float32, "pos"), _ptr(out), M, N, K, epilogue, tokens, _stream())
+    return out
+
+
+def patchify(x: torch.Tensor, patch: int) -> torch.Tensor:
+    B, Cin, S, S2 = x.shape
+    assert S == S2
+    g = S // patch
+    out = torch.empty((B * g * g, Cin * patch * patch), dtype=torch.bfloat16, device=x.device)
+    _lib.call("vtc_patchify", _ptr(x, torch.float32, "x"), _ptr(out), B, Cin, S, patch, _stream())
+    return out
+
+
+def cls_token_rows(cls_token: torch.Tensor, pos_embed: torch.Tensor, tokens: torch.Tensor) -> None:
+    B, N, D = tokens.shape
+    _lib.call("vtc_cls_token_rows", _ptr(cls_token, torch.float32), _ptr(pos_embed, torch.float32), _ptr(tokens, torch.float32),
+              B, N, D, _stream())
+
+
+def layernorm_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+    D = x.shape[-1]
+    rows = x.numel() // D
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("vtc_layernorm_bf16", _ptr(x, torch.float32, "x"), _ptr(weight, torch.float32), _ptr(bias, torch.float32), _ptr(out),
+              rows, D, eps, _stream())
+    return out
+
+
+def attention(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, want_cls: bool = True,
+              want_attn: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """qkv [B,N,3*H*64] bf16 -> (out [B,N,H*64] bf16, cls_rows [B,H,N] fp32 | None, attn [B,H,N,N] fp32 | None)."""
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if want_cls else None
+    attn = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv.device) if want_attn else None
+    _lib.call("vtc_attention", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls),
+              _ptr(attn), B, N, heads, scale, _stream())
+    return out, cls, attn
+
+
+def head_mean(attn: torch.Tensor) -> torch.Tensor:
+    B, H, N, _ = attn.shape
+    out = torch.empty((B, N, N), dtype=torch.float32, device=attn.device)
+    _lib.call("vtc_head_mean", _ptr(attn, torch.float32), _ptr(out), B, H, N, _stream())
+    return out
+
+
+def cls_stat(cls_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, H, N = cls_rows.shape
+    cmap = torch.empty((B, N - 1), dtype=torch.float32, device=cls_rows.device)
+    gmax = torch.zeros((1,), dtype=torch.float32, device=cls_rows.device)
+    _lib.call("vtc_cls_stat", _ptr(cls_rows, torch.float32), _ptr(cmap), _ptr(gmax), B, H, N, _stream())
+    return cmap, gmax
+
+
+def cls_mask(cls_map: torch.Tensor, gmax: torch.Tensor, thresh: float = 0.25, per_image: bool = False,
+             forced_bg: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, P = cls_map.shape
+    bg = torch.empty((B, P), dtype=torch.uint8, device=cls_map.device)
+    kb = torch.empty((B, P + 1), dtype=torch.float32, device=cls_map.device)
+    _lib.call("vtc_cls_mask", _ptr(cls_map, torch.float32), _ptr(gmax, torch.float32), _ptr(forced_bg, torch.uint8), thresh,
+              int(per_image), _ptr(bg), _ptr(kb), B, P + 1, _stream())
+    return bg, kb
+
+
+def rollout(attn_mean: torch.Tensor) -> torch.Tensor:
+    """attn_mean [L,B,N,N] fp32 -> un-normalised rollout row [B,N-1] (predict.py:215-232)."""
+    L, B, N, _ = attn_mean.shape
+    out = torch.empty((B, N - 1), dtype=torch.float32, device=attn_mean.device)
+    _lib.call("vtc_rollout", _ptr(attn_mean, torch.float32), _ptr(out), L, B, N, _stream())
+    return out
+
+
+def cls_layer_map(cls_rows: torch.Tensor, first: int, last: int) -> torch.Tensor:
+    L, B, H, N = cls_rows.shape
+    out = torch.empty((B, N - 1), dtype=torch.float32, device=cls_rows.device)
+    _lib.call("vtc_cls_layer_map", _ptr(cls_rows, torch.float32), _ptr(out), L, first, last, B, H, N, _stream())
+    return out
+
+
+def cam_project(tokens: torch.Tensor, w: torch.Tensor, relu: bool = True, eps: float = 1e-5) -> torch.Tensor:
+    B, N, D = tokens.shape
+    Ccls = w.shape[0]
+    g = int(round((N - 1) ** 0.5))
+    out = torch.empty((B, Ccls, g, g), dtype=torch.float32, device=tokens.device)
+    _lib.call("vtc_cam_project", _ptr(tokens, torch.float32, "tokens"), _ptr(w, torch.float32, "w"), _ptr(out), B, N, D, Ccls,
+              int(relu), eps, _stream())
+    return out
+
+
+def normalize_max_(maps: torch.Tensor) -> torch.Tensor:
+    P = maps.shape[-1]
+    _lib.call("vtc_normalize_max", _ptr(maps, torch.float32), maps.numel() // P, P, _stream())
+    return maps
+
+
+def upsample_bilinear(maps: torch.Tensor, out_hw: Tuple[int, int], as_u8: bool = False) -> torch.Tensor:
+    """maps [..., g, g] fp32 -> [..., H, W] (fp32, or uint8 = trunc(255*v))."""
+    g = maps.shape[-1]
+    n = maps.numel() // (g * g)
+    H, W = out_hw
+    out = torch.empty((*maps.shape[:-2], H, W), dtype=torch.uint8 if as_u8 else torch.float32, device=maps.device)
+    _lib.call("vtc_upsample_bilinear_u8" if as_u8 else "vtc_upsample_bilinear", _ptr(maps, torch.float32), _ptr(out), n, g, H, W, _stream())
+    return out
+
+
+def cam_label(cam: torch.Tensor, labels: torch.Tensor, out_hw: Tuple[int, int], bg_thresh: float = 0.25) -> torch.Tensor:
+    B, Ccls, g, _ = cam.shape
+    H, W = out_hw
+    lab = labels.to(torch.uint8).contiguous()
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=cam.device)
+    _lib.call("vtc_cam_label", _ptr(cam, torch.float32), _ptr(lab, torch.uint8), bg_thresh, _ptr(out), B, Ccls, g, H, W, _stream())
+    return out
+
+
+def hwp_cos_vote(hwp_logits: torch.Tensor, head1_w: torch.Tensor, hwp_tokens: torch.Tensor, tokens: torch.Tensor,
+                 sig_thresh: float = 0.9) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, N, D = tokens.shape
+    K = hwp_tokens.shape[1]
+    Ccls = head1_w.shape[0]
+    g = int(round((N - 1) ** 0.5))
+    p2c = torch.empty((B, K), dtype=torch.int32, device=tokens.device)
+    cos = torch.empty((B, K, g, g), dtype=torch.float32, device=tokens.device)
+    _lib.call("vtc_hwp_cos_vote", _ptr(hwp_logits, torch.float32), _ptr(head1_w, torch.float32), _ptr(hwp_tokens, torch.float32),
+              _ptr(tokens, torch.float32), sig_thresh, _ptr(p2c), _ptr(cos), B, N, D, Ccls, K, _stream())
+    return p2c, cos
+
+
+def hwp_seg(cos: torch.Tensor, p2c: torch.Tensor, bg_map: torch.Tensor, out_hw: Tuple[int, int], cos_thresh: float = 0.5,
+            bg_thresh: float = 0.05) -> torch.Tensor:
+    B, K, g, _ = cos.shape
+    H, W = out_hw
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=cos.device)
+    _lib.call("vtc_hwp_seg", _ptr(cos, torch.float32), _ptr(p2c, torch.int32), _ptr(bg_map, torch.float32), cos_thresh, bg_thresh,
+              _ptr(out), B, K, g, H, W, _stream())
+    return out
+
+
+def confmat_update(mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
+    n = mat.shape[0]
+    _lib.call("vtc_confmat_update", _ptr(gt, torch.uint8, "gt"), _ptr(pred, torch.uint8, "pred"), gt.numel(), n,
+              _ptr(mat, torch.int64, "mat"), _stream())
+    return mat

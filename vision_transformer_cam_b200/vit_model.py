@@ -1,0 +1,469 @@
+"""Drop-in replacement for the reference `vit_model.py` on B200.
+
+Same public surface (`VisionTransformer`, `Block`, `Attention`, `Mlp`, `PatchEmbed`, `DropPath`, `drop_path`,
+`_init_vit_weights`, the eight `vit_*` factories), same constructor arguments, same parameter names / shapes /
+state_dict layout (incl. the unused `norm1[256]`, `norm2[32]` and the real `head1`), same RNG consumption at
+construction (so `torch.manual_seed(s); create_model(...)` yields the reference's weights), and the same 6-tuple
+from `forward` (reference vit_model.py:411-424).  The compute is not PyTorch: every forward runs the hand-written
+sm_100a kernels of libvtc.so through the C-ABI (`include/vtc.h`); there is no eager / CPU fallback.
+
+Differences, all deliberate: no import-time matplotlib / palette.json side effects; the
+hard-coded 197 tokens / 12 heads of the reference are generalised to N / H; inference only (no autograd graph).
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from dataclasses import dataclass
+from functools import partial
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+def drop_path(x, drop_prob: float = 0., training: bool = False):
+    """Stochastic depth per sample (reference vit_model.py:20-36).  Every factory uses rate 0, so this is the identity
+    on the fused path; kept for API compatibility."""
+    if drop_prob == 0. or not training:
+        return x
+    keep = 1.0 - drop_prob
+    mask = torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device).add_(keep).floor_()
+    return x.div(keep) * mask
+
+
+class DropPath(nn.Module):
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        return drop_path(x, self.drop_prob, self.training)
+
+
+# ---- per-module bf16 weight cache (module-level forwards only; the fused model packs its own) ---------------------
+def _bf16(param: torch.Tensor, cache: dict) -> torch.Tensor:
+    key = (param.data_ptr(), param._version, param.device)
+    hit = cache.get("w")
+    if hit is None or hit[0] != key:
+        cache["w"] = (key, ops.cast_bf16(param.detach().reshape(param.shape[0], -1).contiguous()))
+    return cache["w"][1]
+
+
+def _require_cuda(x: torch.Tensor, what: str) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: input is on {x.device}; this implementation runs on sm_100a CUDA devices only "
+                           "(no CPU fallback) -- move the model and the input to the GPU")
+
+
+def _linear_f32(x2d_bf16: torch.Tensor, lin: nn.Linear, cache: dict, gelu: bool = False, out_f32: bool = True) -> torch.Tensor:
+    w = _bf16(lin.weight, cache)
+    bias = lin.bias.detach() if lin.bias is not None else torch.zeros(lin.out_features, device=w.device)
+    if not out_f32:
+        return ops.gemm_bf16(x2d_bf16, w, bias, _lib.EPI_BIAS_GELU if gelu else _lib.EPI_BIAS)
+    zero = torch.zeros((x2d_bf16.shape[0], lin.out_features), dtype=torch.float32, device=w.device)
+    return ops.gemm_bf16(x2d_bf16, w, bias, _lib.EPI_BIAS_RESIDUAL, residual=zero, out=zero)
+
+
+class PatchEmbed(nn.Module):
+    """Image -> patch tokens (reference vit_model.py:51-83): a k=s=patch conv, i.e. patchify + GEMM."""
+
+    def __init__(self, img_size=224, patch_size=16, in_c=3, embed_dim=768, norm_layer=None):
+        super().__init__()
+        img_size = (img_size, img_size)
+        patch_size = (patch_size, patch_size)
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.grid_size = (img_size[0] // patch_size[0], img_size[1] // patch_size[1])
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.proj = nn.Conv2d(in_c, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
+        self._cache: dict = {}
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        assert H == self.img_size[0] and W == self.img_size[1], \
+            f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
+        _require_cuda(x, "PatchEmbed")
+        patches = ops.patchify(x.detach().float().contiguous(), self.patch_size[0])
+        w = _bf16(self.proj.weight, self._cache)
+        D = w.shape[0]
+        zero = torch.zeros((patches.shape[0], D), dtype=torch.float32, device=x.device)
+        out = ops.gemm_bf16(patches, w, self.proj.bias.detach(), _lib.EPI_BIAS_RESIDUAL, residual=zero, out=zero)
+        return self.norm(out.view(B, self.num_patches, D))
+
+
+class Attention(nn.Module):
+    """Multi-head attention with the reference's additive background mask (vit_model.py:86-140)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop_ratio=0., proj_drop_ratio=0.):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop_ratio)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop_ratio)
+        self._cq: dict = {}
+        self._cp: dict = {}
+
+    def forward(self, x, current_layer, mask_indices):
+        """x [B,N,C] fp32 -> (out [B,N,C] fp32, weights [B,H,N,N] fp32).  `mask_indices` [B,N,N] is the reference's
+        additive mask -100*min(v_i+v_j,1); it is applied for current_layer > 4 exactly as a per-key bias (row 0 of the
+        mask, v_0 = 0; rows with v_i = 1 only receive a softmax-invariant constant)."""
+        _require_cuda(x, "Attention")
+        B, N, C = x.shape
+        xb = ops.cast_bf16(x.detach().float().contiguous()).view(B * N, C)
+        qkv = _linear_f32(xb, self.qkv, self._cq, out_f32=False).view(B, N, 3 * C)
+        kb = None
+        if current_layer > 4 and mask_indices is not None:
+            kb = mask_indices[:, 0, :].to(device=x.device, dtype=torch.float32).contiguous()
+        o, _, weights = ops.attention(qkv, self.num_heads, float(self.scale), key_bias=kb, want_cls=False, want_attn=True)
+        out = _linear_f32(o.view(B * N, C), self.proj, self._cp).view(B, N, C)
+        return out, weights
+
+
+class Mlp(nn.Module):
+    """fc1 -> GELU(erf) -> fc2 (reference vit_model.py:143-164); GELU is fused into the fc1 GEMM epilogue."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+        self._c1: dict = {}
+        self._c2: dict = {}
+
+    def forward(self, x):
+        _require_cuda(x, "Mlp")
+        shp = x.shape
+        xb = ops.cast_bf16(x.detach().float().contiguous()).view(-1, shp[-1])
+        h = _linear_f32(xb, self.fc1, self._c1, gelu=True, out_f32=False)
+        return _linear_f32(h, self.fc2, self._c2).view(*shp[:-1], -1)
+
+
+class Block(nn.Module):
+    """Pre-norm transformer block (reference vit_model.py:167-200)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_ratio=0., attn_drop_ratio=0.,
+                 drop_path_ratio=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                              attn_drop_ratio=attn_drop_ratio, proj_drop_ratio=drop_ratio)
+        self.drop_path = DropPath(drop_path_ratio) if drop_path_ratio > 0. else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop_ratio)
+
+    def forward(self, x, current_layer, mask_indices):
+        _require_cuda(x, "Block")
+        B, N, C = x.shape
+        x = x.detach().float().contiguous()
+        a = self.attn
+        y = ops.layernorm_bf16(x, self.norm1.weight.detach(), self.norm1.bias.detach(), self.norm1.eps).view(B * N, C)
+        qkv = _linear_f32(y, a.qkv, a._cq, out_f32=False).view(B, N, 3 * C)
+        kb = None
+        if current_layer > 4 and mask_indices is not None:
+            kb = mask_indices[:, 0, :].to(device=x.device, dtype=torch.float32).contiguous()
+        o, _, weights = ops.attention(qkv, a.num_heads, float(a.scale), key_bias=kb, want_cls=False, want_attn=True)
+        x1 = ops.gemm_bf16(o.view(B * N, C), _bf16(a.proj.weight, a._cp), a.proj.bias.detach(), _lib.EPI_BIAS_RESIDUAL,
+                           residual=x.view(B * N, C))
+        y2 = ops.layernorm_bf16(x1, self.norm2.weight.detach(), self.norm2.bias.detach(), self.norm2.eps)
+        h = _linear_f32(y2, self.mlp.fc1, self.mlp._c1, gelu=True, out_f32=False)
+        x2 = ops.gemm_bf16(h, _bf16(self.mlp.fc2.weight, self.mlp._c2), self.mlp.fc2.bias.detach(), _lib.EPI_BIAS_RESIDUAL,
+                           residual=x1, out=x1)
+        return x2.view(B, N, C), weights
+
+
+@dataclass
+class CamForward:
+    """Compact outputs of `VisionTransformer.forward_cam` (everything the CAM / rollout / pseudo-label code consumes)."""
+    logits: torch.Tensor                 # [B,C]
+    hwp_logits: torch.Tensor             # [B,C]
+    hwp_tokens: torch.Tensor             # [B,K,D]
+    topk_idx: torch.Tensor               # [B,K] int32
+    tokens: torch.Tensor                 # [Lt,B,N,D] trailing block outputs (tokens[-1] = block-L output)
+    cls_rows: torch.Tensor               # [L,B,H,N]
+    attn: Optional[torch.Tensor] = None       # [La,B,H,N,N]
+    attn_mean: Optional[torch.Tensor] = None  # [L,B,N,N]
+    bg: Optional[torch.Tensor] = None         # [L,B,P] uint8
+    cls_map: Optional[torch.Tensor] = None    # [L,B,P]
+
+    @property
+    def tokens_last(self) -> torch.Tensor:
+        return self.tokens[-1]
+
+
+class _Engine:
+    """Owns the libvtc model handle, the packed bf16 weights and the workspace for one VisionTransformer."""
+
+    def __init__(self, model: "VisionTransformer"):
+        self.lib = _lib.load()
+        pe = model.patch_embed
+        cfg = _lib.Config(img_size=pe.img_size[0], patch_size=pe.patch_size[0], in_c=pe.proj.in_channels,
+                          num_classes=model.num_classes, embed_dim=model.embed_dim, depth=len(model.blocks),
+                          num_heads=model.blocks[0].attn.num_heads, mlp_hidden=model.blocks[0].mlp.fc1.out_features,
+                          representation_size=model.num_features if model.has_logits else 0,
+                          mask_from=4, mask_thresh=0.25, topk=16, ln_eps=float(model.norm.eps))
+        self.cfg = cfg
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.vtc_model_create(ctypes.byref(cfg), ctypes.byref(handle)), "vtc_model_create")
+        self.handle = handle
+        self.packed: Optional[torch.Tensor] = None
+        self.key = None
+        self.ws: Optional[torch.Tensor] = None
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.vtc_model_destroy(self.handle)
+        except Exception:
+            pass
+
+    def ensure_packed(self, model: "VisionTransformer", device: torch.device) -> None:
+        params = dict(model.named_parameters())
+        key = (device, tuple((p.data_ptr(), p._version) for p in params.values()))
+        if key == self.key:
+            return
+        for n, p in params.items():
+            if p.device != device:
+                raise RuntimeError(f"parameter {n} is on {p.device}, input on {device}")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError(f"parameter {n} must be contiguous fp32")
+        L = len(model.blocks)
+        layers = (_lib.LayerWeights * L)()
+        for i, blk in enumerate(model.blocks):
+            lw = layers[i]
+            lw.norm1_w, lw.norm1_b = blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr()
+            lw.qkv_w, lw.qkv_b = blk.attn.qkv.weight.data_ptr(), blk.attn.qkv.bias.data_ptr()
+            lw.proj_w, lw.proj_b = blk.attn.proj.weight.data_ptr(), blk.attn.proj.bias.data_ptr()
+            lw.norm2_w, lw.norm2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
+            lw.fc1_w, lw.fc1_b = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc1.bias.data_ptr()
+            lw.fc2_w, lw.fc2_b = blk.mlp.fc2.weight.data_ptr(), blk.mlp.fc2.bias.data_ptr()
+        w = _lib.Weights()
+        w.cls_token, w.pos_embed = model.cls_token.data_ptr(), model.pos_embed.data_ptr()
+        w.patch_w, w.patch_b = model.patch_embed.proj.weight.data_ptr(), model.patch_embed.proj.bias.data_ptr()
+        w.norm_w, w.norm_b = model.norm.weight.data_ptr(), model.norm.bias.data_ptr()
+        if model.has_logits:
+            w.pre_w, w.pre_b = model.pre_logits.fc.weight.data_ptr(), model.pre_logits.fc.bias.data_ptr()
+        w.head_w, w.head_b = model.head.weight.data_ptr(), model.head.bias.data_ptr()
+        w.head1_w, w.head1_b = model.head1.weight.data_ptr(), model.head1.bias.data_ptr()
+        w.layers = layers
+        w.num_layers = L
+        nbytes = self.lib.vtc_model_packed_bytes(self.handle)
+        if self.packed is None or self.packed.device != device or self.packed.numel() < nbytes:
+            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(self.lib.vtc_model_pack_weights(self.handle, ctypes.byref(w), self.packed.data_ptr(), nbytes,
+                                                   torch.cuda.current_stream(device).cuda_stream), "vtc_model_pack_weights")
+        self.key = key
+        self._keep = (layers, w)
+
+    def run(self, model: "VisionTransformer", x: torch.Tensor, tokens_layers: int, attn_layers: int, attn_mean: bool, bg: bool,
+            cls_map: bool, mask_norm: str, forced_bg: Optional[Dict[int, torch.Tensor]], forced_topk: Optional[torch.Tensor]) -> CamForward:
+        dev = x.device
+        cfg = self.cfg
+        B = x.shape[0]
+        g = cfg.img_size // cfg.patch_size
+        P, N, D, H, L, Ccls, K = g * g, g * g + 1, cfg.embed_dim, cfg.num_heads, cfg.depth, cfg.num_classes, cfg.topk
+        with torch.cuda.device(dev):
+            self.ensure_packed(model, dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            out = CamForward(
+                logits=torch.empty((B, Ccls), **f32), hwp_logits=torch.empty((B, Ccls), **f32),
+                hwp_tokens=torch.empty((B, K, D), **f32), topk_idx=torch.empty((B, K), dtype=torch.int32, device=dev),
+                tokens=torch.empty((tokens_layers, B, N, D), **f32), cls_rows=torch.empty((L, B, H, N), **f32))
+            if attn_layers > 0:
+                out.attn = torch.empty((attn_layers, B, H, N, N), **f32)
+            if attn_mean:
+                out.attn_mean = torch.empty((L, B, N, N), **f32)
+            if bg:
+                out.bg = torch.empty((L, B, P), dtype=torch.uint8, device=dev)
+            if cls_map:
+                out.cls_map = torch.empty((L, B, P), **f32)
+            o = _lib.Outputs(logits=out.logits.data_ptr(), hwp_logits=out.hwp_logits.data_ptr(), hwp_tokens=out.hwp_tokens.data_ptr(),
+                             topk_idx=out.topk_idx.data_ptr(), tokens=out.tokens.data_ptr(), tokens_layers=tokens_layers,
+                             cls_rows=out.cls_rows.data_ptr(), attn=out.attn.data_ptr() if out.attn is not None else None,
+                             attn_layers=attn_layers, attn_mean=out.attn_mean.data_ptr() if attn_mean else None,
+                             bg=out.bg.data_ptr() if bg else None, cls_map=out.cls_map.data_ptr() if cls_map else None)
+            forcing = None
+            keep = []
+            if forced_bg or forced_topk is not None:
+                forcing = _lib.Forcing()
+                if forced_bg:
+                    buf = torch.zeros((L, B, P), dtype=torch.uint8, device=dev)
+                    mask = 0
+                    for l, v in forced_bg.items():
+                        buf[l] = v.to(device=dev, dtype=torch.uint8)
+                        mask |= 1 << l
+                    forcing.bg, forcing.bg_layer_mask = buf.data_ptr(), mask
+                    keep.append(buf)
+                if forced_topk is not None:
+                    tk = forced_topk.to(device=dev, dtype=torch.int32).contiguous()
+                    forcing.topk_idx = tk.data_ptr()
+                    keep.append(tk)
+            need = self.lib.vtc_workspace_bytes(self.handle, B, ctypes.byref(o))
+            if self.ws is None or self.ws.device != dev or self.ws.numel() < need:
+                self.ws = None
+                self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            flags = _lib.FWD_MASK_NORM_IMAGE if mask_norm == "image" else 0
+            _lib.check(self.lib.vtc_forward(self.handle, x.data_ptr(), B, ctypes.byref(o),
+                                            ctypes.byref(forcing) if forcing is not None else None, self.ws.data_ptr(),
+                                            self.ws.numel(), flags, torch.cuda.current_stream(dev).cuda_stream), "vtc_forward")
+            del keep
+        return out
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img_size=224, patch_size=16, in_c=3, num_classes=1000,
+                 embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0, qkv_bias=True,
+                 qk_scale=None, representation_size=None, distilled=False, drop_ratio=0.,
+                 attn_drop_ratio=0., drop_path_ratio=0., embed_layer=PatchEmbed, norm_layer=None,
+                 act_layer=None, is_train=True):
+        """Arguments as in the reference (vit_model.py:215-219).  `distilled` models are not supported (the reference's
+        own forward cannot run them); dropout / drop-path rates must be 0 (every factory's value)."""
+        super().__init__()
+        if distilled:
+            raise NotImplementedError("distilled ViT: unreachable in the reference forward (vit_model.py:404-412)")
+        if drop_ratio or attn_drop_ratio or drop_path_ratio:
+            raise NotImplementedError("non-zero dropout / drop-path: the fused inference path has no stochastic ops")
+        if not qkv_bias:
+            raise NotImplementedError("qkv_bias=False is not used by any reference factory")
+        self.num_classes = num_classes
+        self.num_features = self.embed_dim = embed_dim
+        self.num_tokens = 1
+        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
+        act_layer = act_layer or nn.GELU
+
+        # construction order == the reference's, so the RNG stream (default nn inits) is consumed identically
+        self.patch_embed = embed_layer(img_size=img_size, patch_size=patch_size, in_c=in_c, embed_dim=embed_dim)
+        num_patches = self.patch_embed.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.dist_token = None
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + self.num_tokens, embed_dim))
+        self.pos_drop = nn.Dropout(p=drop_ratio)
+        self.blocks = nn.Sequential(*[
+            Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                  drop_ratio=drop_ratio, attn_drop_ratio=attn_drop_ratio, drop_path_ratio=0.,
+                  norm_layer=norm_layer, act_layer=act_layer)
+            for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        if representation_size:
+            self.has_logits = True
+            self.num_features = representation_size
+            self.pre_logits = nn.Sequential(OrderedDict([("fc", nn.Linear(embed_dim, representation_size)), ("act", nn.Tanh())]))
+        else:
+            self.has_logits = False
+            self.pre_logits = nn.Identity()
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+        self.head_dist = None
+
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+        self.apply(_init_vit_weights)
+
+        # created after the init pass -> default nn init, exactly like the reference (vit_model.py:292-295)
+        self.norm1 = norm_layer(256)
+        self.norm2 = norm_layer(32)
+        self.head1 = nn.Linear(self.num_features, num_classes)
+        self.relu = nn.ReLU()
+        self.is_train = is_train
+        self.final_seg_count = 0
+        self._engine: Optional[_Engine] = None
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None          # the libvtc handle is process-local; it is rebuilt lazily
+        return state
+
+    # -- fused path -----------------------------------------------------------------------------------------------
+    def _check_input(self, x: torch.Tensor) -> torch.Tensor:
+        B, C, H, W = x.shape
+        isz = self.patch_embed.img_size
+        assert H == isz[0] and W == isz[1], f"Input image size ({H}*{W}) doesn't match model ({isz[0]}*{isz[1]})."
+        _require_cuda(x, "VisionTransformer")
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        return x.contiguous()
+
+    @torch.no_grad()
+    def forward_cam(self, x: torch.Tensor, tokens_layers: int = 1, attn_layers: int = 0, attn_mean: bool = False,
+                    bg: bool = False, cls_map: bool = False, mask_norm: str = "batch",
+                    forced_bg: Optional[Dict[int, torch.Tensor]] = None, forced_topk: Optional[torch.Tensor] = None) -> CamForward:
+        """Fused forward with compact outputs (no [B,H,N,N] tensors unless `attn_layers` > 0)."""
+        assert mask_norm in ("batch", "image")
+        x = self._check_input(x)
+        if self._engine is None:
+            self._engine = _Engine(self)
+        return self._engine.run(self, x, tokens_layers, attn_layers, attn_mean, bg, cls_map, mask_norm, forced_bg, forced_topk)
+
+    def forward(self, x):
+        """Reference-compatible 6-tuple (vit_model.py:424): (logits [B,C], attn_weights list of [B,H,N,N], attn_matrix list
+        of [B,N,D], hwp logits [B,C], head1.weight.data [C,D], hwp tokens [B,16,D]); the lists hold the last
+        min(depth,12) layers (vit_model.py:322)."""
+        keep = min(len(self.blocks), 12)
+        o = self.forward_cam(x, tokens_layers=keep, attn_layers=keep)
+        attn_weights = [o.attn[i] for i in range(keep)]
+        attn_matrix = [o.tokens[i] for i in range(keep)]
+        return o.logits, attn_weights, attn_matrix, o.hwp_logits, self.head1.weight.data, o.hwp_tokens
+
+
+def _init_vit_weights(m):
+    """ViT weight initialisation (reference vit_model.py:427-442)."""
+    if isinstance(m, nn.Linear):
+        nn.init.trunc_normal_(m.weight, std=.01)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+    elif isinstance(m, nn.Conv2d):
+        nn.init.kaiming_normal_(m.weight, mode="fan_out")
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+    elif isinstance(m, nn.LayerNorm):
+        nn.init.zeros_(m.bias)
+        nn.init.ones_(m.weight)
+
+
+# ---- factories (reference vit_model.py:445-577): same names, arguments and hyper-parameters -------------------------
+def _vit(patch, dim, depth, heads, num_classes, rep):
+    return VisionTransformer(img_size=224, patch_size=patch, embed_dim=dim, depth=depth, num_heads=heads,
+                             representation_size=rep, num_classes=num_classes)
+
+
+def vit_base_patch16_224(num_classes: int = 1000):
+    return _vit(16, 768, 12, 12, num_classes, None)
+
+
+def vit_base_patch16_224_in21k(num_classes: int = 21843, has_logits: bool = True):
+    return _vit(16, 768, 12, 12, num_classes, 768 if has_logits else None)
+
+
+def vit_base_patch32_224(num_classes: int = 1000):
+    return _vit(32, 768, 12, 12, num_classes, None)
+
+
+def vit_base_patch32_224_in21k(num_classes: int = 21843, has_logits: bool = True):
+    return _vit(32, 768, 12, 12, num_classes, 768 if has_logits else None)
+
+
+def vit_large_patch16_224(num_classes: int = 1000):
+    return _vit(16, 1024, 24, 16, num_classes, None)
+
+
+def vit_large_patch16_224_in21k(num_classes: int = 21843, has_logits: bool = True):
+    return _vit(16, 1024, 24, 16, num_classes, 1024 if has_logits else None)
+
+
+def vit_large_patch32_224_in21k(num_classes: int = 21843, has_logits: bool = True):
+    return _vit(32, 1024, 24, 16, num_classes, 1024 if has_logits else None)
+
+
+def vit_huge_patch14_224_in21k(num_classes: int = 21843, has_logits: bool = True):
+    """ViT-H/14: constructible (state_dict parity) but the fused path rejects patch 14 / head_dim 80 at the first forward."""
+    return _vit(14, 1280, 32, 16, num_classes, 1280 if has_logits else None)
