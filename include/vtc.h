@@ -166,7 +166,9 @@ VTC_API int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, f
 VTC_API int vtc_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim,
                        float eps, void* stream);
 /* Attention core (vit_model.py:113-137): qkv bf16 [B,N,3,H,64] -> out bf16 [B,N,H*64];
- * key_bias [B,N] additive logit bias per key (0 / -100, pre-multiplied by nothing) or NULL (vit_model.py:118-124);
+ * key_bias [B,N] = -100*v (v = background vector incl. the CLS entry 0) or NULL: the reference mask
+ * -100*min(v_i+v_j,1) (vit_model.py:118-124,348-361), i.e. key j is biased by key_bias[j] on query rows with v_i = 0
+ * and rows with v_i = 1 stay unmasked (their uniform -100 is softmax-invariant);
  * cls_rows [B,H,N] fp32 (P[b,h,0,:]) or NULL; attn [B,H,N,N] fp32 full P or NULL. */
 VTC_API int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
                   int32_t n_tokens, int32_t heads, float scale, void* stream);

@@ -158,9 +158,17 @@ def main():
             store["layer_maps14"] = m14
             cam = PP.classic_cam(out[2][-1], out[4])
             store["classic_cam"] = cam.numpy()
-            labels = (torch.sigmoid(out[3]) >= 0.9).float()
+            # image-level labels for the label-restricted pseudo label (utils.py:100-108): a row of the reference's own
+            # voc12/cls_labels.npy with two classes (VOC mean is 1.55 labels / image)
+            cls_labels = np.load(os.path.join(ref_shim.REFERENCE_DIR, "voc12", "cls_labels.npy"), allow_pickle=True).item()
+            two = sorted(k for k, v in cls_labels.items() if v.sum() == 2)[0]
+            labels = torch.from_numpy(cls_labels[two].astype(np.float32))[None]
+            rep["cam_label_source_image"] = str(two)
             store["cam_label"] = PP.cam_pseudo_label(cam, labels, (h, w)).numpy()
             store["cam_labels_in"] = labels.numpy()
+            labels_sig = (torch.sigmoid(out[3]) >= 0.9).float()          # validate.py:132-134 label set (8 of 20 here)
+            store["cam_label_sig"] = PP.cam_pseudo_label(cam, labels_sig, (h, w)).numpy()
+            store["cam_labels_sig_in"] = labels_sig.numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
     with open(os.path.join(HERE, "REPORT.json"), "w") as f:
         json.dump(report, f, indent=1)

@@ -131,8 +131,9 @@ def _attn_ref(qkv, H, scale, kb):
     D = D3 // 3
     q, k, v = qkv.float().view(B, N, 3, H, D // H).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-2, -1)) * scale
-    if kb is not None:
-        s = s + kb[:, None, None, :]
+    if kb is not None:                       # reference mask: -100 * min(v_i + v_j, 1)  (vit_model.py:348-361)
+        v_ = (kb != 0).float()
+        s = s - 100.0 * torch.clamp(v_[:, :, None] + v_[:, None, :], max=1.0)[:, None]
     p = s.softmax(-1)
     o = (p @ v).transpose(1, 2).reshape(B, N, D)
     return o, p

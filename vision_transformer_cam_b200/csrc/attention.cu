@@ -1,5 +1,6 @@
 // Fused multi-head attention for the ViT blocks (vit_model.py:113-137): per (image, head)
-//   S = Q K^T * scale (+ per-key bias of the layer>4 background mask), P = softmax(S), O = P V
+//   S = Q K^T * scale (+ the layer>4 background mask: -100 on background keys, for foreground query rows),
+//   P = softmax(S), O = P V
 // with both contractions on tcgen05 (S and O accumulate in TMEM) and the softmax in fp32 registers.  Besides O the
 // kernel emits what the reference reads back from the full P tensor: the CLS query row P[b,h,0,:] (mask builder,
 // top-k head, per-layer maps) and, on request, the whole P (the 6-tuple's attn_weights / the rollout's head mean).
@@ -155,6 +156,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
             const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * 256;
             const int nchunks = (N + 31) >> 5;
             const float sc = p.scale_log2;
+            // The reference mask is -100*min(v_i + v_j, 1) (vit_model.py:348-361): a query row that is itself background
+            // (v_i = 1) receives a uniform -100, i.e. no masking at all; only foreground rows see the per-key bias.
+            const float rb = (row < N && kb_s[row] != 0.f) ? 0.f : 1.f;
 
             mbar_wait(&s_full[tile], 0);
             tc_fence_after();
@@ -167,7 +171,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int col = c * 32 + j;
-                    const float x = fmaf(__uint_as_float(r[j]), sc, kb_s[col]);
+                    const float x = fmaf(__uint_as_float(r[j]), sc, rb * kb_s[col]);
                     if (col < N) m = fmaxf(m, x);
                 }
             }
@@ -183,8 +187,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     const int col = c * 32 + j;
-                    float e0 = exp2f(fmaf(__uint_as_float(r[j]), sc, kb_s[col]) - m);
-                    float e1 = exp2f(fmaf(__uint_as_float(r[j + 1]), sc, kb_s[col + 1]) - m);
+                    float e0 = exp2f(fmaf(__uint_as_float(r[j]), sc, rb * kb_s[col]) - m);
+                    float e1 = exp2f(fmaf(__uint_as_float(r[j + 1]), sc, rb * kb_s[col + 1]) - m);
                     if (col >= N) e0 = 0.f;
                     if (col + 1 >= N) e1 = 0.f;
                     sum += e0 + e1;
@@ -212,7 +216,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = c * 32 + j;
-                        if (wr && col < N) dst[col] = exp2f(fmaf(__uint_as_float(r[j]), sc, kb_s[col]) - m) * inv;
+                        if (wr && col < N) dst[col] = exp2f(fmaf(__uint_as_float(r[j]), sc, rb * kb_s[col]) - m) * inv;
                     }
                 }
             }
