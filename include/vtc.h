@@ -122,6 +122,8 @@ VTC_API int vtc_version(void);
 VTC_API const char* vtc_last_error(void);
 /* VTC_OK iff the current CUDA device is sm_100 class (compute capability 10.x). */
 VTC_API int vtc_check_device(void);
+/* number of CUDA kernels this library has launched in this process (every vtc_* kernel launch counts once) */
+VTC_API uint64_t vtc_launch_count(void);
 
 /* replaces VisionTransformer.__init__ shape bookkeeping (vit_model.py:215-301) */
 VTC_API int vtc_model_create(const vtc_config* cfg, vtc_model** out);
@@ -141,6 +143,18 @@ VTC_API size_t vtc_workspace_bytes(const vtc_model* m, int32_t batch, const vtc_
  * background mask, high-weight-patch head, final norm + head.  x: [B,in_c,S,S] fp32 NCHW. */
 VTC_API int vtc_forward(vtc_model* m, const float* x, int32_t batch, const vtc_outputs* outs, const vtc_forcing* forcing,
                 void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* ---- per-kernel timing of the forward (bench.py's roofline numbers) -----------------------------
+ * When enabled, vtc_forward brackets every kernel launch with CUDA events on the launch stream;
+ * vtc_model_profile_read synchronises on them and ADDS the elapsed milliseconds / launch counts per kind
+ * into the caller's arrays (length VTC_PROF_KINDS), then forgets the recorded spans. */
+enum {
+    VTC_PROF_PATCHIFY = 0, VTC_PROF_GEMM_PATCH = 1, VTC_PROF_LAYERNORM = 2, VTC_PROF_GEMM_QKV = 3, VTC_PROF_ATTENTION = 4,
+    VTC_PROF_GEMM_PROJ = 5, VTC_PROF_GEMM_FC1 = 6, VTC_PROF_GEMM_FC2 = 7, VTC_PROF_CLS = 8, VTC_PROF_HEAD_MEAN = 9,
+    VTC_PROF_HEADS = 10, VTC_PROF_KINDS = 11
+};
+VTC_API int vtc_model_profile(vtc_model* m, int32_t enable);
+VTC_API int vtc_model_profile_read(vtc_model* m, float* ms_per_kind, int32_t* launches_per_kind);
 
 /* ---- per-kernel entry points (unit parity; the model forward is built from these) -------------- */
 enum { VTC_EPI_BIAS = 0, VTC_EPI_BIAS_GELU = 1, VTC_EPI_BIAS_RESIDUAL = 2, VTC_EPI_PATCH_EMBED = 3 };

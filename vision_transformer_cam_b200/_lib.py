@@ -14,6 +14,7 @@ ERR_NAMES = {-1: "VTC_ERR_ARG", -2: "VTC_ERR_SHAPE", -3: "VTC_ERR_ARCH", -4: "VT
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_PATCH_EMBED = 0, 1, 2, 3
 FWD_MASK_NORM_IMAGE = 1 << 0
 FWD_FP32_SPLIT = 1 << 1
+PROF_KINDS = ("patchify", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "cls", "head_mean", "heads")
 
 c_f32p = C.c_void_p   # device pointers are passed as integers
 
@@ -59,6 +60,9 @@ SIGNATURES = {
     "vtc_version": (C.c_int, []),
     "vtc_last_error": (C.c_char_p, []),
     "vtc_check_device": (C.c_int, []),
+    "vtc_launch_count": (C.c_uint64, []),
+    "vtc_model_profile": (C.c_int, [_P, _I]),
+    "vtc_model_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "vtc_model_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "vtc_model_destroy": (C.c_int, [_P]),
     "vtc_model_packed_bytes": (_Z, [_P]),

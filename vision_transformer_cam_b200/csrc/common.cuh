@@ -21,7 +21,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_e != cudaSuccess) return ::vtc::cuda_fail(_e, #expr, __FILE__, __LINE__); \
     } while (0)
 
-#define VTC_CHECK_LAUNCH() VTC_CUDA(cudaGetLastError())
+void note_launch();   // global kernel-launch counter (vtc_launch_count)
+
+#define VTC_CHECK_LAUNCH()             \
+    do {                               \
+        ::vtc::note_launch();          \
+        VTC_CUDA(cudaGetLastError());  \
+    } while (0)
 
 #define VTC_REQUIRE(cond, code, ...)                 \
     do {                                             \

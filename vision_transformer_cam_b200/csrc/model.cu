@@ -16,6 +16,10 @@ struct vtc_model {
     struct LayerPacked { const __nv_bfloat16 *qkv, *proj, *fc1, *fc2; };
     std::vector<LayerPacked> lp;
     bool packed = false;
+    // optional per-kernel timing (vtc_model_profile)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;     // pool, two events per span
+    std::vector<int> prof_kind;           // kind of span i (events 2i, 2i+1)
 };
 
 namespace vtc {
@@ -59,6 +63,31 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     return ws;
 }
 
+struct Span {
+    vtc_model* m;
+    cudaStream_t st;
+    bool on;
+    Span(vtc_model* m_, cudaStream_t st_, int kind) : m(m_), st(st_), on(m_->prof_on) {
+        if (!on) return;
+        const size_t i = m->prof_kind.size();
+        while (m->prof_ev.size() < 2 * (i + 1)) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+            m->prof_ev.push_back(e);
+        }
+        m->prof_kind.push_back(kind);
+        cudaEventRecord(m->prof_ev[2 * i], st);
+    }
+    ~Span() {
+        if (on) cudaEventRecord(m->prof_ev[2 * (m->prof_kind.size() - 1) + 1], st);
+    }
+};
+#define VTC_STEP(kind, call)                       \
+    do {                                           \
+        Span _span(m, st, kind);                   \
+        if ((rc = (call)) != VTC_OK) return rc;    \
+    } while (0)
+
 static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, const vtc_forcing* f, void* workspace, size_t ws_bytes,
                    uint32_t flags, cudaStream_t st) {
     VTC_REQUIRE(m && x && o && workspace, VTC_ERR_ARG, "forward: null pointer");
@@ -84,10 +113,9 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
 
     // ---- patch embedding + token assembly (vit_model.py:306-314)
     float* t_cur = ws.tok;
-    if ((rc = patchify(x, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st)) != VTC_OK) return rc;
-    if ((rc = cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st)) != VTC_OK) return rc;
-    if ((rc = gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st)) != VTC_OK)
-        return rc;
+    VTC_STEP(VTC_PROF_PATCHIFY, patchify(x, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st));
+    VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));
+    VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st));
     VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * L, st));
     if (o->bg) VTC_CUDA(cudaMemsetAsync(o->bg, 0, static_cast<size_t>(L) * B * P, st));
 
@@ -105,32 +133,33 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
         if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
         else if (o->attn_mean) attn_l = ws.attn_tmp;
 
-        if ((rc = layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st)) != VTC_OK) return rc;
-        if ((rc = gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st)) != VTC_OK) return rc;
+        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st));
+        VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st));
         const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
-        if ((rc = attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st)) != VTC_OK) return rc;
-        if ((rc = gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st)) != VTC_OK) return rc;
-        if ((rc = layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st)) != VTC_OK) return rc;
-        if ((rc = gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st)) != VTC_OK) return rc;
-        if ((rc = gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st)) != VTC_OK) return rc;
+        VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st));
+        VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st));
+        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st));
+        VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st));
+        VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st));
         t_cur = t_out;
 
-        if (o->attn_mean && (rc = head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st)) != VTC_OK) return rc;
+        if (o->attn_mean) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));
         if (want_map) {
             float* map_l = o->cls_map ? o->cls_map + static_cast<size_t>(l) * B * P : ws.cls_map;
-            if ((rc = cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st)) != VTC_OK) return rc;
+            VTC_STEP(VTC_PROF_CLS, cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st));
             last_map = map_l;
             if (l >= m->cfg.mask_from) {                                                                        // vit_model.py:325
                 const uint8_t* forced = (f && f->bg && (f->bg_layer_mask >> l & 1u)) ? f->bg + static_cast<size_t>(l) * B * P : nullptr;
                 uint8_t* bg_l = o->bg ? o->bg + static_cast<size_t>(l) * B * P : nullptr;
-                if ((rc = cls_mask(map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, B, N, st)) != VTC_OK) return rc;
+                VTC_STEP(VTC_PROF_CLS, cls_mask(map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, B, N, st));
                 have_bias = true;
             }
         }
     }
     HeadParams hp{m->w.norm_w, m->w.norm_b, m->w.pre_w, m->w.pre_b, m->w.head_w, m->w.head_b, m->w.head1_w, m->w.head1_b,
                   D, m->R, m->C, m->cfg.topk, N, m->cfg.ln_eps};
-    return topk_heads(hp, t_cur, last_map, f ? f->topk_idx : nullptr, o->logits, o->hwp_logits, o->hwp_tokens, o->topk_idx, B, st);
+    VTC_STEP(VTC_PROF_HEADS, topk_heads(hp, t_cur, last_map, f ? f->topk_idx : nullptr, o->logits, o->hwp_logits, o->hwp_tokens, o->topk_idx, B, st));
+    return VTC_OK;
 }
 
 }  // namespace vtc
@@ -170,7 +199,30 @@ int vtc_model_create(const vtc_config* cfg, vtc_model** out) {
 }
 
 int vtc_model_destroy(vtc_model* m) {
+    if (m) for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
     delete m;
+    return VTC_OK;
+}
+
+int vtc_model_profile(vtc_model* m, int32_t enable) {
+    using namespace vtc;
+    VTC_REQUIRE(m, VTC_ERR_ARG, "profile: null model");
+    m->prof_on = enable != 0;
+    m->prof_kind.clear();
+    return VTC_OK;
+}
+
+int vtc_model_profile_read(vtc_model* m, float* ms_per_kind, int32_t* launches_per_kind) {
+    using namespace vtc;
+    VTC_REQUIRE(m && ms_per_kind && launches_per_kind, VTC_ERR_ARG, "profile_read: null pointer");
+    for (size_t i = 0; i < m->prof_kind.size(); ++i) {
+        VTC_CUDA(cudaEventSynchronize(m->prof_ev[2 * i + 1]));
+        float ms = 0.f;
+        VTC_CUDA(cudaEventElapsedTime(&ms, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+        ms_per_kind[m->prof_kind[i]] += ms;
+        launches_per_kind[m->prof_kind[i]] += 1;
+    }
+    m->prof_kind.clear();
     return VTC_OK;
 }
 

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -10,6 +11,9 @@
 namespace vtc {
 
 static thread_local char g_last_error[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_last_error(const char* fmt, ...) {
     va_list ap;
@@ -108,4 +112,5 @@ extern "C" {
 int vtc_version(void) { return VTC_VERSION; }
 const char* vtc_last_error(void) { return vtc::g_last_error; }
 int vtc_check_device(void) { return vtc::check_arch(); }
+uint64_t vtc_launch_count(void) { return vtc::g_launches.load(std::memory_order_relaxed); }
 }

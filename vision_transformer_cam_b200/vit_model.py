@@ -227,6 +227,17 @@ class _Engine:
         except Exception:
             pass
 
+    def profile(self, enable: bool) -> None:
+        _lib.check(self.lib.vtc_model_profile(self.handle, int(enable)), "vtc_model_profile")
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """Per-kernel-kind (milliseconds, launches) accumulated since the last read (synchronises on the recorded events)."""
+        n = len(_lib.PROF_KINDS)
+        ms = (ctypes.c_float * n)()
+        cnt = (ctypes.c_int32 * n)()
+        _lib.check(self.lib.vtc_model_profile_read(self.handle, ms, cnt), "vtc_model_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROF_KINDS)}
+
     def ensure_packed(self, model: "VisionTransformer", device: torch.device) -> None:
         params = dict(model.named_parameters())
         key = (device, tuple((p.data_ptr(), p._version) for p in params.values()))
@@ -403,6 +414,16 @@ class VisionTransformer(nn.Module):
         if self._engine is None:
             self._engine = _Engine(self)
         return self._engine.run(self, x, tokens_layers, attn_layers, attn_mean, bg, cls_map, mask_norm, forced_bg, forced_topk)
+
+    def kernel_profile(self, enable: Optional[bool] = None):
+        """enable/disable CUDA-event timing of every kernel of the fused forward, or (no argument) read the accumulated
+        {kind: (ms, launches)} table.  Used by bench.py for the roofline numbers."""
+        if self._engine is None:
+            self._engine = _Engine(self)
+        if enable is None:
+            return self._engine.profile_read()
+        self._engine.profile(enable)
+        return None
 
     def forward(self, x):
         """Reference-compatible 6-tuple (vit_model.py:424): (logits [B,C], attn_weights list of [B,H,N,N], attn_matrix list
