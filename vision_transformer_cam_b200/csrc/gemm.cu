@@ -7,7 +7,10 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 per instruction)
 //   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns, bias/GELU/residual in registers, vector stores.
 //               Two TMEM accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "ops.h"
 #include "tma_host.h"
 
 namespace vtc {
@@ -162,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         float v2 = __uint_as_float(r[4 * j + 2]) + b4.z;
                         float v3 = __uint_as_float(r[4 * j + 3]) + b4.w;
                         if (EPI == VTC_EPI_BIAS_GELU) {
-                            v0 = gelu_erf_fast(v0); v1 = gelu_erf_fast(v1); v2 = gelu_erf_fast(v2); v3 = gelu_erf_fast(v3);
+                            v0 = gelu_erf_mufu(v0); v1 = gelu_erf_mufu(v1); v2 = gelu_erf_mufu(v2); v3 = gelu_erf_mufu(v3);
                         }
                         o[2 * j] = pack_bf16x2(v0, v1);
                         o[2 * j + 1] = pack_bf16x2(v2, v3);
@@ -216,40 +219,311 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const gem
     return VTC_OK;
 }
 
+// ======================================================================================================================
+// v2: CTA-pair kernel (tcgen05 cta_group::2).  One 256x256 output tile per pair: each CTA stages its own 128 rows of A
+// and 128 of the 256 W rows per k-block (32 KB instead of 48 KB per CTA and k-block -> 1.5x less L2->SM traffic, which
+// is what bounds the single-CTA kernel), the leader issues M=256 MMAs that write 128 accumulator rows into each CTA's
+// TMEM, and each CTA drains its own half through a shared-memory staged, fully coalesced TMA store:
+//   bf16 outputs           cp.async.bulk.tensor store of 128x64 boxes
+//   fp32 residual stream   cp.reduce.async.bulk.tensor .add of 128x32 boxes: out += acc + bias happens in L2, the SMs
+//                          never read the residual.
+namespace gemm2 {
+constexpr int BM = 128;            // rows per CTA (256 per pair)
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 5;
+constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;     // 16 KB: this CTA's half of the W tile
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int OUT_BUF_BYTES = 128 * 128;       // 128 rows x 128 B staging tile
+constexpr int OFF_OUT = STAGES * STAGE_BYTES;  // [2 halves][2 buffers]
+constexpr int OFF_BAR = OFF_OUT + 4 * OUT_BUF_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "gemm2 smem budget");
+
+struct Params {
+    const float* bias;
+    int M, N, K;
+};
+}  // namespace gemm2
+
+template <int EPI>
+__global__ void __launch_bounds__(gemm2::THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const gemm2::Params p) {
+    using namespace gemm2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // used in the leader CTA only
+    uint64_t* empty_bar = full_bar + STAGES;                             // per CTA
+    uint64_t* tfull_bar = empty_bar + STAGES;                            // per CTA
+    uint64_t* tempty_bar = tfull_bar + 2;                                // used in the leader CTA only
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * EPI_WARPS);     // epilogue warps of BOTH CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+    const int num_n = p.N / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = p.K / BK;
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
+                const int n0 = (tile % num_n) * BN + rank * (BN / 2);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);     // both CTAs' bytes land on this barrier
+                    uint8_t* a_dst = smem + s * STAGE_BYTES;
+                    tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+                    tma_load_2d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 16);
+                        const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 16);
+                        umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[s], 3);          // frees the stage in both CTAs
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_2sm(&tfull_bar[as], 3);             // accumulator ready in both CTAs
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        const int r_local = quarter * 32 + lane;
+        const bool issuer = (quarter == 0) && (lane == 0);
+        const uint32_t bar_id = 1 + half;
+        uint8_t* stage_out = smem + OFF_OUT + half * 2 * OUT_BUF_BYTES;
+        constexpr int CHUNK_COLS = (EPI == VTC_EPI_BIAS_RESIDUAL) ? 32 : 64;     // 128-byte rows
+        constexpr int NCHUNK = 128 / CHUNK_COLS;
+        int as = 0;
+        uint32_t aph = 0;
+        int buf = 0;
+        for (int tile = pair; tile < num_tiles; tile += npairs) {
+            const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
+            const int n0 = (tile % num_n) * BN;
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * 128;
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col0 = half * 128 + c * CHUNK_COLS;
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0);
+                uint32_t pk[32];
+                if (EPI == VTC_EPI_BIAS_RESIDUAL) {
+                    tmem_ld_32x32b_x32(t_row + c * 32, pk);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(bias4 + j);
+                        pk[4 * j + 0] = __float_as_uint(__uint_as_float(pk[4 * j + 0]) + b4.x);
+                        pk[4 * j + 1] = __float_as_uint(__uint_as_float(pk[4 * j + 1]) + b4.y);
+                        pk[4 * j + 2] = __float_as_uint(__uint_as_float(pk[4 * j + 2]) + b4.z);
+                        pk[4 * j + 3] = __float_as_uint(__uint_as_float(pk[4 * j + 3]) + b4.w);
+                    }
+                } else {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(t_row + c * 64, r0);
+                    tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(bias4 + j);
+                        const float4 c4 = __ldg(bias4 + 8 + j);
+                        float v0 = __uint_as_float(r0[4 * j + 0]) + b4.x, v1 = __uint_as_float(r0[4 * j + 1]) + b4.y;
+                        float v2 = __uint_as_float(r0[4 * j + 2]) + b4.z, v3 = __uint_as_float(r0[4 * j + 3]) + b4.w;
+                        float w0 = __uint_as_float(r1[4 * j + 0]) + c4.x, w1 = __uint_as_float(r1[4 * j + 1]) + c4.y;
+                        float w2 = __uint_as_float(r1[4 * j + 2]) + c4.z, w3 = __uint_as_float(r1[4 * j + 3]) + c4.w;
+                        if (EPI == VTC_EPI_BIAS_GELU) {
+                            v0 = gelu_erf_mufu(v0); v1 = gelu_erf_mufu(v1); v2 = gelu_erf_mufu(v2); v3 = gelu_erf_mufu(v3);
+                            w0 = gelu_erf_mufu(w0); w1 = gelu_erf_mufu(w1); w2 = gelu_erf_mufu(w2); w3 = gelu_erf_mufu(w3);
+                        }
+                        pk[2 * j] = pack_bf16x2(v0, v1);
+                        pk[2 * j + 1] = pack_bf16x2(v2, v3);
+                        pk[16 + 2 * j] = pack_bf16x2(w0, w1);
+                        pk[16 + 2 * j + 1] = pack_bf16x2(w2, w3);
+                    }
+                }
+                // staging buffer `buf` is free once the bulk store issued from it two chunks ago has read it
+                if (issuer) tma_store_wait_read<1>();
+                named_bar_sync(bar_id, 128);
+                uint8_t* row_ptr = stage_out + buf * OUT_BUF_BYTES + r_local * 128;
+#pragma unroll
+                for (int g8 = 0; g8 < 8; ++g8)
+                    st_u4(row_ptr + ((g8 ^ (r_local & 7)) * 16), make_uint4(pk[4 * g8], pk[4 * g8 + 1], pk[4 * g8 + 2], pk[4 * g8 + 3]));
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (issuer) {
+                    if (EPI == VTC_EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, n0 + col0, m0);
+                    else tma_store_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, n0 + col0, m0);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);      // the leader's MMA thread owns the TMEM schedule
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if (issuer) tma_store_wait_all<0>();
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();              // the peer may still read this CTA's smem / signal its barriers until here
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const gemm2::Params& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = cdiv(p.M, 2 * gemm2::BM) * (p.N / gemm2::BN);
+    int pairs = device_sm_count() / 2;
+    if (tiles < pairs) pairs = tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(gemm2::THREADS);
+    cfg.dynamicSmemBytes = gemm2::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    note_launch();
+    VTC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<EPI>, tmA, tmB, tmO, p));
+    return VTC_OK;
+}
+
+static bool use_v1() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VTC_GEMM_V1");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out, int M,
               int N, int K, int epilogue, int tokens, cudaStream_t stream) {
     VTC_REQUIRE(A && W && bias && out, VTC_ERR_ARG, "gemm: null pointer");
     VTC_REQUIRE(M > 0 && N > 0 && K > 0, VTC_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
     VTC_REQUIRE(K % gemm::BK == 0, VTC_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", K, gemm::BK);
     VTC_REQUIRE(N % gemm::BN == 0, VTC_ERR_SHAPE, "gemm: N=%d must be a multiple of %d", N, gemm::BN);
+    VTC_REQUIRE(epilogue >= VTC_EPI_BIAS && epilogue <= VTC_EPI_PATCH_EMBED, VTC_ERR_ARG, "gemm: unknown epilogue %d", epilogue);
     VTC_REQUIRE(epilogue != VTC_EPI_BIAS_RESIDUAL || residual, VTC_ERR_ARG, "gemm: residual epilogue without residual");
     VTC_REQUIRE(epilogue != VTC_EPI_PATCH_EMBED || (pos && tokens > 1 && M % (tokens - 1) == 0), VTC_ERR_ARG,
                 "gemm: patch-embed epilogue needs pos_embed and M %% (tokens-1) == 0");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
+    const bool v1 = use_v1() || epilogue == VTC_EPI_PATCH_EMBED;
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
         uint64_t strides[1] = {(uint64_t)K * 2};
-        uint32_t box[2] = {gemm::BK, gemm::BM};
+        uint32_t box[2] = {gemm::BK, 128};
         rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
         if (rc != VTC_OK) return rc;
     }
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t strides[1] = {(uint64_t)K * 2};
-        uint32_t box[2] = {gemm::BK, gemm::BN};
+        uint32_t box[2] = {gemm::BK, v1 ? 256u : 128u};
         rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
         if (rc != VTC_OK) return rc;
     }
-    gemm::Params p{bias, residual, pos, out, M, N, K, tokens};
-    switch (epilogue) {
-        case VTC_EPI_BIAS: return launch_gemm<VTC_EPI_BIAS>(tmA, tmB, p, stream);
-        case VTC_EPI_BIAS_GELU: return launch_gemm<VTC_EPI_BIAS_GELU>(tmA, tmB, p, stream);
-        case VTC_EPI_BIAS_RESIDUAL: return launch_gemm<VTC_EPI_BIAS_RESIDUAL>(tmA, tmB, p, stream);
-        case VTC_EPI_PATCH_EMBED: return launch_gemm<VTC_EPI_PATCH_EMBED>(tmA, tmB, p, stream);
-        default: set_last_error("gemm: unknown epilogue %d", epilogue); return VTC_ERR_ARG;
+    if (v1) {
+        gemm::Params p{bias, residual, pos, out, M, N, K, tokens};
+        switch (epilogue) {
+            case VTC_EPI_BIAS: return launch_gemm<VTC_EPI_BIAS>(tmA, tmB, p, stream);
+            case VTC_EPI_BIAS_GELU: return launch_gemm<VTC_EPI_BIAS_GELU>(tmA, tmB, p, stream);
+            case VTC_EPI_BIAS_RESIDUAL: return launch_gemm<VTC_EPI_BIAS_RESIDUAL>(tmA, tmB, p, stream);
+            default: return launch_gemm<VTC_EPI_PATCH_EMBED>(tmA, tmB, p, stream);
+        }
     }
+    CUtensorMap tmO;
+    gemm2::Params p2{bias, M, N, K};
+    if (epilogue == VTC_EPI_BIAS_RESIDUAL) {
+        // out = residual + A.W^T + bias, with the add done by the TMA reduction into `out`
+        if (out != static_cast<const void*>(residual))
+            VTC_CUDA(cudaMemcpyAsync(out, residual, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+        uint64_t strides[1] = {(uint64_t)N * 4};
+        uint32_t box[2] = {32, 128};
+        rc = make_tmap_f32(&tmO, out, 2, dims, strides, box);
+        if (rc != VTC_OK) return rc;
+        return launch_gemm2<VTC_EPI_BIAS_RESIDUAL>(tmA, tmB, tmO, p2, stream);
+    }
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)N * 2};
+    uint32_t box[2] = {64, 128};
+    rc = make_tmap_bf16(&tmO, out, 2, dims, strides, box);
+    if (rc != VTC_OK) return rc;
+    if (epilogue == VTC_EPI_BIAS) return launch_gemm2<VTC_EPI_BIAS>(tmA, tmB, tmO, p2, stream);
+    return launch_gemm2<VTC_EPI_BIAS_GELU>(tmA, tmB, tmO, p2, stream);
 }
 
 }  // namespace vtc

@@ -76,8 +76,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+static int make_tmap(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
     PFN_encodeTiled enc = get_encode();
     VTC_REQUIRE(enc != nullptr, VTC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, VTC_ERR_ARG, "TMA base pointer must be 16-byte aligned");
@@ -95,7 +95,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
                         (unsigned long long)gstr[i - 1]);
         }
     }
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+    CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -104,6 +104,15 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
         return VTC_ERR_CUDA;
     }
     return VTC_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+    return make_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+    return make_tmap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 }  // namespace vtc
