@@ -12,6 +12,8 @@
 //               zero-filled by TMA), tcgen05.mma issue.
 // P is handed to the second MMA through shared memory as bf16 in the canonical K-major 128-byte-swizzle layout;
 // V is consumed MN-major straight from the TMA tile (no transpose anywhere).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.h"
 #include "tma_host.h"
@@ -260,28 +262,338 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
+// ======================================================================================================================
+// v2: one CTA per (image, head, 128-query-row tile), two CTAs resident per SM so that one CTA's TMA / prologue /
+// epilogue latency hides behind the other's softmax.
+//   * smem 109 KB: Q 16 KB + K 32 KB; the bf16 P tile (64 KB, K-major 128B swizzle) OVERLAYS Q and K, which are dead once
+//     S = Q K^T has been committed; V 32 KB (MN-major, consumed as the TMA wrote it).  TMEM 256 columns: S, then O on top.
+//   * the reference's background mask -100*min(v_i + v_j, 1) is applied BY THE TENSOR CORE: one extra K-step with
+//     Q_aug[i] = [v_i == 0] and K_aug[j] = -100/scale * v_j (bf16 -800 for scale 1/8), so the softmax code has no mask
+//     handling at all and background query rows stay unmasked exactly like the reference (vit_model.py:348-361).
+//   * softmax per element: pass 1 FMNMX on the raw accumulator; pass 2 FFMA + MUFU.EX2 + FADD + cvt/pack; TMEM loads are
+//     software-pipelined one 32-column chunk ahead.
+namespace attn2 {
+constexpr int HD = 64;
+constexpr int MAXN = 256;
+constexpr int Q_BYTES = 128 * HD * 2;                 // 16 KB
+constexpr int KV_BYTES = MAXN * HD * 2;               // 32 KB
+constexpr int P_KBLOCK_BYTES = 128 * 128;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = Q_BYTES;
+constexpr int OFF_P = 0;                              // overlays Q + K
+constexpr int OFF_V = 4 * P_KBLOCK_BYTES;             // 64 KB
+constexpr int OFF_QAUG = OFF_V + KV_BYTES;            // 128 rows x 32 B, no swizzle
+constexpr int OFF_KAUG = OFF_QAUG + 128 * 32;         // 256 rows x 32 B, no swizzle
+constexpr int OFF_CLS = OFF_KAUG + MAXN * 32;         // CLS row staging [256] floats
+constexpr int OFF_BAR = OFF_CLS + MAXN * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int THREADS = 160;
+static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two attention CTAs per SM");
+}  // namespace attn2
+
+struct Attn2Params {
+    const float* key_bias;   // [B,N] or null
+    __nv_bfloat16* out;      // [B,N,H*64]
+    float* cls_rows;         // [B,H,N] or null
+    float* attn;             // [B,H,N,N] or null
+    int B, N, H;
+    float scale, scale_log2;
+};
+
+template <bool CLS>
+__device__ __forceinline__ void softmax_pass2(uint32_t t_s, int nchunks, int N, float sc, float neg_m, uint8_t* p_row, int r_local,
+                                              float* cls_s, bool is_cls_thread, float& sum_out) {
+    float sum = 0.f;
+    uint32_t cur[32], nxt[32];
+    tmem_ld_32x32b_x32(t_s, cur);
+    tmem_ld_wait();
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, nxt);
+        uint32_t pk[16];
+        const bool tail = (c * 32 + 32 > N);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(cur[j]), sc, neg_m));
+            float e1 = ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sc, neg_m));
+            if (tail) {
+                if (c * 32 + j >= N) e0 = 0.f;
+                if (c * 32 + j + 1 >= N) e1 = 0.f;
+            }
+            sum += e0 + e1;
+            if (CLS) {
+                if (is_cls_thread) { cls_s[c * 32 + j] = e0; cls_s[c * 32 + j + 1] = e1; }
+            }
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+        }
+        uint8_t* kblk = p_row + (c >> 1) * attn2::P_KBLOCK_BYTES;
+        const int g0 = (c & 1) * 4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            st_u4(kblk + (((g0 + g) ^ (r_local & 7)) * 16), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+        if (c + 1 < nchunks) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
+        }
+    }
+    sum_out = sum;
+}
+
+__global__ void __launch_bounds__(attn2::THREADS, 2)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const Attn2Params p) {
+    using namespace attn2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* bar_qk = bars + 0;
+    uint64_t* bar_v = bars + 1;
+    uint64_t* s_full = bars + 2;
+    uint64_t* p_full = bars + 3;
+    uint64_t* o_full = bars + 4;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+    float* cls_s = reinterpret_cast<float*>(smem + OFF_CLS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int N = p.N;
+    const int ntiles = (N + 127) >> 7;
+    const int mt = blockIdx.x % ntiles;
+    const int bh = blockIdx.x / ntiles;
+    const int b = bh / p.H;
+    const int h = bh - b * p.H;
+    const int NP = (N + 15) & ~15;
+    const bool has_bias = p.key_bias != nullptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmKV);
+            mbar_init(bar_qk, 1);
+            mbar_init(bar_v, 1);
+            mbar_init(s_full, 1);
+            mbar_init(p_full, 128);
+            mbar_init(o_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 256);
+    } else if (has_bias) {
+        // augmented K-step operands (no-swizzle K-major core matrices: 8 rows x 16 B, LBO 128 B, SBO 256 B)
+        const float* kb = p.key_bias + static_cast<size_t>(b) * N;
+        const float inv_scale = 1.0f / p.scale;
+        {
+            const int r = threadIdx.x;                       // 0..127: query row of this tile
+            const int row = mt * 128 + r;
+            const float flag = (row < N && kb[row] == 0.f) ? 1.0f : 0.0f;
+            uint8_t* dst = smem + OFF_QAUG + (r >> 3) * 256 + (r & 7) * 16;
+            st_u4(dst, make_uint4(pack_bf16x2(flag, 0.f), 0u, 0u, 0u));
+            st_u4(dst + 128, make_uint4(0u, 0u, 0u, 0u));
+        }
+        for (int j = threadIdx.x; j < MAXN; j += 128) {
+            const float v = (j < N) ? kb[j] * inv_scale : 0.f;
+            uint8_t* dst = smem + OFF_KAUG + (j >> 3) * 256 + (j & 7) * 16;
+            st_u4(dst, make_uint4(pack_bf16x2(v, 0.f), 0u, 0u, 0u));
+            st_u4(dst + 128, make_uint4(0u, 0u, 0u, 0u));
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const int D = p.H * HD;
+            mbar_arrive_expect_tx(bar_qk, Q_BYTES + KV_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(smem + OFF_Q)), "l"(reinterpret_cast<uint64_t>(&tmQ)), "r"(smem_u32(bar_qk)), "r"(h * HD), "r"(mt * 128), "r"(b)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(smem + OFF_K)), "l"(reinterpret_cast<uint64_t>(&tmKV)), "r"(smem_u32(bar_qk)), "r"(D + h * HD), "r"(0), "r"(b)
+                : "memory");
+            mbar_arrive_expect_tx(bar_v, KV_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(smem + OFF_V)), "l"(reinterpret_cast<uint64_t>(&tmKV)), "r"(smem_u32(bar_v)), "r"(2 * D + h * HD), "r"(0), "r"(b)
+                : "memory");
+
+            mbar_wait(bar_qk, 0);
+            tc_fence_after();
+            const uint32_t idesc_s = make_idesc_bf16(128, NP, 0, 0);
+            const uint32_t q_addr = smem_u32(smem + OFF_Q);
+            const uint32_t k_addr = smem_u32(smem + OFF_K);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+                umma_bf16(tmem_base, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16),
+                          idesc_s, k != 0 ? 1u : 0u);
+            if (has_bias)
+                umma_bf16(tmem_base, make_smem_desc(smem_u32(smem + OFF_QAUG), 256, 128, 0), make_smem_desc(smem_u32(smem + OFF_KAUG), 256, 128, 0),
+                          idesc_s, 1u);
+            umma_commit(s_full);
+
+            mbar_wait(bar_v, 0);
+            mbar_wait(p_full, 0);
+            tc_fence_after();
+            const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
+            const uint32_t v_addr = smem_u32(smem + OFF_V);
+            const uint32_t p_addr = smem_u32(smem + OFF_P);
+            const int ksteps = NP / 16;
+            for (int j = 0; j < ksteps; ++j)
+                umma_bf16(tmem_base, make_smem_desc_sw128(p_addr + (j >> 2) * P_KBLOCK_BYTES + (j & 3) * 32, 1024, 16),
+                          make_smem_desc_sw128(v_addr + j * 2048, 1024, 1024), idesc_o, j != 0 ? 1u : 0u);
+            umma_commit(o_full);
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp;
+        const int r_local = quarter * 32 + lane;
+        const int row = mt * 128 + r_local;
+        const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int nchunks = (N + 31) >> 5;
+        const float sc = p.scale_log2;
+        const bool warp_active = (mt * 128 + quarter * 32) < N;      // warp-uniform: any valid query row in this warp?
+
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        float inv = 0.f;
+        if (warp_active) {
+            // pass 1: row max of the raw accumulator (scale > 0, the mask is already inside S)
+            float m = -INFINITY;
+            {
+                uint32_t cur[32], nxt[32];
+                tmem_ld_32x32b_x32(t_s, cur);
+                tmem_ld_wait();
+                for (int c = 0; c < nchunks; ++c) {
+                    if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, nxt);
+                    if (c * 32 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j < N) m = fmaxf(m, __uint_as_float(cur[j]));
+                    }
+                    if (c + 1 < nchunks) {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
+                    }
+                }
+            }
+            const float neg_m = -m * sc;
+            uint8_t* p_row = smem + OFF_P + r_local * 128;
+            float sum;
+            const bool cls_warp = (mt == 0) && (quarter == 0) && (p.cls_rows != nullptr);     // warp-uniform
+            if (cls_warp) softmax_pass2<true>(t_s, nchunks, N, sc, neg_m, p_row, r_local, cls_s, lane == 0, sum);
+            else softmax_pass2<false>(t_s, nchunks, N, sc, neg_m, p_row, r_local, cls_s, false, sum);
+            inv = 1.0f / sum;
+            if (p.attn != nullptr) {
+                // pass 3 (on request): normalised fp32 P rows; CTA-uniform branch, only the stores are predicated
+                const bool wr = row < N;
+                float* dst = p.attn + ((static_cast<size_t>(b) * p.H + h) * N + (wr ? row : 0)) * N;
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_s + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        if (wr && col < N) dst[col] = ex2_approx(fmaf(__uint_as_float(r[j]), sc, neg_m)) * inv;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            if (cls_warp) {
+                const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
+                __syncwarp();
+                float* dst = p.cls_rows + (static_cast<size_t>(b) * p.H + h) * N;
+                for (int j = lane; j < N; j += 32) dst[j] = cls_s[j] * inv0;
+            }
+        }
+        mbar_arrive(p_full);
+
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        if (warp_active) {
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32b_x32(t_s, o0);
+            tmem_ld_32x32b_x32(t_s + 32, o1);
+            tmem_ld_wait();
+            if (row < N) {
+                __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * (p.H * HD) + h * HD;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    st_u4(dst + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
+                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
+                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
+                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv)));
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    st_u4(dst + 32 + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv)));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+static bool attn_use_v1() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VTC_ATTN_V1");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_out, int batch, int n_tokens, int heads,
               float scale, cudaStream_t stream) {
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
+    VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
     VTC_REQUIRE(n_tokens <= attn::MAXN, VTC_ERR_SHAPE,
                 "attention: %d tokens > %d: the KV-blocked long-sequence kernel is not built yet", n_tokens, attn::MAXN);
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     const int D = heads * attn::HD;
-    CUtensorMap tm;
     uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)n_tokens, (uint64_t)batch};
     uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)n_tokens * 3 * D * 2};
+    CUtensorMap tmKV;
     uint32_t box[3] = {attn::HD, attn::MAXN, 1};
-    rc = make_tmap_bf16(&tm, qkv, 3, dims, strides, box);
+    rc = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, box);
     if (rc != VTC_OK) return rc;
-    static bool configured = false;
-    if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-        configured = true;
+    if (attn_use_v1()) {
+        static bool configured = false;
+        if (!configured) {
+            VTC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+            configured = true;
+        }
+        AttnParams p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale * 1.4426950408889634f};
+        attention_kernel<<<batch * heads, attn::THREADS, attn::SMEM_BYTES, stream>>>(tmKV, p);
+        VTC_CHECK_LAUNCH();
+        return VTC_OK;
     }
-    AttnParams p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale * 1.4426950408889634f};
-    attention_kernel<<<batch * heads, attn::THREADS, attn::SMEM_BYTES, stream>>>(tm, p);
+    CUtensorMap tmQ;
+    uint32_t boxq[3] = {attn::HD, 128, 1};
+    rc = make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq);
+    if (rc != VTC_OK) return rc;
+    static bool configured2 = false;
+    if (!configured2) {
+        VTC_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn2::SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured2 = true;
+    }
+    Attn2Params p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale, scale * 1.4426950408889634f};
+    const int ntiles = (n_tokens + 127) / 128;
+    attention2_kernel<<<batch * heads * ntiles, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }

@@ -217,6 +217,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
     d |= static_cast<uint64_t>(2) << 61;    // LayoutType::SWIZZLE_128B
     return d;
 }
+// Generic form: layout_type 0 = no swizzle ("interleave": 8x16-byte core matrices, LBO = byte distance between core
+// matrices adjacent in K, SBO = between 8-row groups), 2 = 128B, 4 = 64B, 6 = 32B swizzle.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t lbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout_type & 7u) << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate (cute::UMMA::InstrDescriptor).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
