@@ -300,43 +300,68 @@ struct Attn2Params {
     float scale, scale_log2;
 };
 
+// One 32-column chunk of pass 2: e = 2^(s*sc - m*sc) with packed fp32x2 FMAs, row-sum partials, bf16 pack, swizzled STS.
+template <bool CLS>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&cur)[32], int c, int N, uint64_t sc2, uint64_t negm2, uint64_t& sum2,
+                                              uint8_t* p_row, int r_local, float* cls_s, bool is_cls_thread) {
+    uint32_t pk[16];
+    const bool tail = (c * 32 + 32 > N);
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        float x0, x1;
+        unpack2(fma2(pack2u(cur[j], cur[j + 1]), sc2, negm2), x0, x1);
+        float e0 = ex2_approx(x0);
+        float e1 = ex2_approx(x1);
+        if (tail) {
+            if (c * 32 + j >= N) e0 = 0.f;
+            if (c * 32 + j + 1 >= N) e1 = 0.f;
+        }
+        sum2 = add2(sum2, pack2(e0, e1));
+        if (CLS) {
+            if (is_cls_thread) { cls_s[c * 32 + j] = e0; cls_s[c * 32 + j + 1] = e1; }
+        }
+        pk[j >> 1] = pack_bf16x2(e0, e1);
+    }
+    uint8_t* kblk = p_row + (c >> 1) * attn2::P_KBLOCK_BYTES;
+    const int g0 = (c & 1) * 4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        st_u4(kblk + (((g0 + g) ^ (r_local & 7)) * 16), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+}
+
+// Pass 2 over all chunks; TMEM loads run one chunk ahead in two ping-pong register buffers (no copies).
 template <bool CLS>
 __device__ __forceinline__ void softmax_pass2(uint32_t t_s, int nchunks, int N, float sc, float neg_m, uint8_t* p_row, int r_local,
                                               float* cls_s, bool is_cls_thread, float& sum_out) {
-    float sum = 0.f;
-    uint32_t cur[32], nxt[32];
-    tmem_ld_32x32b_x32(t_s, cur);
-    tmem_ld_wait();
-    for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, nxt);
-        uint32_t pk[16];
-        const bool tail = (c * 32 + 32 > N);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            float e0 = ex2_approx(fmaf(__uint_as_float(cur[j]), sc, neg_m));
-            float e1 = ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sc, neg_m));
-            if (tail) {
-                if (c * 32 + j >= N) e0 = 0.f;
-                if (c * 32 + j + 1 >= N) e1 = 0.f;
-            }
-            sum += e0 + e1;
-            if (CLS) {
-                if (is_cls_thread) { cls_s[c * 32 + j] = e0; cls_s[c * 32 + j + 1] = e1; }
-            }
-            pk[j >> 1] = pack_bf16x2(e0, e1);
-        }
-        uint8_t* kblk = p_row + (c >> 1) * attn2::P_KBLOCK_BYTES;
-        const int g0 = (c & 1) * 4;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-            st_u4(kblk + (((g0 + g) ^ (r_local & 7)) * 16), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+    const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
+    uint64_t sum2 = pack2(0.f, 0.f);
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32b_x32(t_s, ra);
+    for (int c = 0; c < nchunks; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, rb);
+        softmax_chunk<CLS>(ra, c, N, sc2, negm2, sum2, p_row, r_local, cls_s, is_cls_thread);
         if (c + 1 < nchunks) {
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
+            if (c + 2 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 2) * 32, ra);
+            softmax_chunk<CLS>(rb, c + 1, N, sc2, negm2, sum2, p_row, r_local, cls_s, is_cls_thread);
         }
     }
-    sum_out = sum;
+    float s0, s1;
+    unpack2(sum2, s0, s1);
+    sum_out = s0 + s1;
+}
+
+__device__ __forceinline__ float chunk_max(const uint32_t (&cur)[32], int c, int N, float m) {
+    if (c * 32 + 32 <= N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < N) m = fmaxf(m, __uint_as_float(cur[j]));
+    }
+    return m;
 }
 
 __global__ void __launch_bounds__(attn2::THREADS, 2)
@@ -463,23 +488,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             // pass 1: row max of the raw accumulator (scale > 0, the mask is already inside S)
             float m = -INFINITY;
             {
-                uint32_t cur[32], nxt[32];
-                tmem_ld_32x32b_x32(t_s, cur);
-                tmem_ld_wait();
-                for (int c = 0; c < nchunks; ++c) {
-                    if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, nxt);
-                    if (c * 32 + 32 <= N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < N) m = fmaxf(m, __uint_as_float(cur[j]));
-                    }
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(t_s, ra);
+                for (int c = 0; c < nchunks; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, rb);
+                    m = chunk_max(ra, c, N, m);
                     if (c + 1 < nchunks) {
                         tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
+                        if (c + 2 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 2) * 32, ra);
+                        m = chunk_max(rb, c + 1, N, m);
                     }
                 }
             }

@@ -129,17 +129,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a mis-programmed pipeline traps (-> CUDA error on the host) instead of hanging
 // the GPU box.  try_wait suspends in hardware, so the bound is ~seconds, never hit when correct.
 #ifndef VTC_MBAR_SPIN_LIMIT
-#define VTC_MBAR_SPIN_LIMIT (1u << 22)
+#define VTC_MBAR_SPIN_LIMIT (1u << 20)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -341,6 +341,70 @@ __device__ __forceinline__ float gelu_erf_mufu(float x) {
     const float erf_abs = fmaf(-p, e, 1.0f);
     const float hx = 0.5f * x;
     return fmaf(copysignf(erf_abs, x), hx, hx);
+}
+
+
+// ---- packed fp32x2 arithmetic (Blackwell: two fp32 FMAs per issue slot) ------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// erf-GELU of two values at once for the GEMM epilogue.
+//   gelu(x) = relu(x) - |x/2| * erfc(|x|/sqrt2),   erfc(|x|/sqrt2) = 2^P6(min(|x|, 6))
+// P6 = degree-6 polynomial fit of log2(erfc(a/sqrt2)) on [0,6] (tools/fit_gelu.py): |gelu error| <= 4.3e-7 absolute over
+// [-8,8] in fp32 arithmetic -- three orders of magnitude below the bf16 rounding of the stored activation.  One MUFU.EX2
+// and 4.5 packed-FMA issue slots per element (the A&S 7.1.26 form needs 2 MUFU + 13 scalar FMA-pipe ops and made the
+// fc1 epilogue, not the tensor core, the bottleneck).
+#define VTC_GELU_P0 (-7.278096290974645e-06f)
+#define VTC_GELU_P1 (-1.1510897874832153f)
+#define VTC_GELU_P2 (-0.4590291380882263f)
+#define VTC_GELU_P3 (-0.05316730961203575f)
+#define VTC_GELU_P4 (0.007976981811225414f)
+#define VTC_GELU_P5 (-0.0007510420400649309f)
+#define VTC_GELU_P6 (3.223069870728068e-05f)
+__device__ __forceinline__ void gelu2(float x0, float x1, float& g0, float& g1) {
+    const float a0 = fminf(fabsf(x0), 6.0f), a1 = fminf(fabsf(x1), 6.0f);
+    const uint64_t a = pack2(a0, a1);
+    uint64_t p = fma2(pack2(VTC_GELU_P6, VTC_GELU_P6), a, pack2(VTC_GELU_P5, VTC_GELU_P5));
+    p = fma2(p, a, pack2(VTC_GELU_P4, VTC_GELU_P4));
+    p = fma2(p, a, pack2(VTC_GELU_P3, VTC_GELU_P3));
+    p = fma2(p, a, pack2(VTC_GELU_P2, VTC_GELU_P2));
+    p = fma2(p, a, pack2(VTC_GELU_P1, VTC_GELU_P1));
+    p = fma2(p, a, pack2(VTC_GELU_P0, VTC_GELU_P0));
+    float p0, p1;
+    unpack2(p, p0, p1);
+    const float e0 = ex2_approx(p0), e1 = ex2_approx(p1);
+    const uint64_t h = mul2(pack2(x0, x1), pack2(0.5f, 0.5f));
+    float h0, h1;
+    unpack2(h, h0, h1);
+    const uint64_t nh = pack2(-fabsf(h0), -fabsf(h1));                 // -|x/2|
+    const uint64_t r = fma2(nh, pack2(e0, e1), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    unpack2(r, g0, g1);
 }
 
 // ---- vectorised global access -------------------------------------------------------------------

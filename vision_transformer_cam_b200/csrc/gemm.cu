@@ -387,13 +387,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int j = 0; j < 8; ++j) {
                         const float4 b4 = __ldg(bias4 + j);
                         const float4 c4 = __ldg(bias4 + 8 + j);
-                        float v0 = __uint_as_float(r0[4 * j + 0]) + b4.x, v1 = __uint_as_float(r0[4 * j + 1]) + b4.y;
-                        float v2 = __uint_as_float(r0[4 * j + 2]) + b4.z, v3 = __uint_as_float(r0[4 * j + 3]) + b4.w;
-                        float w0 = __uint_as_float(r1[4 * j + 0]) + c4.x, w1 = __uint_as_float(r1[4 * j + 1]) + c4.y;
-                        float w2 = __uint_as_float(r1[4 * j + 2]) + c4.z, w3 = __uint_as_float(r1[4 * j + 3]) + c4.w;
+                        float v0, v1, v2, v3, w0, w1, w2, w3;
+                        unpack2(add2(pack2u(r0[4 * j + 0], r0[4 * j + 1]), pack2(b4.x, b4.y)), v0, v1);
+                        unpack2(add2(pack2u(r0[4 * j + 2], r0[4 * j + 3]), pack2(b4.z, b4.w)), v2, v3);
+                        unpack2(add2(pack2u(r1[4 * j + 0], r1[4 * j + 1]), pack2(c4.x, c4.y)), w0, w1);
+                        unpack2(add2(pack2u(r1[4 * j + 2], r1[4 * j + 3]), pack2(c4.z, c4.w)), w2, w3);
                         if (EPI == VTC_EPI_BIAS_GELU) {
-                            v0 = gelu_erf_mufu(v0); v1 = gelu_erf_mufu(v1); v2 = gelu_erf_mufu(v2); v3 = gelu_erf_mufu(v3);
-                            w0 = gelu_erf_mufu(w0); w1 = gelu_erf_mufu(w1); w2 = gelu_erf_mufu(w2); w3 = gelu_erf_mufu(w3);
+                            gelu2(v0, v1, v0, v1);
+                            gelu2(v2, v3, v2, v3);
+                            gelu2(w0, w1, w0, w1);
+                            gelu2(w2, w3, w2, w3);
                         }
                         pk[2 * j] = pack_bf16x2(v0, v1);
                         pk[2 * j + 1] = pack_bf16x2(v2, v3);

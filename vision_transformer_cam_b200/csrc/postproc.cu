@@ -118,7 +118,48 @@ int cls_layer_map(const float* cls_rows, float* map, int layers, int first, int 
 // cam[b,c,p] = <W[c,:], F[b,p,:]> on the block-L patch tokens, ReLU, per-map min-max (t.py:66-70, utils.py:84-85).
 // One CTA per image: W staged once in shared memory, each warp streams patch rows with float4 loads, C running dot
 // products per lane, shuffle reduction, raw maps kept in shared memory for the normalisation pass.
-constexpr int CAM_MAXC = 32;
+constexpr int CAM_MAXC = 32;     // classes per pass (more classes: several passes over the tokens)
+constexpr int CAM_PB = 4;        // patches per warp iteration: each W float4 read from smem feeds 4 patches
+template <int CB>
+__device__ __forceinline__ void cam_rows(const float* __restrict__ F, const float* __restrict__ ws, float* __restrict__ raw, int P, int D,
+                                         int c0, int cn, int relu, int warp, int lane) {
+    const int nv = D / 128;
+    for (int p0 = warp * CAM_PB; p0 < P; p0 += 8 * CAM_PB) {
+        float acc[CAM_PB][CB];
+#pragma unroll
+        for (int q = 0; q < CAM_PB; ++q)
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[q][c] = 0.f;
+        for (int i = 0; i < nv; ++i) {
+            const int d = (lane + 32 * i) * 4;
+            float4 f[CAM_PB];
+#pragma unroll
+            for (int q = 0; q < CAM_PB; ++q) {
+                const int pp = (p0 + q < P) ? p0 + q : P - 1;
+                f[q] = ld_stream_f4(F + static_cast<size_t>(pp) * D + d);
+            }
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                if (c < cn) {
+                    const float4 wv = *reinterpret_cast<const float4*>(ws + (c0 + c) * D + d);
+#pragma unroll
+                    for (int q = 0; q < CAM_PB; ++q)
+                        acc[q][c] = fmaf(f[q].x, wv.x, fmaf(f[q].y, wv.y, fmaf(f[q].z, wv.z, fmaf(f[q].w, wv.w, acc[q][c]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CAM_PB; ++q)
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                if (c < cn) {
+                    const float s = warp_sum(acc[q][c]);
+                    if (lane == 0 && p0 + q < P) raw[(c0 + c) * P + p0 + q] = relu ? fmaxf(s, 0.f) : s;
+                }
+            }
+    }
+}
+
 __global__ void __launch_bounds__(256) cam_project_kernel(const float* __restrict__ tokens, const float* __restrict__ w, float* __restrict__ cam,
                                                           int N, int D, int C, int relu, float eps) {
     extern __shared__ float sm[];
@@ -130,30 +171,9 @@ __global__ void __launch_bounds__(256) cam_project_kernel(const float* __restric
     for (int i = threadIdx.x; i < C * D / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = ldg_f4(w + 4 * i);
     __syncthreads();
     const float* F = tokens + (static_cast<size_t>(b) * N + 1) * D;
-    const int nv = D / 128;         // float4 per lane
-    for (int p = warp; p < P; p += 8) {
-        float acc[CAM_MAXC];
-#pragma unroll
-        for (int c = 0; c < CAM_MAXC; ++c) acc[c] = 0.f;
-        const float* row = F + static_cast<size_t>(p) * D;
-        for (int i = 0; i < nv; ++i) {
-            const int d = (lane + 32 * i) * 4;
-            const float4 f = ld_stream_f4(row + d);
-#pragma unroll
-            for (int c = 0; c < CAM_MAXC; ++c) {
-                if (c < C) {
-                    const float4 wv = *reinterpret_cast<const float4*>(ws + c * D + d);
-                    acc[c] = fmaf(f.x, wv.x, fmaf(f.y, wv.y, fmaf(f.z, wv.z, fmaf(f.w, wv.w, acc[c]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < CAM_MAXC; ++c) {
-            if (c < C) {
-                const float s = warp_sum(acc[c]);
-                if (lane == 0) raw[c * P + p] = relu ? fmaxf(s, 0.f) : s;
-            }
-        }
+    for (int c0 = 0; c0 < C; c0 += 10) {          // 10 classes x 4 patches = 40 accumulators per lane
+        const int cn = (C - c0 < 10) ? C - c0 : 10;
+        cam_rows<10>(F, ws, raw, P, D, c0, cn, relu, warp, lane);
     }
     __syncthreads();
     for (int c = warp; c < C; c += 8) {
@@ -169,8 +189,8 @@ __global__ void __launch_bounds__(256) cam_project_kernel(const float* __restric
 
 int cam_project(const float* tokens, const float* w, float* cam, int batch, int n_tokens, int dim, int classes, int relu, float eps, cudaStream_t stream) {
     VTC_REQUIRE(tokens && w && cam, VTC_ERR_ARG, "cam_project: null pointer");
-    VTC_REQUIRE(batch > 0 && n_tokens > 1 && dim % 128 == 0 && classes > 0 && classes <= CAM_MAXC, VTC_ERR_SHAPE,
-                "cam_project: dim %d (multiple of 128) classes %d (<= %d)", dim, classes, CAM_MAXC);
+    VTC_REQUIRE(batch > 0 && n_tokens > 1 && dim % 128 == 0 && classes > 0 && classes <= 64, VTC_ERR_SHAPE,
+                "cam_project: dim %d (multiple of 128) classes %d (<= 64)", dim, classes);
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     const size_t smem = sizeof(float) * (static_cast<size_t>(classes) * dim + static_cast<size_t>(classes) * (n_tokens - 1));
