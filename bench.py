@@ -171,7 +171,7 @@ def main():
     model = V.vit_base_patch16_224_in21k(num_classes=C, has_logits=False).to(dev).eval()
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_dev = torch.randn((B, 3, IMG, IMG), generator=g, device=dev)
-    gathered = torch.empty((world, B, C, 14, 14), device=dev) if world > 1 else None
+    gathered = torch.empty((world * B, C, 14, 14), device=dev) if world > 1 else None
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
 
     def step(x):

@@ -1,0 +1,50 @@
+"""2 GPUs (gpurun --gpus 2): the sharded CAM extraction over NCCL equals the single-rank run."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+import vision_transformer_cam_b200 as V
+from vision_transformer_cam_b200 import dist as D, pipeline
+from oracle import vit_forward as VF
+rank, local_rank, world = D.init_from_env("nccl")
+dev = torch.device("cuda", local_rank)
+torch.manual_seed(0)
+model = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).to(dev).eval()
+get = lambda lo, hi: VF.make_images(lo, hi - lo).to(dev)
+n = 10
+# batch 1 per call => the batch-global mask max is per image, so the result is independent of the sharding
+out = pipeline.extract_cams_sharded(model, get, n_items=n, batch=1)
+assert out["cam"].shape[0] == n and out["rollout"].shape == (n, 196)
+if rank == 0:
+    ref = torch.cat([pipeline.extract_cams_sharded(model, get, n_items=1, batch=1, gather=False)["cam"] if False else
+                     __import__("vision_transformer_cam_b200").cam.classic_cam(model.forward_cam(get(i, i + 1)).tokens_last, model.head1.weight.data)
+                     for i in range(n)])
+    assert torch.equal(ref, out["cam"]), float((ref - out["cam"]).abs().max())
+c = torch.tensor([rank + 1], dtype=torch.int64, device=dev)
+D.reduce_counters(c)
+assert int(c) == world * (world + 1) // 2
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_nccl_sharded_extraction_equals_single_rank(tmp_path, lib_built):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

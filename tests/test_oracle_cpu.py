@@ -1,0 +1,105 @@
+"""CPU: the oracle restatement against the golden vectors that were produced by EXECUTING THE REFERENCE
+(tests/golden/make_golden.py; /root/reference is not needed at test time)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import vit_forward as VF, postproc as PP
+
+
+@pytest.fixture(scope="module")
+def sd0():
+    return VF.init_state_dict(VF.VIT_B16_224, seed=0)
+
+
+def test_constructor_matches_reference_state_dict(sd0):
+    sig = json.load(open(os.path.join(GOLDEN, "state_dict_signature.json")))
+    assert len(sig["keys"]) == 158 and set(sig["keys"]) == set(sd0.keys())
+    assert sum(v.numel() for v in sd0.values()) == 85829992
+    for k in sig["keys"]:
+        assert list(sd0[k].shape) == sig["shapes"][k]
+        s, a = sig["sig"][k]
+        assert abs(float(sd0[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(a)) and abs(float(sd0[k].double().abs().sum()) - a) <= 1e-9 * max(1.0, a)
+
+
+def test_oracle_forward_reproduces_reference_peaked_b1(sd0):
+    gold = np.load(os.path.join(GOLDEN, "peaked_b1.npz"))
+    sd = VF.peaked(sd0)
+    x = VF.make_images(0, 1)
+    assert abs(float(x.double().sum()) - float(gold["x_sig"][0])) < 1e-6
+    out = VF.forward(sd, x, VF.VIT_B16_224)
+    # same torch build -> bit identical (REPORT.json: 0.0); leave 1e-5 for other BLAS builds
+    assert float(np.abs(out["logits"].numpy() - gold["logits"]).max()) <= 1e-5
+    assert float(np.abs(out["hwp"].numpy() - gold["hwp"]).max()) <= 1e-4
+    assert float(np.abs(out["cls_rows"].numpy() - gold["cls_rows"]).max()) <= 1e-6
+    assert np.array_equal(out["topk_idx"].numpy(), gold["topk_idx"])
+    bg = np.stack([b.numpy().astype(np.uint8) for b in out["bg"] if b is not None])
+    assert np.array_equal(bg, gold["bg"]) and 0.1 < bg.mean() < 0.9
+    # post-processing restatement vs the exec'd reference lines
+    assert float(np.abs(PP.rollout_dense(out["P"])[0].numpy() - gold["rollout_row"]).max()) <= 1e-6
+    assert float(np.abs(PP.layer_maps(out["P"])[:, 0].numpy() - gold["layer_maps14"]).max()) <= 1e-6
+    assert float(np.abs(PP.bg_map(out["cls_rows"]).numpy() - gold["val_bg_map"]).max()) <= 1e-6
+    p2c = PP.hwp_patch_classes(out["hwp"][0], sd["head1.weight"], out["ori"][0])
+    assert np.array_equal(p2c.numpy(), gold["val_patch_to_cls"])
+    seg = PP.hwp_pseudo_seg(out["hwp"], sd["head1.weight"], out["ori"], out["X"][-1], out["cls_rows"], (375, 500))
+    assert float((seg[0].numpy() == gold["val_seg"]).mean()) >= 0.9999
+    cam = PP.classic_cam(out["X"][-1], sd["head1.weight"])
+    assert float(np.abs(cam.numpy() - gold["classic_cam"]).max()) <= 1e-5
+    lab = PP.cam_pseudo_label(cam, torch.from_numpy(gold["cam_labels_in"]), (375, 500))
+    assert float((lab.numpy() == gold["cam_label"]).mean()) >= 0.9999
+
+
+def test_rollout_vector_chain_equals_dense_chain():
+    """The CUDA path evaluates only the CLS row of the product (reverse vector-matrix chain); same numbers as the
+    reference's dense chain (predict.py:221-232)."""
+    g = torch.Generator().manual_seed(3)
+    P_list = [(torch.randn((2, 3, 50, 50), generator=g) * 2).softmax(-1) for _ in range(5)]
+    aug = PP.augment(PP.head_mean(P_list))
+    r = torch.zeros(2, 50)
+    r[:, 0] = 1
+    for l in range(4, -1, -1):
+        r = torch.einsum("bi,bij->bj", r, aug[l])
+    assert float((r[:, 1:] - PP.rollout_dense(P_list)).abs().max()) < 1e-6
+
+
+def test_mask_is_key_bias_on_foreground_rows_only():
+    """-100*min(v_i+v_j,1) (vit_model.py:348-361) == per-key bias -100*v_j on rows with v_i = 0, nothing on rows with
+    v_i = 1 (a uniform -100 is softmax invariant): the form the CUDA kernel implements."""
+    g = torch.Generator().manual_seed(5)
+    s = torch.randn((2, 3, 20, 20), generator=g) * 3
+    v = (torch.rand((2, 20), generator=g) < 0.4).float()
+    v[:, 0] = 0
+    full = (s - 100.0 * torch.clamp(v[:, :, None] + v[:, None, :], max=1.0)[:, None]).softmax(-1)
+    mine = (s - 100.0 * (1 - v)[:, None, :, None] * v[:, None, None, :]).softmax(-1)
+    assert float((full - mine).abs().max()) < 1e-6
+
+
+def test_confusion_matrix_and_ap_known_answers():
+    gt = np.array([0, 1, 1, 2, 255, 2], dtype=np.uint8)
+    pr = np.array([0, 1, 2, 2, 1, 0], dtype=np.uint8)
+    m = PP.confmat_update(None, gt, pr, num_classes=2)
+    assert m.tolist() == [[1, 0, 0], [0, 1, 1], [1, 0, 1]]
+    acc_g, acc, iu = PP.confmat_compute(m)
+    assert abs(acc_g - 0.6) < 1e-6 and np.allclose(iu, [0.5, 0.5, 1 / 3], atol=1e-6)
+    # the example printed by the reference's utils.py:265-271
+    from sklearn.metrics import average_precision_score
+    y, s = [1, 0, 1, 0, 0, 0], [.98, .3, .86, .85, .36, .48]
+    assert abs(PP.average_precision(np.array(y), np.array(s)) - average_precision_score(y, s)) < 1e-12
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        y = rng.integers(0, 2, 20)
+        s = rng.random(20).round(1)      # ties
+        if y.sum():
+            assert abs(PP.average_precision(y, s) - average_precision_score(y, s)) < 1e-12
+
+
+def test_generalised_configs_run_small():
+    """197 -> N and 12 -> H generalisation (BASELINE configs 4/5 have no runnable reference): a small non-224 model."""
+    cfg = VF.VitConfig(img_size=64, patch_size=16, embed_dim=128, depth=6, num_heads=2, num_classes=5, topk=4)
+    sd = VF.peaked(VF.init_state_dict(cfg, 1), qkv_scale=20.0)
+    out = VF.forward(sd, VF.make_images(0, 2, size=64), cfg)
+    assert out["logits"].shape == (2, 5) and out["ori"].shape == (2, 4, 128) and out["P"][0].shape == (2, 2, 17, 17)

@@ -298,6 +298,7 @@ struct Attn2Params {
     float* attn;             // [B,H,N,N] or null
     int B, N, H;
     float scale, scale_log2;
+    unsigned long long* trace;   // debug: per-CTA phase timestamps (vtc_debug_set_trace), normally null
 };
 
 // One 32-column chunk of pass 2: e = 2^(s*sc - m*sc) with packed fp32x2 FMAs, row-sum partials, bf16 pack, swizzled STS.
@@ -388,6 +389,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int h = bh - b * p.H;
     const int NP = (N + 15) & ~15;
     const bool has_bias = p.key_bias != nullptr;
+    unsigned long long* tr = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+    auto stamp = [&](int slot) {
+        if (tr) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tr[slot] = t;
+        }
+    };
+    if (threadIdx.x == 0) stamp(0);
 
     if (warp == 4) {
         if (lane == 0) {
@@ -426,6 +436,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 0) stamp(1);
 
     if (warp == 4) {
         if (lane == 0) {
@@ -446,6 +457,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 : "memory");
 
             mbar_wait(bar_qk, 0);
+            stamp(6);
             tc_fence_after();
             const uint32_t idesc_s = make_idesc_bf16(128, NP, 0, 0);
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
@@ -482,6 +494,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const bool warp_active = (mt * 128 + quarter * 32) < N;      // warp-uniform: any valid query row in this warp?
 
         mbar_wait(s_full, 0);
+        if (threadIdx.x == 0) stamp(2);
         tc_fence_after();
         float inv = 0.f;
         if (warp_active) {
@@ -532,9 +545,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 for (int j = lane; j < N; j += 32) dst[j] = cls_s[j] * inv0;
             }
         }
+        if (threadIdx.x == 0) stamp(3);
         mbar_arrive(p_full);
 
         mbar_wait(o_full, 0);
+        if (threadIdx.x == 0) stamp(4);
         tc_fence_after();
         if (warp_active) {
             uint32_t o0[32], o1[32];
@@ -558,10 +573,14 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         }
     }
+    if (threadIdx.x == 0) stamp(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (threadIdx.x == 0) stamp(7);
 }
+
+static unsigned long long* g_attn_trace = nullptr;
 
 static bool attn_use_v1() {
     static int v = -1;
@@ -609,7 +628,8 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
         VTC_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured2 = true;
     }
-    Attn2Params p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale, scale * 1.4426950408889634f};
+    Attn2Params p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale, scale * 1.4426950408889634f,
+                  g_attn_trace};
     const int ntiles = (n_tokens + 127) / 128;
     attention2_kernel<<<batch * heads * ntiles, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
     VTC_CHECK_LAUNCH();
@@ -647,6 +667,8 @@ int head_mean(const float* attn_in, float* mean, int batch, int heads, int n_tok
 }  // namespace vtc
 
 extern "C" {
+// debug hook (not part of include/vtc.h): device buffer of 8 x uint64 per attention CTA receiving %globaltimer stamps
+__attribute__((visibility("default"))) void vtc_debug_set_attention_trace(void* buf) { vtc::g_attn_trace = static_cast<unsigned long long*>(buf); }
 int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch, int32_t n_tokens,
                   int32_t heads, float scale, void* stream) {
     return vtc::attention(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream));

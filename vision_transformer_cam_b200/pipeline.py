@@ -1,0 +1,99 @@
+"""The callers either side of the fused forward, as library functions: what predict.py:129-293 computes for an image
+(rollout map, per-layer CLS maps, class scores) and what validate.py:121-292 computes over a dataset (pseudo
+segmentation, confusion matrix / mIoU, mAP) -- batched, on the GPU, optionally sharded over the GPUs of one box.
+
+File / image IO, plotting and argparse of the reference drivers are out of scope; inputs here are already
+normalised image tensors [B,3,S,S] (the output of the reference's transforms, predict.py:72-75)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from . import cam as CAM
+from . import dist as D
+from .vit_model import VisionTransformer
+
+
+@dataclass
+class Prediction:
+    """predict.py outputs for a batch."""
+    logits: torch.Tensor            # [B,C] head
+    hwp_scores: torch.Tensor        # [B,C] sigmoid(hwp logits)         predict.py:291
+    rollout: torch.Tensor           # [B,H,W] rollout map / max          predict.py:229-247
+    layer_maps: torch.Tensor        # [L,B,H,W] uint8 per-layer CLS maps predict.py:261-269
+    cam: torch.Tensor               # [B,C,g,g] classic CAM              t.py:55-75
+
+
+@torch.no_grad()
+def predict(model: VisionTransformer, x: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> Prediction:
+    """predict.py:129-293 for a batch of normalised images (the reference runs batch 1)."""
+    out_hw = out_hw or (x.shape[-2], x.shape[-1])
+    o = model.forward_cam(x, attn_mean=True)
+    return Prediction(logits=o.logits, hwp_scores=torch.sigmoid(o.hwp_logits), rollout=CAM.rollout_map(o.attn_mean, out_hw),
+                      layer_maps=CAM.layer_maps(o.cls_rows, out_hw, as_u8=True),
+                      cam=CAM.classic_cam(o.tokens_last, model.head1.weight.data))
+
+
+class Validator:
+    """validate.py:118-292: pseudo segmentation + confusion matrix + per-image AP, accumulated on the GPU and reduced over
+    ranks at the end.  `mask_norm='image'` makes every image independent of its batch (the reference validates at batch 1,
+    where the batch-global max of vit_model.py:335 is per image)."""
+
+    def __init__(self, model: VisionTransformer, num_classes: int = 20, device="cuda"):
+        self.model = model
+        self.num_classes = num_classes
+        self.confmat = CAM.ConfusionMatrix(num_classes, device=device)
+        self.ap_sum = 0.0
+        self.ap_count = 0
+        self.device = torch.device(device)
+
+    @torch.no_grad()
+    def step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, seg_labels: Optional[torch.Tensor] = None,
+             out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """x [B,3,S,S]; target [B,C] multi-hot (mAP, validate.py:266-273); seg_labels [B,H,W] uint8 with 255 = ignore
+        (confusion matrix, validate.py:276).  Returns the pseudo segmentation uint8 [B,H,W]."""
+        out_hw = out_hw or ((seg_labels.shape[-2], seg_labels.shape[-1]) if seg_labels is not None else (x.shape[-2], x.shape[-1]))
+        o = self.model.forward_cam(x, mask_norm="image")
+        seg = CAM.hwp_pseudo_seg(o, self.model.head1.weight.data, out_hw)
+        if seg_labels is not None:
+            self.confmat.update(seg_labels.to(self.device), seg)
+        if target is not None:
+            aps = CAM.compute_mAP(target, torch.sigmoid(o.hwp_logits))
+            self.ap_sum += float(sum(aps))
+            self.ap_count += len(aps)
+        return seg
+
+    def finalize(self) -> Dict[str, object]:
+        """All-reduce the counters (NCCL / gloo) and compute global accuracy, per-class IoU, mIoU and mAP."""
+        stats = torch.tensor([self.ap_sum, float(self.ap_count)], dtype=torch.float64, device=self.confmat.mat.device)
+        D.reduce_counters(self.confmat.mat)
+        D.reduce_counters(stats)
+        acc_global, acc, iu = self.confmat.compute()
+        return dict(global_acc=float(acc_global), per_class_acc=acc.tolist(), iou=iu.tolist(), miou=float(iu.nanmean()),
+                    mAP=float(stats[0] / stats[1]) if float(stats[1]) > 0 else float("nan"), confmat=self.confmat.mat.clone())
+
+
+@torch.no_grad()
+def extract_cams_sharded(model: VisionTransformer, get_images: Callable[[int, int], torch.Tensor], n_items: int, batch: int = 256,
+                         with_rollout: bool = True, gather: bool = True) -> Dict[str, torch.Tensor]:
+    """BASELINE config 3: CAM (+ rollout) extraction over an `n_items`-image set, batch-sharded over the ranks of the
+    process group.  `get_images(lo, hi)` returns the normalised images [hi-lo,3,S,S] of global indices [lo,hi) on this
+    rank's GPU.  Returns (on every rank when `gather`) cam [n,C,g,g], rollout [n,g*g] and hwp_logits [n,C] in global
+    image order; collectives: one all_gather per output, outside the forward."""
+    rank, world = D.rank_world()
+    lo, hi = D.shard_range(n_items, rank, world)
+    cams, rolls, hwps = [], [], []
+    for b0, b1 in D.batches(lo, hi, batch):
+        o = model.forward_cam(get_images(b0, b1), attn_mean=with_rollout)
+        cams.append(CAM.classic_cam(o.tokens_last, model.head1.weight.data))
+        hwps.append(o.hwp_logits)
+        if with_rollout:
+            rolls.append(CAM.rollout_row(o.attn_mean))
+    out = {"cam": torch.cat(cams), "hwp_logits": torch.cat(hwps)}
+    if with_rollout:
+        out["rollout"] = torch.cat(rolls)
+    if gather and world > 1:
+        out = {k: D.gather_shards(v, n_items) for k, v in out.items()}
+    return out
