@@ -136,6 +136,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (for event loops that watch several barriers)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a mis-programmed pipeline traps (-> CUDA error on the host) instead of hanging
 // the GPU box.  try_wait suspends in hardware, so the bound is ~seconds, never hit when correct.
 #ifndef VTC_MBAR_SPIN_LIMIT
@@ -257,6 +269,25 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+// registers -> TMEM: 32 lanes x 16 columns of 32 bit (thread i of the warp writes lane base_lane + i)
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem: lane = row, 16-bit K elements packed two per column] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
@@ -372,6 +403,29 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
+}
+
+
+// 2^x for two values on the FMA pipe (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-5 polynomial for 2^f
+// (max relative error 3.7e-7, tools/fit_exp2.py), exponent re-inserted with one integer multiply-add.  B200 retires
+// only ~8 MUFU.EX2 per clock per SM, which bounds the attention softmax; half of its exponentials take this path.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t t2 = add2(x2, pack2(12582912.0f, 12582912.0f));
+    const uint64_t n2 = add2(t2, pack2(-12582912.0f, -12582912.0f));
+    const uint64_t f2 = fma2(n2, pack2(-1.0f, -1.0f), x2);
+    uint64_t q = fma2(pack2(0.0013395280111581087f, 0.0013395280111581087f), f2, pack2(0.009670763276517391f, 0.009670763276517391f));
+    q = fma2(q, f2, pack2(0.05550340563058853f, 0.05550340563058853f));
+    q = fma2(q, f2, pack2(0.24022211134433746f, 0.24022211134433746f));
+    q = fma2(q, f2, pack2(0.6931471824645996f, 0.6931471824645996f));
+    q = fma2(q, f2, pack2(1.0f, 1.0f));
+    float q0, q1, t0, t1;
+    unpack2(q, q0, q1);
+    unpack2(t2, t0, t1);
+    e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
 // erf-GELU of two values at once for the GEMM epilogue.
