@@ -186,6 +186,12 @@ VTC_API int vtc_layernorm_bf16(const float* x, const float* gamma, const float* 
  * cls_rows [B,H,N] fp32 (P[b,h,0,:]) or NULL; attn [B,H,N,N] fp32 full P or NULL. */
 VTC_API int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
                   int32_t n_tokens, int32_t heads, float scale, void* stream);
+/* The KV-blocked kernel behind vtc_attention for n_tokens > 256 (ViT-B/16-448: 785 tokens, ViT-L/16-384: 577 tokens),
+ * callable directly for any n_tokens <= 2048.  Same arguments and outputs as vtc_attention.
+ *   split != 0 ("fp32 mode"): operands are (hi, lo) bf16 pairs, x ~= hi + lo: qkv is [B,N,2,3,H,64] (all hi parts of a
+ *   token, then all lo parts), out is [B*N,2,H*64]; every product is evaluated as hi.hi + lo.hi + hi.lo in fp32. */
+VTC_API int vtc_attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
+                     int32_t n_tokens, int32_t heads, float scale, int32_t split, void* stream);
 /* head mean of P: attn [B,H,N,N] -> mean [B,N,N] (predict.py:189-190) */
 VTC_API int vtc_head_mean(const float* attn, float* mean, int32_t batch, int32_t heads, int32_t n_tokens, void* stream);
 /* CLS-row statistic (vit_model.py:329-335): cls_rows [B,H,N] -> cls_map [B,P] = ((mean_h + e0)/rowsum)[1:], and

@@ -126,8 +126,12 @@ print("rank", rank, "ok")
 def test_gloo_world_size_2_gather_and_reduce(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
+    import socket
+    with socket.socket() as sock:            # a free port: a fixed one collides with a run that has just finished
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(script), ROOT]
+           "--master-port", str(port), str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

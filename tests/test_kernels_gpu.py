@@ -187,9 +187,55 @@ def test_attention_large_dynamic_range(dev, amp):
         assert relerr(out.float(), out_ref.float()) < 1.5e-2
 
 
+@pytest.mark.parametrize("B,N,H,masked", [(2, 577, 16, True), (2, 785, 12, True), (1, 785, 3, False), (3, 197, 12, True),
+                                          (2, 256, 4, False), (5, 129, 2, True), (1, 50, 3, True), (1, 1025, 2, True)])
+def test_attention_kv_blocked(dev, B, N, H, masked):
+    """KV-blocked kernel (BASELINE configs 4 / 5: 785 and 577 tokens, and short sequences through the same code):
+    O, CLS rows and the full P of the second sweep against fp32 torch."""
+    from vision_transformer_cam_b200 import ops
+    qkv = _rand((B, N, 3 * H * 64), 50, dev, 1.5).bfloat16()
+    kb = None
+    if masked:
+        g = torch.Generator().manual_seed(51)
+        kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+        kb[:, 0] = 0
+        kb = kb.to(dev)
+    ref_o, ref_p = _attn_ref(qkv, H, 0.125, kb)
+    out, cls, attn = ops.attention_kv(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=True)
+    assert float((attn - ref_p).abs().max()) < 5e-6, float((attn - ref_p).abs().max())
+    assert float((cls - ref_p[:, :, 0, :]).abs().max()) < 5e-6
+    assert float((attn.sum(-1) - 1).abs().max()) < 2e-5
+    assert relerr(out.float(), ref_o) < 1e-2, relerr(out.float(), ref_o)
+    out2, cls2, _ = ops.attention_kv(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
+    assert torch.equal(out2, out) and torch.equal(cls2, cls)
+    if N > 256:      # vtc_attention dispatches long sequences to the same kernel
+        out3, cls3, _ = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
+        assert torch.equal(out3, out) and torch.equal(cls3, cls)
+
+
+@pytest.mark.parametrize("amp", [4.0, 12.0])
+def test_attention_kv_large_dynamic_range(dev, amp):
+    """Peaked logits over several key blocks: the lazy rescale must also rescale the O accumulator in TMEM."""
+    from vision_transformer_cam_b200 import ops
+    B, N, H = 2, 577, 4
+    qkv = _rand((B, N, 3 * H * 64), 55, dev, 1.0)
+    qkv[:, :, : 2 * H * 64] *= amp
+    qkv = qkv.bfloat16()
+    g = torch.Generator().manual_seed(56)
+    kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+    kb[:, 0] = 0
+    kb = kb.to(dev)
+    for bias in (None, kb):
+        out, cls, attn = ops.attention_kv(qkv, H, 0.125, key_bias=bias, want_cls=True, want_attn=True)
+        ref_o, ref_p = _attn_ref(qkv, H, 0.125, bias)
+        assert float((attn - ref_p).abs().max()) < 5e-5, float((attn - ref_p).abs().max())
+        assert float((cls - ref_p[:, :, 0, :]).abs().max()) < 2e-5
+        assert relerr(out.float(), ref_o) < 1.5e-2, relerr(out.float(), ref_o)
+
+
 def test_attention_too_long_is_an_error(dev):
     from vision_transformer_cam_b200 import ops, _lib
-    qkv = torch.zeros((1, 577, 3 * 64), device=dev, dtype=torch.bfloat16)
+    qkv = torch.zeros((1, 2049, 3 * 64), device=dev, dtype=torch.bfloat16)
     with pytest.raises(_lib.VtcError):
         ops.attention(qkv, 1, 0.125)
 

@@ -985,8 +985,13 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
-    VTC_REQUIRE(n_tokens <= attn::MAXN, VTC_ERR_SHAPE,
-                "attention: %d tokens > %d: the KV-blocked long-sequence kernel is not built yet", n_tokens, attn::MAXN);
+    static int kv_env = -1;
+    if (kv_env < 0) {
+        const char* e = getenv("VTC_ATTN_KV");
+        kv_env = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (n_tokens > attn::MAXN || kv_env == 1)      // long sequences: KV-blocked kernel (attention_kv.cu)
+        return attention_kv(qkv, key_bias, out, cls_rows, attn_out, batch, n_tokens, heads, scale, false, stream);
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     const int D = heads * attn::HD;

@@ -14,6 +14,9 @@ int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream);
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
               float scale, cudaStream_t stream);
+// KV-blocked kernel (attention_kv.cu): any n_tokens <= 2048; split = (hi, lo) bf16 operands: qkv [B,N,2,3,H,64], out [B*N,2,H*64]
+int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
+                 float scale, bool split, cudaStream_t stream);
 int head_mean(const float* attn, float* mean, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,

@@ -89,6 +89,20 @@ def attention(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[to
     return out, cls, attn
 
 
+def attention_kv(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, want_cls: bool = True,
+                 want_attn: bool = False, split: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """The KV-blocked kernel called directly (any N <= 2048).  split: qkv [B,N,2*3*H*64] and out [B,N,2*H*64] hold
+    (hi | lo) bf16 halves per token (`split_bf16`)."""
+    B, N, W = qkv.shape
+    D = W // (6 if split else 3)
+    out = torch.empty((B, N, D * (2 if split else 1)), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if want_cls else None
+    attn = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv.device) if want_attn else None
+    _lib.call("vtc_attention_kv", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls),
+              _ptr(attn), B, N, heads, scale, int(split), _stream())
+    return out, cls, attn
+
+
 def head_mean(attn: torch.Tensor) -> torch.Tensor:
     B, H, N, _ = attn.shape
     out = torch.empty((B, N, N), dtype=torch.float32, device=attn.device)
