@@ -1,0 +1,110 @@
+"""BASELINE.json configs 4 and 5 on the B200: ViT-B/16 at 448 px (785 tokens, rollout through all 12 layers) and
+ViT-L/16 at 384 px (577 tokens, 16 heads, 24 layers).  The reference hard-codes 197 tokens / 12 heads
+(vit_model.py:123,319,350), so the truth here is the generalised CPU oracle (oracle/vit_forward.py, identical to the
+reference where the reference runs) on the same seeded weights and images.  Tolerances: north_star bf16 bars."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2
+PEAKED_TOL = 2e-2        # see tests/test_forward_gpu.py
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a, b = torch.as_tensor(a).double().cpu().flatten(), torch.as_tensor(b).double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _build(cfg):
+    import vision_transformer_cam_b200 as V
+    torch.manual_seed(0)
+    model = V.VisionTransformer(img_size=cfg.img_size, patch_size=cfg.patch_size, embed_dim=cfg.embed_dim, depth=cfg.depth,
+                                num_heads=cfg.num_heads, num_classes=cfg.num_classes)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    return model.to("cuda:0").eval(), sd
+
+
+@pytest.fixture(scope="module")
+def b448(lib_built):
+    from oracle import vit_forward as VF
+    model, sd = _build(VF.VIT_B16_448)
+    return dict(model=model, sd=sd, cfg=VF.VIT_B16_448, VF=VF)
+
+
+def test_vit_b16_448_default_forward_cam_rollout(b448):
+    """config 4: 785 tokens; forward, classic CAM and the rollout through all 12 layers (needs every head-mean P)."""
+    from vision_transformer_cam_b200 import cam as CAM
+    from oracle import postproc as PP
+    VF, cfg, model = b448["VF"], b448["cfg"], b448["model"]
+    model.load_state_dict(b448["sd"])
+    x = VF.make_images(0, 2, size=448)
+    ref = VF.forward(b448["sd"], x, cfg)
+    o = model.forward_cam(x.to("cuda:0"), attn_mean=True, bg=True)
+    assert o.cls_rows.shape == (12, 2, 12, 785) and o.attn_mean.shape == (12, 2, 785, 785)
+    e = relerr(o.logits, ref["logits"])
+    c_cam = cosine(CAM.classic_cam(o.tokens_last, model.head1.weight.data), PP.classic_cam(ref["X"][-1], b448["sd"]["head1.weight"]))
+    c_roll = cosine(CAM.rollout_row(o.attn_mean), PP.rollout_dense(ref["P"]))
+    print(f"B/16-448 default: logits relerr {e:.2e} CAM cos {c_cam:.6f} rollout cos {c_roll:.6f}")
+    assert e <= LOGIT_TOL and c_cam >= 0.999 and c_roll >= 0.999
+    assert relerr(o.tokens_last, ref["X"][-1]) <= LOGIT_TOL
+    pbar = torch.stack([p.mean(1) for p in ref["P"]])
+    assert float((o.attn_mean.cpu() - pbar).abs().max()) <= 0.02 * float(pbar.max())
+    assert float((o.cls_rows.cpu() - ref["cls_rows"]).abs().max()) <= 0.02 * float(ref["cls_rows"].max())
+
+
+def test_vit_b16_448_peaked_masked_teacher_forced(b448):
+    """785 tokens with the background mask firing (qkv x5), discrete decisions teacher-forced."""
+    VF, cfg, model = b448["VF"], b448["cfg"], b448["model"]
+    sdp = VF.peaked(b448["sd"])
+    model.load_state_dict(sdp)
+    x = VF.make_images(0, 2, size=448)
+    ref = VF.forward(sdp, x, cfg, keep_P=False)
+    frac = float(torch.stack([b for b in ref["bg"] if b is not None]).mean())
+    assert 0.05 < frac < 0.95, frac
+    forced = {l: b for l, b in enumerate(ref["bg"]) if b is not None}
+    o = model.forward_cam(x.to("cuda:0"), bg=True, forced_bg=forced, forced_topk=ref["topk_idx"])
+    e, eh = relerr(o.logits, ref["logits"]), relerr(o.hwp_logits, ref["hwp"])
+    print(f"B/16-448 peaked (bg fraction {frac:.2f}): logits relerr {e:.2e} hwp relerr {eh:.2e}")
+    assert e <= PEAKED_TOL and eh <= PEAKED_TOL
+    assert relerr(o.hwp_tokens, ref["ori"]) <= PEAKED_TOL
+    # probabilities in the peaked regime: |logit| ~ 25x larger, so bf16 operand rounding moves a probability by up to ~3 %
+    assert float((o.cls_rows.cpu() - ref["cls_rows"]).abs().max()) <= 0.04 * float(ref["cls_rows"].max())
+    free = model.forward_cam(x.to("cuda:0"), bg=True)
+    agree = float((free.bg[4:].cpu() == torch.stack([b for b in ref["bg"] if b is not None]).to(torch.uint8)).float().mean())
+    print(f"free-running bg agreement {agree:.4f}")
+    assert agree >= 0.97
+
+
+def test_vit_l16_384_forward_cam(lib_built):
+    """config 5: D=1024, 16 heads, 24 layers, 577 tokens; the 6-tuple keeps the last 12 layers (vit_model.py:322)."""
+    from vision_transformer_cam_b200 import cam as CAM
+    from oracle import vit_forward as VF, postproc as PP
+    cfg = VF.VIT_L16_384
+    model, sd = _build(cfg)
+    x = VF.make_images(0, 1, size=384)
+    ref = VF.forward(sd, x, cfg, keep_P=False)
+    o = model.forward_cam(x.to("cuda:0"), tokens_layers=12)
+    assert o.cls_rows.shape == (24, 1, 16, 577) and o.tokens.shape == (12, 1, 577, 1024)
+    e = relerr(o.logits, ref["logits"])
+    c_cam = cosine(CAM.classic_cam(o.tokens_last, model.head1.weight.data), PP.classic_cam(ref["X"][-1], sd["head1.weight"]))
+    print(f"L/16-384 default: logits relerr {e:.2e} CAM cos {c_cam:.6f}")
+    assert e <= LOGIT_TOL and c_cam >= 0.999
+    assert relerr(o.tokens[0], ref["X"][12]) <= LOGIT_TOL and relerr(o.tokens[-1], ref["X"][-1]) <= LOGIT_TOL
+    assert float((o.cls_rows.cpu() - ref["cls_rows"]).abs().max()) <= 0.02 * float(ref["cls_rows"].max())
+    # peaked: masks fire on layers 5..23
+    sdp = VF.peaked(sd)
+    model.load_state_dict(sdp)
+    refp = VF.forward(sdp, x, cfg, keep_P=False)
+    forced = {l: b for l, b in enumerate(refp["bg"]) if b is not None}
+    op = model.forward_cam(x.to("cuda:0"), forced_bg=forced, forced_topk=refp["topk_idx"])
+    ep = relerr(op.logits, refp["logits"])
+    print(f"L/16-384 peaked teacher-forced: logits relerr {ep:.2e}")
+    assert ep <= PEAKED_TOL
+    out = model(x.to("cuda:0"))
+    assert len(out[1]) == 12 and out[1][0].shape == (1, 16, 577, 577) and len(out[2]) == 12 and out[5].shape == (1, 16, 1024)
