@@ -89,8 +89,16 @@ typedef struct vtc_weights {
 enum {
     VTC_FWD_MASK_NORM_IMAGE = 1 << 0, /* normalise the CLS map per image instead of the reference's batch-global
                                          max (vit_model.py:335,372) */
-    VTC_FWD_FP32_SPLIT      = 1 << 1  /* reserved: split-bf16 (3x) GEMMs for the 1e-4 "fp32 mode" */
+    VTC_FWD_FP32_SPLIT      = 1 << 1  /* the "fp32 mode" (logits within 1e-4 of the fp32 reference): must be set iff the
+                                         model's precision is VTC_PRECISION_FP32_SPLIT */
 };
+
+/* Arithmetic of the dense contractions (vtc_model_set_precision).
+ *   VTC_PRECISION_BF16        bf16 operands, fp32 accumulation (default; BASELINE's bf16 mode, logits within 1e-2)
+ *   VTC_PRECISION_FP32_SPLIT  every GEMM / attention operand x is carried as a pair of bf16 (hi, lo), x ~= hi + lo
+ *                             (16 mantissa bits), and every product is evaluated on the tensor cores as
+ *                             hi.hi + lo.hi + hi.lo with fp32 accumulation: 3x the MMA work, ~2^-17 relative error */
+enum { VTC_PRECISION_BF16 = 0, VTC_PRECISION_FP32_SPLIT = 1 };
 
 /* Optional teacher forcing of the discrete decisions (tests only; NULL = compute them). */
 typedef struct vtc_forcing {
@@ -128,6 +136,9 @@ VTC_API uint64_t vtc_launch_count(void);
 /* replaces VisionTransformer.__init__ shape bookkeeping (vit_model.py:215-301) */
 VTC_API int vtc_model_create(const vtc_config* cfg, vtc_model** out);
 VTC_API int vtc_model_destroy(vtc_model* m);
+/* Select the arithmetic BEFORE vtc_model_packed_bytes / vtc_model_pack_weights / vtc_workspace_bytes / vtc_forward:
+ * it changes the size and layout of the packed weights and of the workspace. */
+VTC_API int vtc_model_set_precision(vtc_model* m, int32_t precision);
 /* bytes of the packed (bf16, K-major) GEMM weight buffer the caller must provide */
 VTC_API size_t vtc_model_packed_bytes(const vtc_model* m);
 /* fp32 state_dict tensors -> packed bf16 buffer (enqueued on stream); the fp32 vectors (biases, LayerNorm,
@@ -167,6 +178,17 @@ enum { VTC_EPI_BIAS = 0, VTC_EPI_BIAS_GELU = 1, VTC_EPI_BIAS_RESIDUAL = 2, VTC_E
  * Requires K % 64 == 0, Nout % 256 == 0. */
 VTC_API int vtc_gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos,
                   void* out, int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream);
+
+/* The same GEMM on split operands (VTC_PRECISION_FP32_SPLIT): A [M,2K] and W [Nout,2K] hold (hi | lo) bf16 halves per row
+ * (vtc_split_bf16); bf16 outputs are written as halves too, [M,2*Nout]; fp32 outputs are unchanged. */
+VTC_API int vtc_gemm_split(const void* A, const void* W, const float* bias, const float* residual, const float* pos,
+                   void* out, int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream);
+/* fp32 [rows,cols] -> (hi | lo) bf16 halves [rows,2*cols]: hi = bf16(x), lo = bf16(x - hi); cols % 8 == 0 */
+VTC_API int vtc_split_bf16(const float* src, void* dst, size_t rows, size_t cols, void* stream);
+/* vtc_patchify / vtc_layernorm_bf16 with split outputs: patches [B*P, 2*in_c*p*p], y [rows, 2*D] */
+VTC_API int vtc_patchify_split(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream);
+VTC_API int vtc_layernorm_split(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim,
+                        float eps, void* stream);
 
 /* fp32 -> bf16 (weight packing, also used by tests) */
 VTC_API int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream);

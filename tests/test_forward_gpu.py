@@ -199,3 +199,39 @@ def test_full_batch_256_properties(env):
     part = model.forward_cam(x[64:96], mask_norm="image")
     assert torch.equal(part.logits, o.logits[64:96])
     assert torch.equal(part.hwp_tokens, o.hwp_tokens[64:96])
+
+
+FP32_TOL = 1e-4           # BASELINE.json north_star: logits max relative error in fp32 mode
+
+
+def test_fp32_mode_matches_reference_golden(env):
+    """precision='fp32' (split-bf16 operands, 3 tensor-core products per contraction): logits within 1e-4 of the fp32
+    reference on the reference's own weights, and on the peaked regime with the discrete decisions teacher-forced."""
+    model = env["model"]
+    model.set_precision("fp32")
+    try:
+        gold = np.load(os.path.join(GOLDEN, "default_b2.npz"))
+        load(env, "default")
+        x = env["VF"].make_images(0, 2).to(env["dev"])
+        o = model.forward_cam(x, tokens_layers=12, bg=True)
+        e, eh = relerr(o.logits, gold["logits"]), relerr(o.hwp_logits, gold["hwp"])
+        et = relerr(o.tokens[:, :, 0, :], gold["x_cls"])
+        print(f"fp32 mode default: logits {e:.2e} hwp {eh:.2e} cls tokens {et:.2e}")
+        assert e <= FP32_TOL and et <= FP32_TOL
+        assert float((o.cls_rows.cpu() - torch.from_numpy(gold["cls_rows"])).abs().max()) <= 1e-4 * float(gold["cls_rows"].max())
+        assert torch.equal(o.topk_idx.cpu().long().sort(-1).values, torch.from_numpy(gold["topk_idx"]).long().sort(-1).values) or eh <= 1e-2
+        gold = np.load(os.path.join(GOLDEN, "peaked_b3.npz"))
+        load(env, "peaked")
+        x = env["VF"].make_images(0, 3).to(env["dev"])
+        forced = {4 + i: torch.from_numpy(gold["bg"][i]) for i in range(gold["bg"].shape[0])}
+        o = model.forward_cam(x, tokens_layers=12, bg=True, forced_bg=forced, forced_topk=torch.from_numpy(gold["topk_idx"]))
+        e, eh = relerr(o.logits, gold["logits"]), relerr(o.hwp_logits, gold["hwp"])
+        print(f"fp32 mode peaked (teacher-forced): logits {e:.2e} hwp {eh:.2e}")
+        assert e <= FP32_TOL and eh <= FP32_TOL and relerr(o.hwp_tokens, gold["ori"]) <= FP32_TOL
+        # free running: with fp32-grade arithmetic the discrete decisions themselves agree
+        o = model.forward_cam(x, bg=True)
+        agree = float((o.bg[4:].cpu() == torch.from_numpy(gold["bg"])).float().mean())
+        print(f"fp32 mode peaked free-running: bg agreement {agree:.5f} logits {relerr(o.logits, gold['logits']):.2e}")
+        assert agree >= 0.999
+    finally:
+        model.set_precision("bf16")

@@ -340,3 +340,71 @@ def test_hwp_vote_seg_confmat(dev):
     assert np.array_equal(mat.cpu().numpy(), ref_mat)            # integer counters: bit exact
     ops.confmat_update(mat, gt.to(dev), seg)
     assert np.array_equal(mat.cpu().numpy(), 2 * ref_mat)
+
+
+# ------------------------------------------------------------------------- fp32 mode (split-bf16 operands)
+def test_split_roundtrip_and_gemm_split(dev):
+    """x ~= hi + lo carries 16 mantissa bits; the split GEMM (hi.hi + lo.hi + hi.lo, fp32 accumulation) must be ~2^-16
+    accurate against an fp64 matmul of the SAME fp32 operands: 1e-5 of the output scale (bf16 GEMM: ~4e-3)."""
+    from vision_transformer_cam_b200 import ops, _lib
+    M, N, K = 1000, 768, 768
+    a = _rand((M, K), 70, dev)
+    w = _rand((N, K), 71, dev, 0.05)
+    bias = _rand((N,), 72, dev)
+    a2, w2 = ops.split_bf16(a), ops.split_bf16(w)
+    assert a2.shape == (M, 2 * K)
+    assert float((ops.merge_split(a2) - a).abs().max()) <= 2.0 ** -16 * float(a.abs().max())
+    ref = (a.double() @ w.double().T + bias.double())
+    out = ops.gemm_split(a2, w2, bias, _lib.EPI_BIAS)
+    assert out.shape == (M, 2 * N)
+    e = relerr(ops.merge_split(out), ref)
+    assert e < 1e-5, e
+    g = ops.gemm_split(a2, w2, bias, _lib.EPI_BIAS_GELU)
+    eg = relerr(ops.merge_split(g), F.gelu(ref))
+    assert eg < 1e-5, eg
+    res = _rand((M, N), 73, dev)
+    r = ops.gemm_split(a2, w2, bias, _lib.EPI_BIAS_RESIDUAL, residual=res)
+    assert relerr(r, ref + res.double()) < 1e-5
+    # bf16 GEMM on the same data for scale: three orders of magnitude worse
+    assert relerr(ops.gemm_bf16(a.bfloat16(), w.bfloat16(), bias, _lib.EPI_BIAS).float(), ref) > 1e-4
+
+
+def test_layernorm_and_patchify_split(dev):
+    from vision_transformer_cam_b200 import ops
+    x = _rand((300, 768), 74, dev, 3.0) + 0.5
+    w, b = _rand((768,), 75, dev), _rand((768,), 76, dev)
+    y = ops.layernorm_bf16(x, w, b, 1e-6, split=True)
+    ref = F.layer_norm(x.double(), (768,), w.double(), b.double(), 1e-6)
+    assert y.shape == (300, 1536) and relerr(ops.merge_split(y), ref) < 2e-5
+    img = _rand((2, 3, 64, 64), 77, dev)
+    p = ops.patchify(img, 16, split=True)
+    refp = img.unfold(2, 16, 16).unfold(3, 16, 16).permute(0, 2, 3, 1, 4, 5).reshape(2 * 16, 768)
+    assert p.shape == (32, 1536) and float((ops.merge_split(p) - refp).abs().max()) <= 2.0 ** -16 * float(refp.abs().max())
+
+
+@pytest.mark.parametrize("B,N,H,masked", [(2, 197, 12, True), (1, 577, 4, True), (2, 130, 3, False)])
+def test_attention_split(dev, B, N, H, masked):
+    """fp32-mode attention: q, k, v and P as (hi, lo) pairs.  Against fp64 attention of the same fp32 q, k, v."""
+    from vision_transformer_cam_b200 import ops
+    D = H * 64
+    qkv = _rand((B, N, 3 * D), 80, dev, 1.5)
+    kb = None
+    if masked:
+        g = torch.Generator().manual_seed(81)
+        kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+        kb[:, 0] = 0
+        kb = kb.to(dev)
+    q, k, v = qkv.double().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) * 0.125
+    if kb is not None:
+        v_ = (kb != 0).double()
+        s = s - 100.0 * torch.clamp(v_[:, :, None] + v_[:, None, :], max=1.0)[:, None]
+    ref_p = s.softmax(-1)
+    ref_o = (ref_p @ v).transpose(1, 2).reshape(B, N, D)
+    out, cls, attn = ops.attention_kv(ops.split_bf16(qkv), H, 0.125, key_bias=kb, want_cls=True, want_attn=True, split=True)
+    assert out.shape == (B, N, 2 * D)
+    eo = relerr(ops.merge_split(out), ref_o)
+    ep = float((attn.double() - ref_p).abs().max())
+    print(f"split attention N={N}: O relerr {eo:.2e}, P abs err {ep:.2e}")
+    assert eo < 3e-5, eo          # bf16 attention: ~5e-3
+    assert ep < 2e-5 and float((cls.double() - ref_p[:, :, 0, :]).abs().max()) < 2e-5

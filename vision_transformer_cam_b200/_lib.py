@@ -14,6 +14,7 @@ ERR_NAMES = {-1: "VTC_ERR_ARG", -2: "VTC_ERR_SHAPE", -3: "VTC_ERR_ARCH", -4: "VT
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_PATCH_EMBED = 0, 1, 2, 3
 FWD_MASK_NORM_IMAGE = 1 << 0
 FWD_FP32_SPLIT = 1 << 1
+PRECISION_BF16, PRECISION_FP32_SPLIT = 0, 1
 PROF_KINDS = ("patchify", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "cls", "head_mean", "heads")
 
 c_f32p = C.c_void_p   # device pointers are passed as integers
@@ -70,6 +71,11 @@ SIGNATURES = {
     "vtc_workspace_bytes": (_Z, [_P, _I, C.POINTER(Outputs)]),
     "vtc_forward": (C.c_int, [_P, _P, _I, C.POINTER(Outputs), C.POINTER(Forcing), _P, _Z, _U, _P]),
     "vtc_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vtc_model_set_precision": (C.c_int, [_P, _I]),
+    "vtc_gemm_split": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vtc_split_bf16": (C.c_int, [_P, _P, _Z, _Z, _P]),
+    "vtc_patchify_split": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "vtc_layernorm_split": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vtc_cast_bf16": (C.c_int, [_P, _P, _Z, _P]),
     "vtc_patchify": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "vtc_cls_token_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

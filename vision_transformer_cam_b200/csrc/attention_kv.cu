@@ -13,7 +13,7 @@
 // Softmax is single pass with a lazily raised running maximum (as in attention3_kernel): S_j is read from TMEM once,
 // exponentials are taken against the running maximum m, which is only raised when a chunk exceeds it by more than 2^8;
 // in that (rare) event the bf16 P chunks already stored, the row sum, the staged CLS row and the O accumulator in TMEM
-// are rescaled by 2^(m_old - m_new).  P never touches shared memory: it overwrites the consumed S columns as bf16 pairs
+// are rescaled by 2^(m_old - m_new), an exact power of two (m moves by whole octaves).  P never touches shared memory: it overwrites the consumed S columns as bf16 pairs
 // (tcgen05.st) and feeds the second MMA as its TMEM A operand.
 //
 // The reference mask -100*min(v_i + v_j, 1) (vit_model.py:348-361) is applied in registers: key j gets key_bias[j] on
@@ -137,8 +137,11 @@ __device__ __forceinline__ void chunk_sweep1(uint32_t (&cur)[32], int c_in_blk, 
     } else {
         const bool need = (mc - st.m) > RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, need)) {
-            const float f = need ? ex2_approx(st.m - mc) : 1.0f;
-            if (need) st.m = mc;
+            // raise m by a whole number of octaves: the factor is an exact power of two, so rescaling the stored bf16 (hi, lo)
+            // pairs, the fp32 O accumulator and the row sum introduces no rounding at all
+            const int d = need ? static_cast<int>(ceilf(mc - st.m)) : 0;
+            const float f = d >= 127 ? 0.f : __int_as_float((127 - d) << 23);
+            st.m += static_cast<float>(d);
             st.sum2 = mul2(st.sum2, pack2(f, f));
             tmem_st_wait();
             for (int cc = 0; cc < c_in_blk; ++cc) {

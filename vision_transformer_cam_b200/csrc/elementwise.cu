@@ -34,9 +34,51 @@ int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream) {
     return VTC_OK;
 }
 
+// ---- split (fp32 mode) ------------------------------------------------------------------------------
+// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits.  Rows keep their halves side by side, [rows, 2*cols].
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+    hi = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    lo = make_uint4(pack_bf16x2(a.x - __uint_as_float(hi.x << 16), a.y - __uint_as_float(hi.x & 0xffff0000u)),
+                    pack_bf16x2(a.z - __uint_as_float(hi.y << 16), a.w - __uint_as_float(hi.y & 0xffff0000u)),
+                    pack_bf16x2(b.x - __uint_as_float(hi.z << 16), b.y - __uint_as_float(hi.z & 0xffff0000u)),
+                    pack_bf16x2(b.z - __uint_as_float(hi.w << 16), b.w - __uint_as_float(hi.w & 0xffff0000u)));
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t rows, size_t cols) {
+    const size_t c8 = cols / 8;
+    const size_t total = rows * c8;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t r = i / c8, c = (i - r * c8) * 8;
+        const float4 a = ld_stream_f4(src + r * cols + c);
+        const float4 b = ld_stream_f4(src + r * cols + c + 4);
+        uint4 hi, lo;
+        split8(a, b, hi, lo);
+        st_u4(dst + r * 2 * cols + c, hi);
+        st_u4(dst + r * 2 * cols + cols + c, lo);
+    }
+}
+
+int split_bf16(const float* src, void* dst, size_t rows, size_t cols, cudaStream_t stream) {
+    VTC_REQUIRE(src && dst, VTC_ERR_ARG, "split: null pointer");
+    VTC_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0, VTC_ERR_SHAPE, "split: cols must be a positive multiple of 8");
+    VTC_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, VTC_ERR_ARG,
+                "split: pointers must be 16-byte aligned");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t total = rows * (cols / 8);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    split_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 // ---- patchify --------------------------------------------------------------------------------------
 // One thread moves 8 consecutive pixels of one image row: reads are fully coalesced along x (the fp32 side is
 // 2/3 of the bytes); each 16-byte bf16 store lands in patch row (b,py,px) at k = c*p*p + kh*p + kw.
+template <bool SPLIT>
 __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int in_c, int S, int p, size_t total8) {
     const int g = S / p;
     const int kdim = in_c * p * p;
@@ -55,12 +97,15 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
         const int py = y / p, kh = y - py * p;
         const int px = x0 / p, kw = x0 - px * p;
         const size_t row = (b * g + py) * g + px;
-        __nv_bfloat16* dst = out + row * kdim + (c * p + kh) * p + kw;
-        st_u4(dst, make_uint4(pack_bf16x2(a0.x, a0.y), pack_bf16x2(a0.z, a0.w), pack_bf16x2(a1.x, a1.y), pack_bf16x2(a1.z, a1.w)));
+        __nv_bfloat16* dst = out + row * kdim * (SPLIT ? 2 : 1) + (c * p + kh) * p + kw;
+        uint4 hi, lo;
+        split8(a0, a1, hi, lo);
+        st_u4(dst, hi);
+        if (SPLIT) st_u4(dst + kdim, lo);
     }
 }
 
-int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream) {
+int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream, int split) {
     VTC_REQUIRE(x && patches, VTC_ERR_ARG, "patchify: null pointer");
     VTC_REQUIRE(batch > 0 && in_c > 0 && img > 0 && patch > 0, VTC_ERR_SHAPE, "patchify: bad shape");
     VTC_REQUIRE(img % patch == 0 && patch % 8 == 0, VTC_ERR_SHAPE, "patchify: img %d / patch %d unsupported (patch %% 8 == 0 required)", img, patch);
@@ -70,7 +115,8 @@ int patchify(const float* x, void* patches, int batch, int in_c, int img, int pa
     size_t blocks = (total8 + 255) / 256;
     const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
     if (blocks > cap) blocks = cap;
-    patchify_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, total8);
+    if (split) patchify_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, total8);
+    else patchify_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, total8);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
@@ -99,7 +145,7 @@ int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens
 // ---- LayerNorm ---------------------------------------------------------------------------------------
 // One warp per row, the row lives in registers (NV float4 per lane), two-pass mean / variance in fp32 exactly
 // like ATen's (sum of squared deviations), bf16 output.  8 rows per 256-thread CTA.
-template <int NV>
+template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows,
                                                         float eps) {
@@ -122,7 +168,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         q += (a * a + b * b) + (c * c + d * d);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-    __nv_bfloat16* dst = y + static_cast<size_t>(row) * D;
+    __nv_bfloat16* dst = y + static_cast<size_t>(row) * D * (SPLIT ? 2 : 1);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = (lane + 32 * i) * 4;
@@ -132,11 +178,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
         const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
         const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
-        *reinterpret_cast<uint2*>(dst + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        const uint2 hi = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        *reinterpret_cast<uint2*>(dst + c) = hi;
+        if (SPLIT)
+            *reinterpret_cast<uint2*>(dst + D + c) =
+                make_uint2(pack_bf16x2(o0 - __uint_as_float(hi.x << 16), o1 - __uint_as_float(hi.x & 0xffff0000u)),
+                           pack_bf16x2(o2 - __uint_as_float(hi.y << 16), o3 - __uint_as_float(hi.y & 0xffff0000u)));
     }
 }
 
-int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream) {
+template <int NV>
+static void launch_ln(int grid, cudaStream_t stream, const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, float eps,
+                      int split) {
+    if (split) layernorm_kernel<NV, true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps);
+    else layernorm_kernel<NV, false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps);
+}
+
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream,
+                   int split) {
     VTC_REQUIRE(x && gamma && beta && y, VTC_ERR_ARG, "layernorm: null pointer");
     VTC_REQUIRE(rows > 0, VTC_ERR_SHAPE, "layernorm: rows=%d", rows);
     int rc = check_arch();
@@ -144,12 +203,12 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* 
     const int grid = cdiv(rows, 8);
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
     switch (dim) {
-        case 256: layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
-        case 384: layernorm_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
-        case 512: layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
-        case 768: layernorm_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
-        case 1024: layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
-        case 1280: layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps); break;
+        case 256: launch_ln<2>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
+        case 384: launch_ln<3>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
+        case 512: launch_ln<4>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
+        case 768: launch_ln<6>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
+        case 1024: launch_ln<8>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
+        case 1280: launch_ln<10>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
         default:
             set_last_error("layernorm: dim %d unsupported (256/384/512/768/1024/1280)", dim);
             return VTC_ERR_SHAPE;
@@ -164,8 +223,18 @@ extern "C" {
 int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
     return vtc::cast_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
 }
+int vtc_split_bf16(const float* src, void* dst, size_t rows, size_t cols, void* stream) {
+    return vtc::split_bf16(src, dst, rows, cols, static_cast<cudaStream_t>(stream));
+}
 int vtc_patchify(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream) {
-    return vtc::patchify(x, patches, batch, in_c, img, patch, static_cast<cudaStream_t>(stream));
+    return vtc::patchify(x, patches, batch, in_c, img, patch, static_cast<cudaStream_t>(stream), 0);
+}
+int vtc_patchify_split(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream) {
+    return vtc::patchify(x, patches, batch, in_c, img, patch, static_cast<cudaStream_t>(stream), 1);
+}
+int vtc_layernorm_split(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim, float eps,
+                        void* stream) {
+    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream), 1);
 }
 int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int32_t batch, int32_t n_tokens, int32_t dim,
                        void* stream) {
@@ -173,6 +242,6 @@ int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, float* to
 }
 int vtc_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim, float eps,
                        void* stream) {
-    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream));
+    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream), 0);
 }
 }

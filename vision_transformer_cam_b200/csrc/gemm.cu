@@ -35,6 +35,7 @@ struct Params {
     void* out;
     int M, N, K;
     int tokens;    // patch-embed epilogue: tokens per image (P = tokens - 1)
+    int split;     // operands are (hi | lo) bf16 halves [rows, 2K]: three K segments hi.hi, lo.hi, hi.lo
 };
 }  // namespace gemm
 
@@ -77,7 +78,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_m = (p.M + BM - 1) / BM;
     const int num_n = p.N / BN;
     const int num_tiles = num_m * num_n;
-    const int num_k = p.K / BK;
+    const int nk1 = p.K / BK;
+    const int num_k = p.split ? 3 * nk1 : nk1;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -87,11 +89,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m0 = (tile / num_n) * BM;
                 const int n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_k; ++kb) {
+                    const int seg = kb / nk1, kr = (kb - seg * nk1) * BK;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
-                    tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-                    tma_load_2d(a_dst + A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                    tma_load_2d(a_dst, &tmA, &full_bar[s], kr + (seg == 1 ? p.K : 0), m0);
+                    tma_load_2d(a_dst + A_BYTES, &tmB, &full_bar[s], kr + (seg == 2 ? p.K : 0), n0);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -246,10 +249,11 @@ static_assert(SMEM_BYTES <= 232448, "gemm2 smem budget");
 struct Params {
     const float* bias;
     int M, N, K;
+    int split;     // see gemm::Params::split; bf16 outputs are then written as (hi | lo) halves [M, 2N]
 };
 }  // namespace gemm2
 
-template <int EPI>
+template <int EPI, bool SPLIT>
 __global__ void __launch_bounds__(gemm2::THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const gemm2::Params p) {
@@ -293,7 +297,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
     const int num_n = p.N / BN;
     const int num_tiles = num_m * num_n;
-    const int num_k = p.K / BK;
+    const int nk1 = p.K / BK;
+    const int num_k = SPLIT ? 3 * nk1 : nk1;
     const int pair = blockIdx.x >> 1;
     const int npairs = gridDim.x >> 1;
 
@@ -305,11 +310,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
                 const int n0 = (tile % num_n) * BN + rank * (BN / 2);
                 for (int kb = 0; kb < num_k; ++kb) {
+                    const int seg = kb / nk1, kr = (kb - seg * nk1) * BK;      // split: A = hi, lo, hi ; W = hi, hi, lo
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);     // both CTAs' bytes land on this barrier
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
-                    tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-                    tma_load_2d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                    tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kr + (seg == 1 ? p.K : 0), m0);
+                    tma_load_2d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], kr + (seg == 2 ? p.K : 0), n0);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -367,6 +373,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int col0 = half * 128 + c * CHUNK_COLS;
                 const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0);
                 uint32_t pk[32];
+                uint32_t pl[(EPI == VTC_EPI_BIAS_RESIDUAL || !SPLIT) ? 1 : 32];      // split mode: low halves
                 if (EPI == VTC_EPI_BIAS_RESIDUAL) {
                     tmem_ld_32x32b_x32(t_row + c * 32, pk);
                     tmem_ld_wait();
@@ -393,32 +400,52 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         unpack2(add2(pack2u(r1[4 * j + 0], r1[4 * j + 1]), pack2(c4.x, c4.y)), w0, w1);
                         unpack2(add2(pack2u(r1[4 * j + 2], r1[4 * j + 3]), pack2(c4.z, c4.w)), w2, w3);
                         if (EPI == VTC_EPI_BIAS_GELU) {
-                            gelu2(v0, v1, v0, v1);
-                            gelu2(v2, v3, v2, v3);
-                            gelu2(w0, w1, w0, w1);
-                            gelu2(w2, w3, w2, w3);
+                            if (SPLIT) {      // fp32 mode: exact erf instead of the 4e-7 polynomial
+                                v0 = gelu_erf_exact(v0); v1 = gelu_erf_exact(v1); v2 = gelu_erf_exact(v2); v3 = gelu_erf_exact(v3);
+                                w0 = gelu_erf_exact(w0); w1 = gelu_erf_exact(w1); w2 = gelu_erf_exact(w2); w3 = gelu_erf_exact(w3);
+                            } else {
+                                gelu2(v0, v1, v0, v1);
+                                gelu2(v2, v3, v2, v3);
+                                gelu2(w0, w1, w0, w1);
+                                gelu2(w2, w3, w2, w3);
+                            }
                         }
                         pk[2 * j] = pack_bf16x2(v0, v1);
                         pk[2 * j + 1] = pack_bf16x2(v2, v3);
                         pk[16 + 2 * j] = pack_bf16x2(w0, w1);
                         pk[16 + 2 * j + 1] = pack_bf16x2(w2, w3);
+                        if (EPI != VTC_EPI_BIAS_RESIDUAL) {
+                            if (SPLIT) {
+                                pl[2 * j] = pack_bf16x2(v0 - __uint_as_float(pk[2 * j] << 16), v1 - __uint_as_float(pk[2 * j] & 0xffff0000u));
+                                pl[2 * j + 1] = pack_bf16x2(v2 - __uint_as_float(pk[2 * j + 1] << 16), v3 - __uint_as_float(pk[2 * j + 1] & 0xffff0000u));
+                                pl[16 + 2 * j] = pack_bf16x2(w0 - __uint_as_float(pk[16 + 2 * j] << 16), w1 - __uint_as_float(pk[16 + 2 * j] & 0xffff0000u));
+                                pl[16 + 2 * j + 1] = pack_bf16x2(w2 - __uint_as_float(pk[16 + 2 * j + 1] << 16), w3 - __uint_as_float(pk[16 + 2 * j + 1] & 0xffff0000u));
+                            }
+                        }
                     }
                 }
-                // staging buffer `buf` is free once the bulk store issued from it two chunks ago has read it
-                if (issuer) tma_store_wait_read<1>();
-                named_bar_sync(bar_id, 128);
-                uint8_t* row_ptr = stage_out + buf * OUT_BUF_BYTES + r_local * 128;
+                // Stage one 128 x 128-byte tile in shared memory (swizzled) and hand it to the TMA; staging buffer `buf` is free
+                // once the bulk store issued from it two tiles ago has read it.
+                auto stage_and_store = [&](const uint32_t* v, int col) {
+                    if (issuer) tma_store_wait_read<1>();
+                    named_bar_sync(bar_id, 128);
+                    uint8_t* row_ptr = stage_out + buf * OUT_BUF_BYTES + r_local * 128;
 #pragma unroll
-                for (int g8 = 0; g8 < 8; ++g8)
-                    st_u4(row_ptr + ((g8 ^ (r_local & 7)) * 16), make_uint4(pk[4 * g8], pk[4 * g8 + 1], pk[4 * g8 + 2], pk[4 * g8 + 3]));
-                fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (issuer) {
-                    if (EPI == VTC_EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, n0 + col0, m0);
-                    else tma_store_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, n0 + col0, m0);
-                    tma_store_commit();
+                    for (int g8 = 0; g8 < 8; ++g8)
+                        st_u4(row_ptr + ((g8 ^ (r_local & 7)) * 16), make_uint4(v[4 * g8], v[4 * g8 + 1], v[4 * g8 + 2], v[4 * g8 + 3]));
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
+                        if (EPI == VTC_EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, m0);
+                        else tma_store_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, m0);
+                        tma_store_commit();
+                    }
+                    buf ^= 1;
+                };
+                stage_and_store(pk, n0 + col0);
+                if (EPI != VTC_EPI_BIAS_RESIDUAL) {
+                    if (SPLIT) stage_and_store(pl, p.N + n0 + col0);
                 }
-                buf ^= 1;
             }
             tc_fence_before();
             __syncwarp();
@@ -434,11 +461,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-template <int EPI>
+template <int EPI, bool SPLIT>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const gemm2::Params& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
         configured = true;
     }
     const int tiles = cdiv(p.M, 2 * gemm2::BM) * (p.N / gemm2::BN);
@@ -457,7 +484,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     note_launch();
-    VTC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<EPI>, tmA, tmB, tmO, p));
+    VTC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<EPI, SPLIT>, tmA, tmB, tmO, p));
     return VTC_OK;
 }
 
@@ -471,7 +498,7 @@ static bool use_v1() {
 }
 
 int gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out, int M,
-              int N, int K, int epilogue, int tokens, cudaStream_t stream) {
+              int N, int K, int epilogue, int tokens, cudaStream_t stream, int split) {
     VTC_REQUIRE(A && W && bias && out, VTC_ERR_ARG, "gemm: null pointer");
     VTC_REQUIRE(M > 0 && N > 0 && K > 0, VTC_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
     VTC_REQUIRE(K % gemm::BK == 0, VTC_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", K, gemm::BK);
@@ -482,24 +509,26 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
                 "gemm: patch-embed epilogue needs pos_embed and M %% (tokens-1) == 0");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    const bool v1 = use_v1() || epilogue == VTC_EPI_PATCH_EMBED;
+    // the single-CTA kernel has no split bf16 epilogue: in split mode it only serves the fp32-output patch embedding
+    const bool v1 = (use_v1() && !split) || epilogue == VTC_EPI_PATCH_EMBED;
+    const uint64_t kcols = static_cast<uint64_t>(split ? 2 : 1) * K;       // (hi | lo) halves side by side
     CUtensorMap tmA, tmB;
     {
-        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-        uint64_t strides[1] = {(uint64_t)K * 2};
+        uint64_t dims[2] = {kcols, (uint64_t)M};
+        uint64_t strides[1] = {kcols * 2};
         uint32_t box[2] = {gemm::BK, 128};
         rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
         if (rc != VTC_OK) return rc;
     }
     {
-        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
-        uint64_t strides[1] = {(uint64_t)K * 2};
+        uint64_t dims[2] = {kcols, (uint64_t)N};
+        uint64_t strides[1] = {kcols * 2};
         uint32_t box[2] = {gemm::BK, v1 ? 256u : 128u};
         rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
         if (rc != VTC_OK) return rc;
     }
     if (v1) {
-        gemm::Params p{bias, residual, pos, out, M, N, K, tokens};
+        gemm::Params p{bias, residual, pos, out, M, N, K, tokens, split};
         switch (epilogue) {
             case VTC_EPI_BIAS: return launch_gemm<VTC_EPI_BIAS>(tmA, tmB, p, stream);
             case VTC_EPI_BIAS_GELU: return launch_gemm<VTC_EPI_BIAS_GELU>(tmA, tmB, p, stream);
@@ -508,7 +537,7 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
         }
     }
     CUtensorMap tmO;
-    gemm2::Params p2{bias, M, N, K};
+    gemm2::Params p2{bias, M, N, K, split};
     if (epilogue == VTC_EPI_BIAS_RESIDUAL) {
         // out = residual + A.W^T + bias, with the add done by the TMA reduction into `out`
         if (out != static_cast<const void*>(residual))
@@ -518,20 +547,27 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
         uint32_t box[2] = {32, 128};
         rc = make_tmap_f32(&tmO, out, 2, dims, strides, box);
         if (rc != VTC_OK) return rc;
-        return launch_gemm2<VTC_EPI_BIAS_RESIDUAL>(tmA, tmB, tmO, p2, stream);
+        return split ? launch_gemm2<VTC_EPI_BIAS_RESIDUAL, true>(tmA, tmB, tmO, p2, stream)
+                     : launch_gemm2<VTC_EPI_BIAS_RESIDUAL, false>(tmA, tmB, tmO, p2, stream);
     }
-    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
-    uint64_t strides[1] = {(uint64_t)N * 2};
+    const uint64_t ocols = static_cast<uint64_t>(split ? 2 : 1) * N;
+    uint64_t dims[2] = {ocols, (uint64_t)M};
+    uint64_t strides[1] = {ocols * 2};
     uint32_t box[2] = {64, 128};
     rc = make_tmap_bf16(&tmO, out, 2, dims, strides, box);
     if (rc != VTC_OK) return rc;
-    if (epilogue == VTC_EPI_BIAS) return launch_gemm2<VTC_EPI_BIAS>(tmA, tmB, tmO, p2, stream);
-    return launch_gemm2<VTC_EPI_BIAS_GELU>(tmA, tmB, tmO, p2, stream);
+    if (epilogue == VTC_EPI_BIAS)
+        return split ? launch_gemm2<VTC_EPI_BIAS, true>(tmA, tmB, tmO, p2, stream) : launch_gemm2<VTC_EPI_BIAS, false>(tmA, tmB, tmO, p2, stream);
+    return split ? launch_gemm2<VTC_EPI_BIAS_GELU, true>(tmA, tmB, tmO, p2, stream) : launch_gemm2<VTC_EPI_BIAS_GELU, false>(tmA, tmB, tmO, p2, stream);
 }
 
 }  // namespace vtc
 
 extern "C" int vtc_gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out,
                              int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream) {
-    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream));
+    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream), 0);
+}
+extern "C" int vtc_gemm_split(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out,
+                              int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream) {
+    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream), 1);
 }

@@ -16,6 +16,8 @@ struct vtc_model {
     struct LayerPacked { const __nv_bfloat16 *qkv, *proj, *fc1, *fc2; };
     std::vector<LayerPacked> lp;
     bool packed = false;
+    bool split = false;          // fp32 mode: GEMM operands and activations as (hi | lo) bf16 halves
+    bool packed_split = false;   // precision the packed buffer was written for
     // optional per-kernel timing (vtc_model_profile)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;     // pool, two events per span
@@ -27,8 +29,8 @@ namespace vtc {
 static size_t seg(size_t elems, size_t elem_bytes) { return align_up(elems * elem_bytes, 256); }
 
 static size_t packed_bytes(const vtc_model* m) {
-    const size_t D = m->D, HID = m->HID;
-    return seg(D * m->KP, 2) + m->L * (seg(3 * D * D, 2) + seg(D * D, 2) + 2 * seg(HID * D, 2));
+    const size_t D = m->D, HID = m->HID, eb = m->split ? 4 : 2;
+    return seg(D * m->KP, eb) + m->L * (seg(3 * D * D, eb) + seg(D * D, eb) + 2 * seg(HID * D, eb));
 }
 
 struct Workspace {
@@ -45,11 +47,12 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     size_t hb = M * m->HID;
     const size_t pb = static_cast<size_t>(B) * m->P * m->KP;
     if (pb > hb) hb = pb;
-    ws.hbuf = reinterpret_cast<__nv_bfloat16*>(take(hb, 2));
+    const size_t eb = m->split ? 4 : 2;      // bf16, or a (hi | lo) pair of bf16
+    ws.hbuf = reinterpret_cast<__nv_bfloat16*>(take(hb, eb));
     ws.patches = ws.hbuf;   // the patch matrix is dead before the first fc1 writes hbuf
-    ws.y = reinterpret_cast<__nv_bfloat16*>(take(M * D, 2));
-    ws.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D, 2));
-    ws.ao = reinterpret_cast<__nv_bfloat16*>(take(M * D, 2));
+    ws.y = reinterpret_cast<__nv_bfloat16*>(take(M * D, eb));
+    ws.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D, eb));
+    ws.ao = reinterpret_cast<__nv_bfloat16*>(take(M * D, eb));
     const bool all_tokens = o && o->tokens && o->tokens_layers >= m->L;
     ws.tok = reinterpret_cast<float*>(take(M * D, 4));    // embedding output / running residual stream
     (void)all_tokens;
@@ -94,7 +97,9 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
     VTC_REQUIRE(m->packed, VTC_ERR_ARG, "forward: vtc_model_pack_weights has not been called");
     VTC_REQUIRE(B > 0, VTC_ERR_SHAPE, "forward: batch %d", B);
     VTC_REQUIRE(o->logits && o->hwp_logits && o->hwp_tokens, VTC_ERR_ARG, "forward: logits / hwp_logits / hwp_tokens are required outputs");
-    VTC_REQUIRE(!(flags & VTC_FWD_FP32_SPLIT), VTC_ERR_ARG, "forward: the split-bf16 fp32 mode is not built yet");
+    VTC_REQUIRE(((flags & VTC_FWD_FP32_SPLIT) != 0) == m->split, VTC_ERR_ARG,
+                "forward: VTC_FWD_FP32_SPLIT must match the model's precision (vtc_model_set_precision)");
+    VTC_REQUIRE(m->packed_split == m->split, VTC_ERR_ARG, "forward: the weights were packed for the other precision; pack them again");
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VTC_ERR_WORKSPACE, "forward: workspace must be 256-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
@@ -110,12 +115,13 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
     VTC_REQUIRE(!o->tokens || Lt >= 1, VTC_ERR_ARG, "forward: tokens requested with tokens_layers == 0");
     const float scale = 1.0f / sqrtf(static_cast<float>(D / H));          // vit_model.py:97
     const int per_image = (flags & VTC_FWD_MASK_NORM_IMAGE) ? 1 : 0;
+    const int sp = m->split ? 1 : 0;
 
     // ---- patch embedding + token assembly (vit_model.py:306-314)
     float* t_cur = ws.tok;
-    VTC_STEP(VTC_PROF_PATCHIFY, patchify(x, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st));
+    VTC_STEP(VTC_PROF_PATCHIFY, patchify(x, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st, sp));
     VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));
-    VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st));
+    VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st, sp));
     VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * L, st));
     if (o->bg) VTC_CUDA(cudaMemsetAsync(o->bg, 0, static_cast<size_t>(L) * B * P, st));
 
@@ -133,14 +139,15 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
         if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
         else if (o->attn_mean) attn_l = ws.attn_tmp;
 
-        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st));
-        VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st));
+        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st, sp));
+        VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp));
         const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
-        VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st));
-        VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st));
-        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st));
-        VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st));
-        VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st));
+        if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st));
+        else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st));
+        VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp));
+        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp));
+        VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st, sp));
+        VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st, sp));
         t_cur = t_out;
 
         if (o->attn_mean) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));
@@ -246,24 +253,34 @@ int vtc_model_pack_weights(vtc_model* m, const vtc_weights* w, void* packed, siz
     size_t off = 0;
     const size_t D = m->D, HID = m->HID;
     int rc;
-    auto pack = [&](const float* src, size_t elems, const __nv_bfloat16** dst) -> int {
+    const bool split = m->split;
+    auto pack = [&](const float* src, size_t rows, size_t cols, const __nv_bfloat16** dst) -> int {
         VTC_REQUIRE(src != nullptr, VTC_ERR_ARG, "pack_weights: missing GEMM weight");
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(base + off);
-        off += seg(elems, 2);
+        off += seg(rows * cols, split ? 4 : 2);
         *dst = d;
-        return cast_bf16(src, d, elems, st);
+        return split ? split_bf16(src, d, rows, cols, st) : cast_bf16(src, d, rows * cols, st);
     };
-    if ((rc = pack(w->patch_w, D * m->KP, &m->patch_w)) != VTC_OK) return rc;
+    if ((rc = pack(w->patch_w, D, m->KP, &m->patch_w)) != VTC_OK) return rc;
     for (int l = 0; l < m->L; ++l) {
         const vtc_layer_weights& lw = m->lw[l];
         VTC_REQUIRE(lw.norm1_w && lw.norm1_b && lw.norm2_w && lw.norm2_b && lw.qkv_b && lw.proj_b && lw.fc1_b && lw.fc2_b, VTC_ERR_ARG,
                     "pack_weights: layer %d misses a vector parameter", l);
-        if ((rc = pack(lw.qkv_w, 3 * D * D, &m->lp[l].qkv)) != VTC_OK) return rc;
-        if ((rc = pack(lw.proj_w, D * D, &m->lp[l].proj)) != VTC_OK) return rc;
-        if ((rc = pack(lw.fc1_w, HID * D, &m->lp[l].fc1)) != VTC_OK) return rc;
-        if ((rc = pack(lw.fc2_w, D * HID, &m->lp[l].fc2)) != VTC_OK) return rc;
+        if ((rc = pack(lw.qkv_w, 3 * D, D, &m->lp[l].qkv)) != VTC_OK) return rc;
+        if ((rc = pack(lw.proj_w, D, D, &m->lp[l].proj)) != VTC_OK) return rc;
+        if ((rc = pack(lw.fc1_w, HID, D, &m->lp[l].fc1)) != VTC_OK) return rc;
+        if ((rc = pack(lw.fc2_w, D, HID, &m->lp[l].fc2)) != VTC_OK) return rc;
     }
     m->packed = true;
+    m->packed_split = split;
+    return VTC_OK;
+}
+
+int vtc_model_set_precision(vtc_model* m, int32_t precision) {
+    using namespace vtc;
+    VTC_REQUIRE(m, VTC_ERR_ARG, "set_precision: null model");
+    VTC_REQUIRE(precision == VTC_PRECISION_BF16 || precision == VTC_PRECISION_FP32_SPLIT, VTC_ERR_ARG, "set_precision: unknown precision %d", precision);
+    m->split = precision == VTC_PRECISION_FP32_SPLIT;
     return VTC_OK;
 }
 

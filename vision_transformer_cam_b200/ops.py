@@ -52,12 +52,47 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: in
     return out
 
 
-def patchify(x: torch.Tensor, patch: int) -> torch.Tensor:
+def split_bf16(src: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., K] -> (hi | lo) bf16 halves [..., 2K] with src ~= hi + lo (the operand format of the fp32 mode)."""
+    K = src.shape[-1]
+    rows = src.numel() // K
+    out = torch.empty(src.shape[:-1] + (2 * K,), dtype=torch.bfloat16, device=src.device)
+    _lib.call("vtc_split_bf16", _ptr(src, torch.float32, "src"), _ptr(out), rows, K, _stream())
+    return out
+
+
+def merge_split(x: torch.Tensor) -> torch.Tensor:
+    """(hi | lo) halves [..., 2K] -> fp32 [..., K] (host-side helper for tests)."""
+    K = x.shape[-1] // 2
+    return x[..., :K].float() + x[..., K:].float()
+
+
+def gemm_split(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int = _lib.EPI_BIAS,
+               residual: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None, tokens: int = 0) -> torch.Tensor:
+    """fp32-mode GEMM: a [M,2K], w [N,2K] split operands; bf16 outputs come back as split halves [M,2N]."""
+    M, K2 = a.shape
+    K = K2 // 2
+    N = w.shape[0]
+    assert w.shape[1] == K2
+    if out is None:
+        if epilogue in (_lib.EPI_BIAS, _lib.EPI_BIAS_GELU):
+            out = torch.empty((M, 2 * N), dtype=torch.bfloat16, device=a.device)
+        elif epilogue == _lib.EPI_BIAS_RESIDUAL:
+            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        else:
+            raise RuntimeError("patch-embed epilogue needs an explicit token buffer `out`")
+    _lib.call("vtc_gemm_split", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32, "bias"),
+              _ptr(residual, torch.float32, "residual"), _ptr(pos, torch.float32, "pos"), _ptr(out), M, N, K, epilogue, tokens, _stream())
+    return out
+
+
+def patchify(x: torch.Tensor, patch: int, split: bool = False) -> torch.Tensor:
     B, Cin, S, S2 = x.shape
     assert S == S2
     g = S // patch
-    out = torch.empty((B * g * g, Cin * patch * patch), dtype=torch.bfloat16, device=x.device)
-    _lib.call("vtc_patchify", _ptr(x, torch.float32, "x"), _ptr(out), B, Cin, S, patch, _stream())
+    out = torch.empty((B * g * g, Cin * patch * patch * (2 if split else 1)), dtype=torch.bfloat16, device=x.device)
+    _lib.call("vtc_patchify_split" if split else "vtc_patchify", _ptr(x, torch.float32, "x"), _ptr(out), B, Cin, S, patch, _stream())
     return out
 
 
@@ -67,12 +102,12 @@ def cls_token_rows(cls_token: torch.Tensor, pos_embed: torch.Tensor, tokens: tor
               B, N, D, _stream())
 
 
-def layernorm_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+def layernorm_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, split: bool = False) -> torch.Tensor:
     D = x.shape[-1]
     rows = x.numel() // D
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib.call("vtc_layernorm_bf16", _ptr(x, torch.float32, "x"), _ptr(weight, torch.float32), _ptr(bias, torch.float32), _ptr(out),
-              rows, D, eps, _stream())
+    out = torch.empty(x.shape[:-1] + (D * (2 if split else 1),), dtype=torch.bfloat16, device=x.device)
+    _lib.call("vtc_layernorm_split" if split else "vtc_layernorm_bf16", _ptr(x, torch.float32, "x"), _ptr(weight, torch.float32),
+              _ptr(bias, torch.float32), _ptr(out), rows, D, eps, _stream())
     return out
 
 

@@ -216,6 +216,7 @@ class _Engine:
         _lib.check(self.lib.vtc_model_create(ctypes.byref(cfg), ctypes.byref(handle)), "vtc_model_create")
         self.handle = handle
         self.packed: Optional[torch.Tensor] = None
+        self.precision = "bf16"
         self.key = None
         self.ws: Optional[torch.Tensor] = None
         self._keep = None
@@ -240,9 +241,13 @@ class _Engine:
 
     def ensure_packed(self, model: "VisionTransformer", device: torch.device) -> None:
         params = dict(model.named_parameters())
-        key = (device, tuple((p.data_ptr(), p._version) for p in params.values()))
+        key = (device, model.precision, tuple((p.data_ptr(), p._version) for p in params.values()))
         if key == self.key:
             return
+        if model.precision != self.precision:
+            _lib.check(self.lib.vtc_model_set_precision(self.handle, _lib.PRECISION_FP32_SPLIT if model.precision == "fp32"
+                                                        else _lib.PRECISION_BF16), "vtc_model_set_precision")
+            self.precision = model.precision
         for n, p in params.items():
             if p.device != device:
                 raise RuntimeError(f"parameter {n} is on {p.device}, input on {device}")
@@ -324,6 +329,8 @@ class _Engine:
                 self.ws = None
                 self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
             flags = _lib.FWD_MASK_NORM_IMAGE if mask_norm == "image" else 0
+            if self.precision == "fp32":
+                flags |= _lib.FWD_FP32_SPLIT
             _lib.check(self.lib.vtc_forward(self.handle, x.data_ptr(), B, ctypes.byref(o),
                                             ctypes.byref(forcing) if forcing is not None else None, self.ws.data_ptr(),
                                             self.ws.numel(), flags, torch.cuda.current_stream(dev).cuda_stream), "vtc_forward")
@@ -386,12 +393,22 @@ class VisionTransformer(nn.Module):
         self.relu = nn.ReLU()
         self.is_train = is_train
         self.final_seg_count = 0
+        self.precision = "bf16"
         self._engine: Optional[_Engine] = None
 
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_engine"] = None          # the libvtc handle is process-local; it is rebuilt lazily
         return state
+
+    def set_precision(self, precision: str) -> "VisionTransformer":
+        """'bf16' (default): bf16 tensor-core operands, logits within 1e-2 of the fp32 reference.  'fp32': every GEMM /
+        attention operand is carried as a (hi, lo) bf16 pair and every product evaluated as hi.hi + lo.hi + hi.lo on the
+        tensor cores (3x the MMA work), logits within 1e-4 (BASELINE.json north_star "fp32 mode")."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        return self
 
     # -- fused path -----------------------------------------------------------------------------------------------
     def _check_input(self, x: torch.Tensor) -> torch.Tensor:
