@@ -208,9 +208,13 @@ def test_attention_kv_blocked(dev, B, N, H, masked):
     assert relerr(out.float(), ref_o) < 1e-2, relerr(out.float(), ref_o)
     out2, cls2, _ = ops.attention_kv(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
     assert torch.equal(out2, out) and torch.equal(cls2, cls)
-    if N > 256:      # vtc_attention dispatches long sequences to the same kernel
-        out3, cls3, _ = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
-        assert torch.equal(out3, out) and torch.equal(cls3, cls)
+    # vtc_attention without the full-P request: the column-split pipelined kernel (attention_cs.cu), any N
+    out3, cls3, _ = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
+    assert relerr(out3.float(), ref_o) < 1e-2, relerr(out3.float(), ref_o)
+    assert float((cls3 - ref_p[:, :, 0, :]).abs().max()) < 5e-6, float((cls3 - ref_p[:, :, 0, :]).abs().max())
+    if N > 256:      # ... and with it: the KV-blocked kernel
+        out4, cls4, attn4 = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=True)
+        assert torch.equal(out4, out) and torch.equal(cls4, cls) and torch.equal(attn4, attn)
 
 
 @pytest.mark.parametrize("amp", [4.0, 12.0])
@@ -230,6 +234,9 @@ def test_attention_kv_large_dynamic_range(dev, amp):
         ref_o, ref_p = _attn_ref(qkv, H, 0.125, bias)
         assert float((attn - ref_p).abs().max()) < 5e-5, float((attn - ref_p).abs().max())
         assert float((cls - ref_p[:, :, 0, :]).abs().max()) < 2e-5
+        assert relerr(out.float(), ref_o) < 1.5e-2, relerr(out.float(), ref_o)
+        out, cls, _ = ops.attention(qkv, H, 0.125, key_bias=bias, want_cls=True, want_attn=False)     # column-split kernel
+        assert float((cls - ref_p[:, :, 0, :]).abs().max()) < 2e-5, float((cls - ref_p[:, :, 0, :]).abs().max())
         assert relerr(out.float(), ref_o) < 1.5e-2, relerr(out.float(), ref_o)
 
 

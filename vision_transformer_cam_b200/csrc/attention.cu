@@ -21,6 +21,7 @@
 namespace vtc {
 
 static unsigned long long* g_attn_trace = nullptr;   // debug hook, see vtc_debug_set_attention_trace
+unsigned long long* attention_trace_buffer() { return g_attn_trace; }
 
 namespace attn {
 constexpr int HD = 64;
@@ -730,6 +731,7 @@ struct Attn3Params {
     int B, N, H;
     float scale, scale_log2;
     unsigned long long* trace;     // debug (vtc_debug_set_attention_trace): [grid][32 items][2 groups][8] %globaltimer stamps
+    int reverse;                   // walk the (image, head) items from the last to the first
 };
 
 __global__ void __launch_bounds__(attn3::THREADS, 1)
@@ -784,8 +786,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     if (warp == 8) {
         // ---------------- producer: TMA loads (and the mask operands) one item ahead ----------------
-        int it = blockIdx.x;
-        for (int i = 0; it < n_items; ++i, it += gridDim.x) {
+        int it_ = blockIdx.x;
+        for (int i = 0; it_ < n_items; ++i, it_ += gridDim.x) {
+            const int it = p.reverse ? n_items - 1 - it_ : it_;
             const int s = i & 1;
             const uint32_t ph = (i >> 1) & 1;
             const int b = it / p.H, h = it - b * p.H;
@@ -900,8 +903,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const float sc = p.scale_log2;
             const bool warp_active = (t * 128 + quarter * 32) < N;
             const bool cls_warp = (t == 0) && (quarter == 0) && (p.cls_rows != nullptr);
-            int it = blockIdx.x;
-            for (int i = 0; it < n_items; ++i, it += gridDim.x) {
+            int it_ = blockIdx.x;
+            for (int i = 0; it_ < n_items; ++i, it_ += gridDim.x) {
+                const int it = p.reverse ? n_items - 1 - it_ : it_;
                 const int b = it / p.H, h = it - b * p.H;
                 const uint32_t ph = i & 1;
                 unsigned long long* tr = (p.trace && i < 32 && (warp & 3) == 0 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 32 + i) * 2 + t) * 8 : nullptr;
@@ -981,7 +985,7 @@ static bool attn_use_v1() {
 }
 
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_out, int batch, int n_tokens, int heads,
-              float scale, cudaStream_t stream) {
+              float scale, cudaStream_t stream, int reverse) {
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
@@ -990,8 +994,15 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
         const char* e = getenv("VTC_ATTN_KV");
         kv_env = (e && e[0] == '1') ? 1 : 0;
     }
-    if (n_tokens > attn::MAXN || kv_env == 1)      // long sequences: KV-blocked kernel (attention_kv.cu)
-        return attention_kv(qkv, key_bias, out, cls_rows, attn_out, batch, n_tokens, heads, scale, false, stream);
+    static int v3_env = -1;
+    if (v3_env < 0) {
+        const char* e = getenv("VTC_ATTN_V3");
+        v3_env = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (attn_out == nullptr && kv_env == 0 && v3_env == 0)      // fast path: column-split pipelined kernel (attention_cs.cu)
+        return attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse);
+    if (n_tokens > attn::MAXN || kv_env == 1)      // full P of long sequences: KV-blocked kernel (attention_kv.cu)
+        return attention_kv(qkv, key_bias, out, cls_rows, attn_out, batch, n_tokens, heads, scale, false, stream, reverse);
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     const int D = heads * attn::HD;
@@ -1032,7 +1043,7 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
             VTC_CUDA(cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn3::SMEM_BYTES));
             configured3 = true;
         }
-        Attn3Params p3{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, batch, n_tokens, heads, scale, scale * 1.4426950408889634f, g_attn_trace};
+        Attn3Params p3{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, batch, n_tokens, heads, scale, scale * 1.4426950408889634f, g_attn_trace, reverse};
         const int items = batch * heads;
         const int grid = items < device_sm_count() ? items : device_sm_count();
         attention3_kernel<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tmQ3, tmKV3, p3);
@@ -1097,7 +1108,7 @@ extern "C" {
 __attribute__((visibility("default"))) void vtc_debug_set_attention_trace(void* buf) { vtc::g_attn_trace = static_cast<unsigned long long*>(buf); }
 int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch, int32_t n_tokens,
                   int32_t heads, float scale, void* stream) {
-    return vtc::attention(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream));
+    return vtc::attention(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream), 0);
 }
 int vtc_head_mean(const float* attn, float* mean, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
     return vtc::head_mean(attn, mean, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));

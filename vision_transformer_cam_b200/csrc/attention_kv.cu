@@ -64,6 +64,7 @@ struct Params {
     int KB, nb;              // keys per block (multiple of 32), number of blocks
     int out_stride, lo_off;
     float scale_log2;
+    int reverse;             // walk the items from the last to the first
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -287,7 +288,8 @@ attention_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---------------- producer ----------------
         if (lane == 0) {
             uint32_t kidx = 0, vidx = 0, qidx = 0;
-            for (int it = first_item; it < n_items; it += item_stride, ++qidx) {
+            for (int it_ = first_item; it_ < n_items; it_ += item_stride, ++qidx) {
+                const int it = p.reverse ? n_items - 1 - it_ : it_;
                 const int qt = it % qtiles;
                 const int bh = it / qtiles;
                 const int b = bh / H, h = bh - b * H;
@@ -384,7 +386,8 @@ attention_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool has_bias = p.key_bias != nullptr;
         uint32_t qidx = 0, step = 0;
         int b_staged = -1;
-        for (int it = first_item; it < n_items; it += item_stride, ++qidx) {
+        for (int it_ = first_item; it_ < n_items; it_ += item_stride, ++qidx) {
+            const int it = p.reverse ? n_items - 1 - it_ : it_;
             const int qt = it % qtiles;
             const int bh = it / qtiles;
             const int b = bh / H, h = bh - b * H;
@@ -537,7 +540,7 @@ static int launch(const void* qkv, const Params& p, cudaStream_t stream) {
 }  // namespace akv
 
 int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_out, int batch, int n_tokens, int heads,
-                 float scale, bool split, cudaStream_t stream) {
+                 float scale, bool split, cudaStream_t stream, int reverse) {
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
@@ -558,6 +561,7 @@ int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_r
     p.out_stride = heads * akv::HD * (split ? 2 : 1);
     p.lo_off = heads * akv::HD;
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.reverse = reverse;
     return split ? akv::launch<true>(qkv, p, stream) : akv::launch<false>(qkv, p, stream);
 }
 
@@ -565,5 +569,5 @@ int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_r
 
 extern "C" int vtc_attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
                                 int32_t n_tokens, int32_t heads, float scale, int32_t split, void* stream) {
-    return vtc::attention_kv(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, split != 0, static_cast<cudaStream_t>(stream));
+    return vtc::attention_kv(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, split != 0, static_cast<cudaStream_t>(stream), 0);
 }

@@ -148,11 +148,12 @@ int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens
 template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows,
-                                                        float eps) {
+                                                        float eps, int reverse) {
     constexpr int D = NV * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
+    int row = blockIdx.x * 8 + warp;
     if (row >= rows) return;
+    if (reverse) row = rows - 1 - row;       // last rows first: they are the ones the previous kernel left in L2
     const float* src = x + static_cast<size_t>(row) * D;
     float4 v[NV];
 #pragma unroll
@@ -189,13 +190,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 template <int NV>
 static void launch_ln(int grid, cudaStream_t stream, const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, float eps,
-                      int split) {
-    if (split) layernorm_kernel<NV, true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps);
-    else layernorm_kernel<NV, false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps);
+                      int split, int reverse) {
+    if (split) layernorm_kernel<NV, true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps, reverse);
+    else layernorm_kernel<NV, false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, eps, reverse);
 }
 
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream,
-                   int split) {
+                   int split, int reverse) {
     VTC_REQUIRE(x && gamma && beta && y, VTC_ERR_ARG, "layernorm: null pointer");
     VTC_REQUIRE(rows > 0, VTC_ERR_SHAPE, "layernorm: rows=%d", rows);
     int rc = check_arch();
@@ -203,12 +204,12 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* 
     const int grid = cdiv(rows, 8);
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
     switch (dim) {
-        case 256: launch_ln<2>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
-        case 384: launch_ln<3>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
-        case 512: launch_ln<4>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
-        case 768: launch_ln<6>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
-        case 1024: launch_ln<8>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
-        case 1280: launch_ln<10>(grid, stream, x, gamma, beta, out, rows, eps, split); break;
+        case 256: launch_ln<2>(grid, stream, x, gamma, beta, out, rows, eps, split, reverse); break;
+        case 384: launch_ln<3>(grid, stream, x, gamma, beta, out, rows, eps, split, reverse); break;
+        case 512: launch_ln<4>(grid, stream, x, gamma, beta, out, rows, eps, split, reverse); break;
+        case 768: launch_ln<6>(grid, stream, x, gamma, beta, out, rows, eps, split, reverse); break;
+        case 1024: launch_ln<8>(grid, stream, x, gamma, beta, out, rows, eps, split, reverse); break;
+        case 1280: launch_ln<10>(grid, stream, x, gamma, beta, out, rows, eps, split, reverse); break;
         default:
             set_last_error("layernorm: dim %d unsupported (256/384/512/768/1024/1280)", dim);
             return VTC_ERR_SHAPE;
@@ -234,7 +235,7 @@ int vtc_patchify_split(const float* x, void* patches, int32_t batch, int32_t in_
 }
 int vtc_layernorm_split(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim, float eps,
                         void* stream) {
-    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream), 1);
+    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream), 1, 0);
 }
 int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int32_t batch, int32_t n_tokens, int32_t dim,
                        void* stream) {
@@ -242,6 +243,6 @@ int vtc_cls_token_rows(const float* cls_token, const float* pos_embed, float* to
 }
 int vtc_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim, float eps,
                        void* stream) {
-    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream), 0);
+    return vtc::layernorm_bf16(x, gamma, beta, y, rows, dim, eps, static_cast<cudaStream_t>(stream), 0, 0);
 }
 }

@@ -250,6 +250,7 @@ struct Params {
     const float* bias;
     int M, N, K;
     int split;     // see gemm::Params::split; bf16 outputs are then written as (hi | lo) halves [M, 2N]
+    int reverse;   // walk the tiles from the last row block to the first (see model.cu: alternating sweep direction)
 };
 }  // namespace gemm2
 
@@ -306,7 +307,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = pair; tile < num_tiles; tile += npairs) {
+            for (int t_ = pair; t_ < num_tiles; t_ += npairs) {
+                const int tile = p.reverse ? num_tiles - 1 - t_ : t_;
                 const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
                 const int n0 = (tile % num_n) * BN + rank * (BN / 2);
                 for (int kb = 0; kb < num_k; ++kb) {
@@ -362,7 +364,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int as = 0;
         uint32_t aph = 0;
         int buf = 0;
-        for (int tile = pair; tile < num_tiles; tile += npairs) {
+        for (int t_ = pair; t_ < num_tiles; t_ += npairs) {
+            const int tile = p.reverse ? num_tiles - 1 - t_ : t_;
             const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
             const int n0 = (tile % num_n) * BN;
             mbar_wait(&tfull_bar[as], aph);
@@ -498,7 +501,7 @@ static bool use_v1() {
 }
 
 int gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out, int M,
-              int N, int K, int epilogue, int tokens, cudaStream_t stream, int split) {
+              int N, int K, int epilogue, int tokens, cudaStream_t stream, int split, int reverse) {
     VTC_REQUIRE(A && W && bias && out, VTC_ERR_ARG, "gemm: null pointer");
     VTC_REQUIRE(M > 0 && N > 0 && K > 0, VTC_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
     VTC_REQUIRE(K % gemm::BK == 0, VTC_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", K, gemm::BK);
@@ -537,7 +540,7 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
         }
     }
     CUtensorMap tmO;
-    gemm2::Params p2{bias, M, N, K, split};
+    gemm2::Params p2{bias, M, N, K, split, reverse};
     if (epilogue == VTC_EPI_BIAS_RESIDUAL) {
         // out = residual + A.W^T + bias, with the add done by the TMA reduction into `out`
         if (out != static_cast<const void*>(residual))
@@ -565,9 +568,9 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
 
 extern "C" int vtc_gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out,
                              int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream) {
-    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream), 0);
+    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream), 0, 0);
 }
 extern "C" int vtc_gemm_split(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out,
                               int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream) {
-    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream), 1);
+    return vtc::gemm_bf16(A, W, bias, residual, pos, out, M, Nout, K, epilogue, tokens, static_cast<cudaStream_t>(stream), 1, 0);
 }

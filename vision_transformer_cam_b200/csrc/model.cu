@@ -1,5 +1,6 @@
 // Model handle + the fused forward: VisionTransformer.forward of the reference (vit_model.py:303-424) as a fixed
 // sequence of kernel launches on one stream.  Host-only state; no device allocation, no synchronisation.
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -127,6 +128,12 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
 
     bool have_bias = false;
     float* last_map = nullptr;
+    // Alternating sweep direction: every kernel of the chain walks its rows / images in the opposite order of its
+    // predecessor, so it starts on the data the predecessor wrote last, which is still in the 126 MB L2 (the activations
+    // of one layer, 77-310 MB each at B = 256, do not fit as a whole: a same-direction sweep would miss on everything).
+    static const bool serpentine = []() { const char* e = getenv("VTC_NO_SERPENTINE"); return !(e && e[0] == '1'); }();
+    int dir = 0;
+    auto next_dir = [&]() { const int d = dir; if (serpentine) dir ^= 1; return d; };
     for (int l = 0; l < L; ++l) {
         const vtc_layer_weights& w = m->lw[l];
         const vtc_model::LayerPacked& pw = m->lp[l];
@@ -139,15 +146,15 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
         if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
         else if (o->attn_mean) attn_l = ws.attn_tmp;
 
-        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st, sp));
-        VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp));
+        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
+        VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp, next_dir()));
         const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
-        if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st));
-        else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st));
-        VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp));
-        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp));
-        VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st, sp));
-        VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st, sp));
+        if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
+        else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
+        VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
+        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
+        VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st, sp, next_dir()));
+        VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
         t_cur = t_out;
 
         if (o->attn_mean) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));

@@ -8,19 +8,23 @@ namespace vtc {
 
 // split != 0 ("fp32 mode"): A [M,2K] and W [N,2K] hold (hi | lo) bf16 halves, bf16 outputs are written as [M,2N] halves
 int gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out, int M,
-              int N, int K, int epilogue, int tokens, cudaStream_t stream, int split = 0);
+              int N, int K, int epilogue, int tokens, cudaStream_t stream, int split = 0, int reverse = 0);
 int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
 // fp32 [rows,cols] -> (hi | lo) bf16 halves [rows, 2*cols], x ~= hi + lo (16 mantissa bits)
 int split_bf16(const float* src, void* dst, size_t rows, size_t cols, cudaStream_t stream);
 int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream, int split = 0);
 int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int batch, int n_tokens, int dim, cudaStream_t stream);
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream,
-                   int split = 0);
+                   int split = 0, int reverse = 0);
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
-              float scale, cudaStream_t stream);
+              float scale, cudaStream_t stream, int reverse = 0);
 // KV-blocked kernel (attention_kv.cu): any n_tokens <= 2048; split = (hi, lo) bf16 operands: qkv [B,N,2,3,H,64], out [B*N,2,H*64]
 int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
-                 float scale, bool split, cudaStream_t stream);
+                 float scale, bool split, cudaStream_t stream, int reverse = 0);
+// column-split pipelined kernel (attention_cs.cu): the fast path when the full P is not requested, any n_tokens <= 2048
+int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
+                 cudaStream_t stream, int reverse = 0);
+unsigned long long* attention_trace_buffer();   // debug: device buffer for %globaltimer stamps (vtc_debug_set_attention_trace) or null
 int head_mean(const float* attn, float* mean, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
