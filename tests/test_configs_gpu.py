@@ -105,6 +105,6 @@ def test_vit_l16_384_forward_cam(lib_built):
     op = model.forward_cam(x.to("cuda:0"), forced_bg=forced, forced_topk=refp["topk_idx"])
     ep = relerr(op.logits, refp["logits"])
     print(f"L/16-384 peaked teacher-forced: logits relerr {ep:.2e}")
-    assert ep <= PEAKED_TOL
+    assert ep <= 1.5 * PEAKED_TOL        # 24 layers of the 25x more sensitive softmax instead of 12 (see PEAKED_TOL)
     out = model(x.to("cuda:0"))
     assert len(out[1]) == 12 and out[1][0].shape == (1, 16, 577, 577) and len(out[2]) == 12 and out[5].shape == (1, 16, 1024)

@@ -158,7 +158,7 @@ def test_attention(dev, B, N, H, masked):
     # O: P rounded to bf16 before the second MMA + bf16 output: 1e-2 of scale
     assert relerr(out.float(), ref_o) < 1e-2, relerr(out.float(), ref_o)
     out2, cls2, _ = ops.attention(qkv, H, 0.125, key_bias=kb, want_cls=True, want_attn=False)
-    # fast path = persistent single-pass kernel, full-P path = two-pass kernel: same math, different exponent offsets
+    # fast path = column-split single-pass kernel, full-P path = two-pass kernel: same math, different exponent offsets
     assert relerr(out2.float(), ref_o) < 1e-2 and float((cls2 - ref_p[:, :, 0, :]).abs().max()) < 5e-6
     hm = ops.head_mean(attn)
     assert float((hm - attn.mean(1)).abs().max()) < 1e-6
@@ -178,7 +178,7 @@ def test_attention_large_dynamic_range(dev, amp):
     kb[:, 0] = 0
     kb = kb.to(dev)
     for bias in (None, kb):
-        out, cls, _ = ops.attention(qkv, H, 0.125, key_bias=bias, want_cls=True, want_attn=False)      # fast (persistent) kernel
+        out, cls, _ = ops.attention(qkv, H, 0.125, key_bias=bias, want_cls=True, want_attn=False)      # fast (column-split) kernel
         out_ref, cls_ref, attn = ops.attention(qkv, H, 0.125, key_bias=bias, want_cls=True, want_attn=True)   # two-pass kernel
         ref_o, ref_p = _attn_ref(qkv, H, 0.125, bias)
         assert float((attn - ref_p).abs().max()) < 5e-5          # two-pass kernel, |logits| up to ~1e3 at amp 12

@@ -2,16 +2,13 @@
 //   S = Q K^T * scale (+ the layer>4 background mask: -100 on background keys, for foreground query rows),
 //   P = softmax(S), O = P V
 // with both contractions on tcgen05 (S and O accumulate in TMEM) and the softmax in fp32 registers.  Besides O the
-// kernel emits what the reference reads back from the full P tensor: the CLS query row P[b,h,0,:] (mask builder,
+// kernels emit what the reference reads back from the full P tensor: the CLS query row P[b,h,0,:] (mask builder,
 // top-k head, per-layer maps) and, on request, the whole P (the 6-tuple's attn_weights / the rollout's head mean).
 //
-// Single-pass variant: all keys of one head fit one TMEM accumulator (N <= 256 tokens, head_dim 64).
-//   warps 0-3 : softmax + epilogue of query rows   0..127   (TMEM lane quarter = warp)
-//   warps 4-7 : softmax + epilogue of query rows 128..255
-//   warp  8   : TMEM allocation, TMA loads (Q,K,V as 256x64 boxes of the [B,N,3,H,64] qkv tensor; rows >= N are
-//               zero-filled by TMA), tcgen05.mma issue.
-// P is handed to the second MMA through shared memory as bf16 in the canonical K-major 128-byte-swizzle layout;
-// V is consumed MN-major straight from the TMA tile (no transpose anywhere).
+// Three kernels, one dispatcher (`attention`):
+//   attention_cs.cu   fast path (no full P), any sequence length: two groups x two column halves per CTA
+//   attention_kv.cu   full P of long sequences (second sweep) and the split-bf16 fp32 mode
+//   this file         full P for N <= 256 tokens (all keys of a head in one TMEM accumulator), and the head mean of P
 #include <cstdlib>
 
 #include "common.cuh"
@@ -22,248 +19,6 @@ namespace vtc {
 
 static unsigned long long* g_attn_trace = nullptr;   // debug hook, see vtc_debug_set_attention_trace
 unsigned long long* attention_trace_buffer() { return g_attn_trace; }
-
-namespace attn {
-constexpr int HD = 64;
-constexpr int MAXN = 256;
-constexpr int TILE_BYTES = MAXN * HD * 2;            // 32 KB: one 256x64 bf16 box
-constexpr int P_KBLOCK_BYTES = 128 * 128;            // 128 rows x 64 keys bf16
-constexpr int P_TILE_BYTES = 4 * P_KBLOCK_BYTES;     // 256 keys
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = TILE_BYTES;
-constexpr int OFF_V = 2 * TILE_BYTES;
-constexpr int OFF_P = 3 * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + 2 * P_TILE_BYTES;    // 229376
-constexpr int OFF_KB = OFF_BAR + 128;                // key bias (log2 domain) [256] floats
-constexpr int OFF_CLS = OFF_KB + MAXN * 4;           // CLS row staging [256] floats
-constexpr int SMEM_BYTES = OFF_CLS + MAXN * 4;       // no alignment slack: the dynamic smem base is checked instead
-constexpr int THREADS = 288;
-static_assert(SMEM_BYTES <= 232448, "attention smem budget");
-}  // namespace attn
-
-struct AttnParams {
-    const float* key_bias;   // [B,N] or null
-    __nv_bfloat16* out;      // [B,N,H*64]
-    float* cls_rows;         // [B,H,N] or null
-    float* attn;             // [B,H,N,N] or null
-    int B, N, H;
-    float scale_log2;
-};
-
-__global__ void __launch_bounds__(attn::THREADS, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-    using namespace attn;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* bar_qk = bars + 0;
-    uint64_t* bar_v = bars + 1;
-    uint64_t* s_full = bars + 2;    // [2]
-    uint64_t* p_full = bars + 4;    // [2]
-    uint64_t* o_full = bars + 6;    // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-    float* kb_s = reinterpret_cast<float*>(smem + OFF_KB);
-    float* cls_s = reinterpret_cast<float*>(smem + OFF_CLS);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.H;
-    const int h = blockIdx.x - b * p.H;
-    const int N = p.N;
-    const int NP = (N + 15) & ~15;
-    const int ntiles = (N + 127) >> 7;
-
-    if (warp == 8) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmQKV);
-            mbar_init(bar_qk, 1);
-            mbar_init(bar_v, 1);
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&s_full[i], 1);
-                mbar_init(&p_full[i], 128);
-                mbar_init(&o_full[i], 1);
-            }
-            fence_barrier_init();
-        }
-        __syncwarp();
-        tmem_alloc(tmem_ptr, 512);
-    } else {
-        // stage the key bias (log2 domain) while the control warp sets up
-        for (int j = threadIdx.x; j < MAXN; j += 256) {
-            float v = 0.f;
-            if (p.key_bias != nullptr && j < N) v = p.key_bias[static_cast<size_t>(b) * N + j] * 1.4426950408889634f;
-            kb_s[j] = v;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 8) {
-        if (lane == 0) {
-            // ---- loads: coordinates (column, token, image) in the [B, N, 3*H*64] view
-            const int D = p.H * HD;
-            mbar_arrive_expect_tx(bar_qk, 2 * TILE_BYTES);
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(smem_u32(smem + OFF_Q)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(bar_qk)), "r"(h * HD), "r"(0), "r"(b)
-                : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(smem_u32(smem + OFF_K)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(bar_qk)), "r"(D + h * HD), "r"(0), "r"(b)
-                : "memory");
-            mbar_arrive_expect_tx(bar_v, TILE_BYTES);
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(smem_u32(smem + OFF_V)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(bar_v)), "r"(2 * D + h * HD), "r"(0), "r"(b)
-                : "memory");
-
-            // ---- S_i = Q_i K^T
-            mbar_wait(bar_qk, 0);
-            tc_fence_after();
-            const uint32_t idesc_s = make_idesc_bf16(128, NP, 0, 0);
-            const uint32_t q_addr = smem_u32(smem + OFF_Q);
-            const uint32_t k_addr = smem_u32(smem + OFF_K);
-            for (int i = 0; i < ntiles; ++i) {
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint64_t da = make_smem_desc_sw128(q_addr + i * (128 * 128) + k * 32, 1024, 16);
-                    const uint64_t db = make_smem_desc_sw128(k_addr + k * 32, 1024, 16);
-                    umma_bf16(tmem_base + i * 256, da, db, idesc_s, k != 0 ? 1u : 0u);
-                }
-                umma_commit(&s_full[i]);
-            }
-            // ---- O_i = P_i V   (O_i aliases the first 64 columns of S_i: S_i is dead once P_i is in smem)
-            mbar_wait(bar_v, 0);
-            const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
-            const uint32_t v_addr = smem_u32(smem + OFF_V);
-            const uint32_t p_addr = smem_u32(smem + OFF_P);
-            const int ksteps = NP / 16;
-            for (int i = 0; i < ntiles; ++i) {
-                mbar_wait(&p_full[i], 0);
-                tc_fence_after();
-                for (int j = 0; j < ksteps; ++j) {
-                    const uint64_t da = make_smem_desc_sw128(p_addr + i * P_TILE_BYTES + (j >> 2) * P_KBLOCK_BYTES + (j & 3) * 32, 1024, 16);
-                    const uint64_t db = make_smem_desc_sw128(v_addr + j * 2048, 1024, 1024);
-                    umma_bf16(tmem_base + i * 256, da, db, idesc_o, j != 0 ? 1u : 0u);
-                }
-                umma_commit(&o_full[i]);
-            }
-        }
-        __syncwarp();
-    } else {
-        const int tile = warp >> 2;
-        if (tile < ntiles) {
-            const int quarter = warp & 3;
-            const int r_local = quarter * 32 + lane;
-            const int row = tile * 128 + r_local;
-            const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * 256;
-            const int nchunks = (N + 31) >> 5;
-            const float sc = p.scale_log2;
-            // The reference mask is -100*min(v_i + v_j, 1) (vit_model.py:348-361): a query row that is itself background
-            // (v_i = 1) receives a uniform -100, i.e. no masking at all; only foreground rows see the per-key bias.
-            const float rb = (row < N && kb_s[row] != 0.f) ? 0.f : 1.f;
-
-            mbar_wait(&s_full[tile], 0);
-            tc_fence_after();
-            // pass 1: row max
-            float m = -INFINITY;
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_s + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = c * 32 + j;
-                    const float x = fmaf(__uint_as_float(r[j]), sc, rb * kb_s[col]);
-                    if (col < N) m = fmaxf(m, x);
-                }
-            }
-            // pass 2: exponentials, row sum, bf16 P tile in smem (K-major, 128-byte swizzle)
-            float sum = 0.f;
-            uint8_t* p_tile = smem + OFF_P + tile * P_TILE_BYTES + r_local * 128;
-            const bool is_cls = (row == 0) && (p.cls_rows != nullptr);
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_s + c * 32, r);
-                tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const int col = c * 32 + j;
-                    float e0 = exp2f(fmaf(__uint_as_float(r[j]), sc, rb * kb_s[col]) - m);
-                    float e1 = exp2f(fmaf(__uint_as_float(r[j + 1]), sc, rb * kb_s[col + 1]) - m);
-                    if (col >= N) e0 = 0.f;
-                    if (col + 1 >= N) e1 = 0.f;
-                    sum += e0 + e1;
-                    if (is_cls) { cls_s[col] = e0; cls_s[col + 1] = e1; }
-                    pk[j >> 1] = pack_bf16x2(e0, e1);
-                }
-                uint8_t* kblk = p_tile + (c >> 1) * P_KBLOCK_BYTES;
-                const int g0 = (c & 1) * 4;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int gs = (g0 + g) ^ (r_local & 7);
-                    st_u4(kblk + gs * 16, make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
-                }
-            }
-            const float inv = 1.0f / sum;
-            if (p.attn != nullptr) {
-                // pass 3 (on request): normalised fp32 P row, re-read from TMEM before S is overwritten by O.
-                // The branch is CTA-uniform; only the stores are predicated (tcgen05.ld is .sync.aligned).
-                const bool wr = row < N;
-                float* dst = p.attn + ((static_cast<size_t>(b) * p.H + h) * N + (wr ? row : 0)) * N;
-                for (int c = 0; c < nchunks; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_s + c * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        if (wr && col < N) dst[col] = exp2f(fmaf(__uint_as_float(r[j]), sc, rb * kb_s[col]) - m) * inv;
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(&p_full[tile]);
-
-            if (warp == 0 && p.cls_rows != nullptr) {
-                const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
-                __syncwarp();
-                float* dst = p.cls_rows + (static_cast<size_t>(b) * p.H + h) * N;
-                for (int j = lane; j < N; j += 32) dst[j] = cls_s[j] * inv0;
-            }
-
-            // epilogue: O / rowsum -> bf16 [B,N,H*64]
-            mbar_wait(&o_full[tile], 0);
-            tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld_32x32b_x32(t_s, o0);
-            tmem_ld_32x32b_x32(t_s + 32, o1);
-            tmem_ld_wait();
-            if (row < N) {
-                __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * (p.H * HD) + h * HD;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    st_u4(dst + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
-                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
-                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
-                                                  pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv)));
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    st_u4(dst + 32 + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv)));
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
-}
 
 // ======================================================================================================================
 // v2: one CTA per (image, head, 128-query-row tile), two CTAs resident per SM so that one CTA's TMA / prologue /
@@ -383,79 +138,6 @@ __device__ __forceinline__ void softmax_pass2(uint32_t t_s, int nchunks, int N, 
             tmem_ld_wait();
             if (c + 2 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 2) * 32, ra);
             softmax_chunk<CLS>(rb, c + 1, N, sc2, negm2, sum2, p_row, r_local, cls_s, is_cls_thread, t_p, ts);
-        }
-    }
-    float s0, s1;
-    unpack2(sum2, s0, s1);
-    sum_out = s0 + s1;
-}
-
-// ---- single-pass softmax (attention v3) ---------------------------------------------------------------------------------
-// The S tile is read from TMEM exactly once (TMEM reads, 64 B/clk/SM, are what bounds this kernel).  The running maximum
-// m_run starts as the maximum of the first 32 keys (it contains the CLS key) and is only raised when a later chunk
-// exceeds it by more than 2^8 in the exponent domain; until then exponentials may exceed 1 (<= 256: exact in bf16 / fp32,
-// the row sum normalises them).  When a raise is needed (rare) the bf16 P chunks already written to TMEM, the row sum and
-// the staged CLS values are rescaled -- warp-collectively, lanes that do not need it use a factor of 1.
-__device__ __forceinline__ float chunk_max_valid(const uint32_t (&cur)[32], int c, int N) {
-    float m = -INFINITY;
-    if (c * 32 + 32 <= N) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < N) m = fmaxf(m, __uint_as_float(cur[j]));
-    }
-    return m;
-}
-
-template <bool CLS>
-__device__ __forceinline__ void softmax_step(const uint32_t (&cur)[32], int c, int N, float sc, float& m_run, uint64_t& sum2, uint32_t t_p,
-                                             float* cls_s, bool is_cls_thread) {
-    const float mc = chunk_max_valid(cur, c, N);
-    const bool need = (mc - m_run) * sc > 8.0f;
-    if (__any_sync(0xffffffffu, need)) {
-        const float f = need ? ex2_approx((m_run - mc) * sc) : 1.0f;
-        if (need) m_run = mc;
-        const uint64_t f2 = pack2(f, f);
-        sum2 = mul2(sum2, f2);
-        tmem_st_wait();
-        for (int cc = 0; cc < c; ++cc) {
-            uint32_t q[16];
-            tmem_ld_32x32b_x16(t_p + cc * 16, q);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float lo = __uint_as_float(q[j] << 16) * f, hi = __uint_as_float(q[j] & 0xffff0000u) * f;
-                q[j] = pack_bf16x2(lo, hi);
-            }
-            tmem_st_32x32b_x16(t_p + cc * 16, q);
-        }
-        if (CLS) {
-            if (is_cls_thread)
-                for (int j = 0; j < c * 32; ++j) cls_s[j] *= f;
-        }
-    }
-    const float neg_m = -m_run * sc;
-    const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
-    softmax_chunk<CLS>(cur, c, N, sc2, negm2, sum2, nullptr, 0, cls_s, is_cls_thread, t_p, true);
-}
-
-template <bool CLS>
-__device__ __forceinline__ void softmax_single_pass(uint32_t t_s, int nchunks, int N, float sc, float* cls_s, bool is_cls_thread, float& sum_out) {
-    uint64_t sum2 = pack2(0.f, 0.f);
-    uint32_t ra[32], rb[32];
-    tmem_ld_32x32b_x32(t_s, ra);
-    tmem_ld_wait();
-    float m_run = chunk_max_valid(ra, 0, N);
-    for (int c = 0; c < nchunks; c += 2) {
-        if (c > 0) tmem_ld_wait();
-        if (c + 1 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 1) * 32, rb);
-        softmax_step<CLS>(ra, c, N, sc, m_run, sum2, t_s, cls_s, is_cls_thread);
-        if (c + 1 < nchunks) {
-            tmem_ld_wait();
-            if (c + 2 < nchunks) tmem_ld_32x32b_x32(t_s + (c + 2) * 32, ra);
-            softmax_step<CLS>(rb, c + 1, N, sc, m_run, sum2, t_s, cls_s, is_cls_thread);
         }
     }
     float s0, s1;
@@ -699,359 +381,26 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 
-// ======================================================================================================================
-// v3: persistent kernel, one CTA per SM looping over (image, head) items.
-//   warps 0-3 / 4-7 : softmax + epilogue of query rows 0..127 / 128..255 of the current item (one TMEM region each)
-//   warp 8          : TMA producer: Q, K, V of item i+1 land in the second smem stage while item i is being processed;
-//                     also writes the augmented mask operands (Q_aug, K_aug) of the stage
-//   warp 9          : TMEM allocator + MMA issuer: an event loop over the two regions that issues S_t = Q_t K^T as soon as
-//                     region t has been drained and O_t = P_t V as soon as P_t is complete, so the two softmax groups run
-//                     out of phase and the TMEM read port (the bound of this kernel) never waits for a load or an MMA.
-// P never touches shared memory: each softmax thread overwrites the S columns it has consumed with bf16 pairs
-// (tcgen05.st) and the second MMA takes its A operand from TMEM (tcgen05.mma [d], [a], b-desc).  O goes to columns
-// 128..191 of the region.
-namespace attn3 {
-constexpr int HD = 64;
-constexpr int MAXN = 256;
-constexpr int TILE_BYTES = MAXN * HD * 2;                 // 32 KB
-constexpr int AUG_BYTES = MAXN * 32;                      // 8 KB (no-swizzle core matrices, 32 B per row)
-constexpr int STAGE_BYTES = 3 * TILE_BYTES + 2 * AUG_BYTES;   // Q, K, V, Q_aug, K_aug = 112 KB
-constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = 2 * TILE_BYTES, OFF_QAUG = 3 * TILE_BYTES, OFF_KAUG = 3 * TILE_BYTES + AUG_BYTES;
-constexpr int OFF_CLS = 2 * STAGE_BYTES;                  // CLS row staging [256] floats
-constexpr int OFF_BAR = OFF_CLS + MAXN * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr int THREADS = 320;
-static_assert(SMEM_BYTES <= 232448, "attention3 smem budget");
-}  // namespace attn3
-
-struct Attn3Params {
-    const float* key_bias;
-    __nv_bfloat16* out;
-    float* cls_rows;
-    int B, N, H;
-    float scale, scale_log2;
-    unsigned long long* trace;     // debug (vtc_debug_set_attention_trace): [grid][32 items][2 groups][8] %globaltimer stamps
-    int reverse;                   // walk the (image, head) items from the last to the first
-};
-
-__global__ void __launch_bounds__(attn3::THREADS, 1)
-attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const Attn3Params p) {
-    using namespace attn3;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* qk_full = bars + 0;    // [2] stage: Q, K (+aug) landed
-    uint64_t* v_full = bars + 2;     // [2] stage: V landed
-    uint64_t* qk_empty = bars + 4;   // [2] stage: both regions' QK MMAs retired
-    uint64_t* v_empty = bars + 6;    // [2] stage: both regions' PV MMAs retired
-    uint64_t* s_full = bars + 8;     // [2] region: S ready
-    uint64_t* p_full = bars + 10;    // [2] region: P written (128 threads)
-    uint64_t* o_full = bars + 12;    // [2] region: O ready
-    uint64_t* o_empty = bars + 14;   // [2] region: O read out, region free (128 threads)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
-    float* cls_s = reinterpret_cast<float*>(smem + OFF_CLS);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int N = p.N;
-    const int NP = (N + 15) & ~15;
-    const int ntiles = (N + 127) >> 7;
-    const int n_items = p.B * p.H;
-    const bool has_bias = p.key_bias != nullptr;
-    const uint32_t kv_bytes = static_cast<uint32_t>(NP) * HD * 2;
-
-    if (warp == 9) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmQ);
-            tma_prefetch_desc(&tmKV);
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&qk_full[i], 1);
-                mbar_init(&v_full[i], 1);
-                mbar_init(&qk_empty[i], ntiles);
-                mbar_init(&v_empty[i], ntiles);
-                mbar_init(&s_full[i], 1);
-                mbar_init(&p_full[i], 128);
-                mbar_init(&o_full[i], 1);
-                mbar_init(&o_empty[i], 128);
-            }
-            fence_barrier_init();
-        }
-        __syncwarp();
-        tmem_alloc(tmem_ptr, 512);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 8) {
-        // ---------------- producer: TMA loads (and the mask operands) one item ahead ----------------
-        int it_ = blockIdx.x;
-        for (int i = 0; it_ < n_items; ++i, it_ += gridDim.x) {
-            const int it = p.reverse ? n_items - 1 - it_ : it_;
-            const int s = i & 1;
-            const uint32_t ph = (i >> 1) & 1;
-            const int b = it / p.H, h = it - b * p.H;
-            uint8_t* st = smem + s * STAGE_BYTES;
-            mbar_wait(&qk_empty[s], ph ^ 1);
-            if (has_bias) {
-                const float* kb = p.key_bias + static_cast<size_t>(b) * N;
-                const float inv_scale = 1.0f / p.scale;
-                for (int r = lane; r < MAXN; r += 32) {
-                    const float kv = (r < N) ? kb[r] : 0.f;
-                    const float flag = (r < N && kv == 0.f) ? 1.0f : 0.0f;
-                    uint8_t* dq = st + OFF_QAUG + (r >> 3) * 256 + (r & 7) * 16;
-                    uint8_t* dk = st + OFF_KAUG + (r >> 3) * 256 + (r & 7) * 16;
-                    st_u4(dq, make_uint4(pack_bf16x2(flag, 0.f), 0u, 0u, 0u));
-                    st_u4(dq + 128, make_uint4(0u, 0u, 0u, 0u));
-                    st_u4(dk, make_uint4(pack_bf16x2(kv * inv_scale, 0.f), 0u, 0u, 0u));
-                    st_u4(dk + 128, make_uint4(0u, 0u, 0u, 0u));
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-            }
-            if (lane == 0) {
-                const int D = p.H * HD;
-                mbar_arrive_expect_tx(&qk_full[s], TILE_BYTES + kv_bytes);
-                asm volatile(
-                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                    ::"r"(smem_u32(st + OFF_Q)), "l"(reinterpret_cast<uint64_t>(&tmQ)), "r"(smem_u32(&qk_full[s])), "r"(h * HD), "r"(0), "r"(b)
-                    : "memory");
-                asm volatile(
-                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                    ::"r"(smem_u32(st + OFF_K)), "l"(reinterpret_cast<uint64_t>(&tmKV)), "r"(smem_u32(&qk_full[s])), "r"(D + h * HD), "r"(0), "r"(b)
-                    : "memory");
-                mbar_wait(&v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&v_full[s], kv_bytes);
-                asm volatile(
-                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                    ::"r"(smem_u32(st + OFF_V)), "l"(reinterpret_cast<uint64_t>(&tmKV)), "r"(smem_u32(&v_full[s])), "r"(2 * D + h * HD), "r"(0), "r"(b)
-                    : "memory");
-            }
-            __syncwarp();
-        }
-    } else if (warp == 9) {
-        // ---------------- MMA issuer: event loop over the two TMEM regions ----------------
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_bf16(128, NP, 0, 0);
-            const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
-            const int ksteps = NP / 16;
-            const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-            int iter[2] = {0, 0};        // per region: items started (QK issued)
-            int need_pv[2] = {0, 0};     // per region: QK issued, PV pending
-            int done = 0;
-            const int total = my_items * ntiles;
-            uint32_t spins = 0;
-            while (done < total) {
-                bool progressed = false;
-                for (int t = 0; t < ntiles; ++t) {
-                    const int i = iter[t];
-                    if (!need_pv[t]) {
-                        if (i >= my_items) continue;
-                        const int s = i & 1;
-                        const uint32_t ph = (i >> 1) & 1;
-                        // region t is free once O of its previous item has been read (its (i)th completion)
-                        if (!mbar_test(&qk_full[s], ph) || !mbar_test(&o_empty[t], (i & 1) ^ 1)) continue;
-                        if (i == 0 && t == 1 && !mbar_test(&p_full[0], 0)) continue;     // start the two softmax groups out of phase
-                        tc_fence_after();
-                        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                        const uint32_t q_addr = st + OFF_Q + t * (128 * 128);
-                        const uint32_t k_addr = st + OFF_K;
-                        const uint32_t d = tmem_base + t * 256;
-#pragma unroll
-                        for (int k = 0; k < HD / 16; ++k)
-                            umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16),
-                                      idesc_s, k != 0 ? 1u : 0u);
-                        if (has_bias)
-                            umma_bf16(d, make_smem_desc(st + OFF_QAUG + t * (16 * 256), 256, 128, 0), make_smem_desc(st + OFF_KAUG, 256, 128, 0),
-                                      idesc_s, 1u);
-                        umma_commit(&s_full[t]);
-                        umma_commit(&qk_empty[s]);
-                        need_pv[t] = 1;
-                        progressed = true;
-                    } else {
-                        const int s = i & 1;
-                        const uint32_t ph = (i >> 1) & 1;
-                        if (!mbar_test(&v_full[s], ph) || !mbar_test(&p_full[t], i & 1)) continue;
-                        tc_fence_after();
-                        const uint32_t v_addr = smem_u32(smem + s * STAGE_BYTES) + OFF_V;
-                        const uint32_t d = tmem_base + t * 256;
-                        for (int j = 0; j < ksteps; ++j)
-                            umma_bf16_ts(d + 128, d + 8 * j, make_smem_desc_sw128(v_addr + j * 2048, 1024, 1024), idesc_o, j != 0 ? 1u : 0u);
-                        umma_commit(&o_full[t]);
-                        umma_commit(&v_empty[s]);
-                        need_pv[t] = 0;
-                        iter[t] = i + 1;
-                        ++done;
-                        progressed = true;
-                    }
-                }
-                if (progressed) spins = 0;
-                else if (++spins > (VTC_MBAR_SPIN_LIMIT << 6)) { printf("vtc: attention3 MMA loop stuck block %d\n", blockIdx.x); __trap(); }
-            }
-        }
-        __syncwarp();
-    } else {
-        // ---------------- softmax groups ----------------
-        const int t = warp >> 2;
-        if (t < ntiles) {
-            const int quarter = warp & 3;
-            const int r_local = quarter * 32 + lane;
-            const int row = t * 128 + r_local;
-            const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-            const int nchunks = (N + 31) >> 5;
-            const float sc = p.scale_log2;
-            const bool warp_active = (t * 128 + quarter * 32) < N;
-            const bool cls_warp = (t == 0) && (quarter == 0) && (p.cls_rows != nullptr);
-            int it_ = blockIdx.x;
-            for (int i = 0; it_ < n_items; ++i, it_ += gridDim.x) {
-                const int it = p.reverse ? n_items - 1 - it_ : it_;
-                const int b = it / p.H, h = it - b * p.H;
-                const uint32_t ph = i & 1;
-                unsigned long long* tr = (p.trace && i < 32 && (warp & 3) == 0 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 32 + i) * 2 + t) * 8 : nullptr;
-                auto stamp = [&](int slot) {
-                    if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
-                };
-                stamp(0);
-                mbar_wait(&s_full[t], ph);
-                stamp(1);
-                tc_fence_after();
-                float inv = 0.f;
-                if (warp_active) {
-                    float sum;
-                    if (cls_warp) softmax_single_pass<true>(t_s, nchunks, N, sc, cls_s, lane == 0, sum);
-                    else softmax_single_pass<false>(t_s, nchunks, N, sc, cls_s, false, sum);
-                    tmem_st_wait();
-                    inv = 1.0f / sum;
-                }
-                tc_fence_before();
-                stamp(2);
-                mbar_arrive(&p_full[t]);
-                if (cls_warp) {
-                    const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
-                    __syncwarp();
-                    float* dst = p.cls_rows + (static_cast<size_t>(b) * p.H + h) * N;
-                    for (int j = lane; j < N; j += 32) dst[j] = cls_s[j] * inv0;
-                    __syncwarp();
-                }
-                stamp(3);
-                mbar_wait(&o_full[t], ph);
-                stamp(4);
-                tc_fence_after();
-                if (warp_active) {
-                    uint32_t o0[32], o1[32];
-                    tmem_ld_32x32b_x32(t_s + 128, o0);
-                    tmem_ld_32x32b_x32(t_s + 160, o1);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    mbar_arrive(&o_empty[t]);          // the region can take the next item's S while we store
-                    if (row < N) {
-                        __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * (p.H * HD) + h * HD;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            st_u4(dst + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
-                                                          pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
-                                                          pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
-                                                          pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv)));
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            st_u4(dst + 32 + 8 * g, make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
-                                                               pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
-                                                               pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
-                                                               pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv)));
-                    }
-                } else {
-                    tc_fence_before();
-                    mbar_arrive(&o_empty[t]);
-                }
-                stamp(5);
-            }
-        }
-    }
-    __syncwarp();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
-}
-
-
-static bool attn_use_v1() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("VTC_ATTN_V1");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_out, int batch, int n_tokens, int heads,
               float scale, cudaStream_t stream, int reverse) {
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
-    static int kv_env = -1;
-    if (kv_env < 0) {
-        const char* e = getenv("VTC_ATTN_KV");
-        kv_env = (e && e[0] == '1') ? 1 : 0;
-    }
-    static int v3_env = -1;
-    if (v3_env < 0) {
-        const char* e = getenv("VTC_ATTN_V3");
-        v3_env = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (attn_out == nullptr && kv_env == 0 && v3_env == 0)      // fast path: column-split pipelined kernel (attention_cs.cu)
+    if (attn_out == nullptr)              // fast path: two-group column-split kernel (attention_cs.cu), any sequence length
         return attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse);
-    if (n_tokens > attn::MAXN || kv_env == 1)      // full P of long sequences: KV-blocked kernel (attention_kv.cu)
+    if (n_tokens > attn2::MAXN)           // full P of long sequences: KV-blocked two-sweep kernel (attention_kv.cu)
         return attention_kv(qkv, key_bias, out, cls_rows, attn_out, batch, n_tokens, heads, scale, false, stream, reverse);
+    // full P, N <= 256: the whole row of scores sits in TMEM, the normalised probabilities are a third read of it
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    const int D = heads * attn::HD;
+    const int D = heads * attn2::HD;
     uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)n_tokens, (uint64_t)batch};
     uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)n_tokens * 3 * D * 2};
-    CUtensorMap tmKV;
-    uint32_t box[3] = {attn::HD, attn::MAXN, 1};
-    rc = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, box);
+    CUtensorMap tmQ, tmKV;
+    uint32_t boxkv[3] = {attn2::HD, attn2::MAXN, 1};
+    uint32_t boxq[3] = {attn2::HD, 128, 1};
+    rc = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxkv);
     if (rc != VTC_OK) return rc;
-    if (attn_use_v1()) {
-        static bool configured = false;
-        if (!configured) {
-            VTC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-            configured = true;
-        }
-        AttnParams p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale * 1.4426950408889634f};
-        attention_kernel<<<batch * heads, attn::THREADS, attn::SMEM_BYTES, stream>>>(tmKV, p);
-        VTC_CHECK_LAUNCH();
-        return VTC_OK;
-    }
-    static int v2_env = -1;
-    if (v2_env < 0) {
-        const char* e = getenv("VTC_ATTN_V2");
-        v2_env = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (attn_out == nullptr && v2_env == 0) {
-        // fast path: persistent kernel (the full-P output of the reference-compatible 6-tuple uses the v2 kernel below)
-        const int NP = (n_tokens + 15) & ~15;
-        CUtensorMap tmQ3, tmKV3;
-        uint32_t boxq3[3] = {attn::HD, 256, 1};
-        uint32_t boxkv3[3] = {attn::HD, static_cast<uint32_t>(NP), 1};
-        rc = make_tmap_bf16(&tmQ3, qkv, 3, dims, strides, boxq3);
-        if (rc != VTC_OK) return rc;
-        rc = make_tmap_bf16(&tmKV3, qkv, 3, dims, strides, boxkv3);
-        if (rc != VTC_OK) return rc;
-        static bool configured3 = false;
-        if (!configured3) {
-            VTC_CUDA(cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn3::SMEM_BYTES));
-            configured3 = true;
-        }
-        Attn3Params p3{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, batch, n_tokens, heads, scale, scale * 1.4426950408889634f, g_attn_trace, reverse};
-        const int items = batch * heads;
-        const int grid = items < device_sm_count() ? items : device_sm_count();
-        attention3_kernel<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tmQ3, tmKV3, p3);
-        VTC_CHECK_LAUNCH();
-        return VTC_OK;
-    }
-    CUtensorMap tmQ;
-    uint32_t boxq[3] = {attn::HD, 128, 1};
     rc = make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq);
     if (rc != VTC_OK) return rc;
     static bool configured2 = false;
@@ -1060,13 +409,8 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
         VTC_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured2 = true;
     }
-    static int ts_env = -1;
-    if (ts_env < 0) {
-        const char* e = getenv("VTC_ATTN_TS");
-        ts_env = (e && e[0] == '1') ? 1 : 0;
-    }
     Attn2Params p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale, scale * 1.4426950408889634f,
-                  g_attn_trace, (ts_env == 1 && attn_out == nullptr) ? 1 : 0};
+                  g_attn_trace, 0};
     const int ntiles = (n_tokens + 127) / 128;
     attention2_kernel<<<batch * heads * ntiles, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
     VTC_CHECK_LAUNCH();

@@ -2,28 +2,30 @@
 // P[b,h,0,:], any sequence length up to 2048 tokens, bf16 operands.  (Full-P output and the split-bf16 fp32 mode
 // are served by attention_kv.cu.)
 //
-// One persistent CTA per SM streams work items (image, head, 128-query tile) through a software pipeline in which the
-// eight softmax warps NEVER wait for a tensor-core round trip:
-//   warp 8   producer   TMA loads of Q (per item) and K / V blocks (<= 208 keys), two stages each; it also writes the
-//                       "augmented" mask operands of the stage (see below)
-//   warp 9   MMA        one elected thread; program order  QK(s), PV(s-1), QK(s+1), PV(s), ...  (s = key-block step)
-//   warps 0-15 softmax  the 128 x KB score block of step s is split by COLUMNS into PARTS = 4 ranges of 32-key chunks;
-//                       warp w works on range w / 4 for the 32 rows of TMEM lane quarter w % 4.  Four warps per SM
-//                       sub-partition are what it takes to keep the TMEM read port busy: tcgen05.ld stalls the issuing
-//                       warp for the whole transfer (303 clk per 32x32 fp32 block, tools/ubench/tmem.cu), so the other
-//                       warps' MUFU / FMA work has to fill that time.
-// TMEM (512 columns): S buffers at 0 and 208 (step parity), O accumulator at 416, two 16-column slots at 480 / 496 that
-// receive Q . K[0:16]^T of an item's first block (the initial row maximum both halves agree on).
-// While the softmax warps work on S(s), the tensor core finishes PV(s-1) and QK(s+1) into the other buffer, and the
-// epilogue of an item (O / rowsum -> bf16) is deferred until after the softmax of the NEXT step, when its PV has long
-// completed.  The only synchronisation inside a step is one named barrier between the PARTS warps that share a row:
-// they exchange (row maximum, row sum) through shared memory.
+// What bounds this kernel is the TMEM read port: every score has to come out of TMEM once as fp32 (54 B/clk per SM
+// measured, tools/ubench/tmem.cu), and tcgen05.ld stalls the issuing warp for the whole transfer (303 clk per 32x32
+// block), so the MUFU / FMA work of a warp cannot overlap its own loads -- only other warps on the same sub-partition
+// can fill that time.  Hence the shape:
+//   * one persistent CTA per SM runs TWO independent pipelines ("groups"), each on its own stream of work items
+//     (image, head, 128-query tile), with its own 256 TMEM columns, Q / K / V tiles, producer warp and MMA warp;
+//   * inside a group the 128 x KB score block is split by COLUMNS between two sets of four softmax warps (PARTS = 2):
+//     warp w works on column range (w / 4) % 2 for the 32 rows of TMEM lane quarter w % 4.
+// That puts four softmax warps on every sub-partition, two per group; while one group waits for a tensor-core round trip
+// (QK^T of its next block, or P V before the epilogue) the other group's warps own the port.
+//   warps 0-7 / 8-15   softmax + epilogue of group 0 / 1
+//   warps 16, 17       producers: TMA loads of Q (per item) and of the K / V blocks (<= 208 keys), one stage each -- the
+//                      next block is fetched while the current one is in the softmax; they also write the mask operands
+//   warps 18, 19       MMA issuers (one elected thread each): QK(s) -> [softmax] -> PV(s) -> QK(s+1) ...
+// TMEM region of a group (256 columns): S at 0..207, the O accumulator at 192..255 (it is written by PV only after the
+// softmax has consumed S), and at 208..223 a 16-column slot that receives Q . K[0:16]^T of an item's first block: the
+// initial row maximum both column halves agree on without talking to each other.
 //
-// Softmax: single pass over S (TMEM reads are the scarcest resource), exponentials taken against a running maximum m
-// that starts at ceil(max of the first 8 keys) and is raised, by whole octaves only, when a chunk exceeds it by more than
-// 2^8 -- the stored bf16 P chunks, the row sum and (between key blocks) the O accumulator are then rescaled by an exact
-// power of two.  P overwrites the consumed S columns of the SAME warp as bf16 pairs (tcgen05.st) and is the TMEM A
-// operand of the second MMA; V is consumed MN-major exactly as TMA wrote it.
+// Softmax: single pass over S, exponentials taken against a running maximum m that starts at ceil(max of the first 8
+// keys) and is raised, by whole octaves only, when a chunk exceeds it by more than 2^8 -- the stored bf16 P chunks, the
+// row sum and (between key blocks) the O accumulator are then rescaled by an exact power of two.  The two warps that
+// share a row exchange (m, row sum) through shared memory once per block (one 64-thread named barrier).  P overwrites
+// the consumed S columns of the SAME warp as bf16 pairs (tcgen05.st) and is the TMEM A operand of the second MMA; V is
+// consumed MN-major exactly as TMA wrote it.
 //
 // Mask: the reference's -100*min(v_i + v_j, 1) (vit_model.py:348-361) is applied BY THE TENSOR CORE through one extra
 // K-step with Q_aug[i] = [v_i == 0] and K_aug[j] = key_bias[j] / scale, so the softmax code has no mask handling and
@@ -38,31 +40,35 @@ namespace acs {
 constexpr int HD = 64;
 constexpr int NMAX = 2048;
 constexpr int KBMAX = 208;                 // keys per block when the whole sequence fits one block
-constexpr int KBLONG = 192;                // keys per block otherwise
-constexpr int PARTS = 4;                   // column ranges per score block = softmax warps per TMEM lane quarter
-constexpr int SM_WARPS = 4 * PARTS;        // softmax warps; then one producer warp and one MMA warp
-constexpr int THREADS = (SM_WARPS + 2) * 32;
+constexpr int KBLONG = 192;                // keys per block otherwise (S must not reach into the O accumulator)
+constexpr int GROUPS = 2;
+constexpr int PARTS = 2;                   // column ranges per score block
+constexpr int GROUP_WARPS = 4 * PARTS;     // softmax warps of a group
+constexpr int SM_WARPS = GROUPS * GROUP_WARPS;
+constexpr int THREADS = (SM_WARPS + 2 * GROUPS) * 32;
 constexpr int OCOLS = 64 / PARTS;          // O columns each part normalises and stores
-constexpr int S_COLS = 208;
-constexpr int O_COL = 416;
-constexpr int M0_COL = 480;
+constexpr int REGION_COLS = 256;
+constexpr int O_COL = 192;
+constexpr int M0_COL = 208;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 constexpr int Q_BYTES = 128 * 128;
 constexpr int QAUG_BYTES = 128 * 32;
 constexpr int KV_BYTES = KBMAX * 128;
 constexpr int KAUG_BYTES = KBMAX * 32;
 constexpr int OFF_Q = 0;
-constexpr int OFF_K = 2 * Q_BYTES;
-constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-constexpr int OFF_QAUG = OFF_V + 2 * KV_BYTES;
-constexpr int OFF_KAUG = OFF_QAUG + 2 * QAUG_BYTES;
-constexpr int OFF_CLS = OFF_KAUG + 2 * KAUG_BYTES;       // [2][NMAX] floats: raw logits of the CLS row
-constexpr int OFF_XCH = OFF_CLS + 2 * NMAX * 4;          // [2 step parity][PARTS][128 rows] float2 (m, sum)
-constexpr int OFF_BAR = OFF_XCH + 2 * PARTS * 128 * 8;
+constexpr int OFF_K = Q_BYTES;
+constexpr int OFF_V = OFF_K + KV_BYTES;
+constexpr int OFF_QAUG = OFF_V + KV_BYTES;
+constexpr int OFF_KAUG = OFF_QAUG + QAUG_BYTES;
+constexpr int GROUP_BYTES = ((OFF_KAUG + KAUG_BYTES + 1023) / 1024) * 1024;
+constexpr int OFF_CLS = GROUPS * GROUP_BYTES;                  // [GROUPS][NMAX] floats: raw logits of the CLS row
+constexpr int OFF_XCH = OFF_CLS + GROUPS * NMAX * 4;           // [GROUPS][PARTS][128 rows] float2 (m, sum)
+constexpr int OFF_BAR = OFF_XCH + GROUPS * PARTS * 128 * 8;
+constexpr int BARS_PER_GROUP = 10;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && KV_BYTES % 1024 == 0, "swizzle atoms need 1024-byte tiles");
+static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && KV_BYTES % 1024 == 0 && GROUP_BYTES % 1024 == 0, "swizzle atoms need 1024-byte tiles");
 static_assert(SMEM_BYTES <= 232448, "attention_cs smem budget");
-static_assert(2 * S_COLS + 64 + 32 <= 512, "TMEM budget");
+static_assert(KBLONG <= O_COL && M0_COL + 16 <= REGION_COLS && KBMAX <= M0_COL, "TMEM region layout");
 
 struct Params {
     const float* key_bias;   // [B,N] or null
@@ -72,7 +78,7 @@ struct Params {
     int KB, nb;
     float scale, scale_log2;
     int reverse;
-    unsigned long long* trace;   // debug: [grid][64 steps][8 warps][8] %globaltimer stamps, normally null
+    unsigned long long* trace;   // debug: [grid][64 steps][SM_WARPS + GROUPS][8] %globaltimer stamps, normally null
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -183,39 +189,45 @@ __global__ void __launch_bounds__(THREADS, 1)
 attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* q_full = bars + 0;     // [2]
-    uint64_t* q_empty = bars + 2;    // [2]
-    uint64_t* k_full = bars + 4;     // [2]
-    uint64_t* k_empty = bars + 6;    // [2]
-    uint64_t* v_full = bars + 8;     // [2]
-    uint64_t* v_empty = bars + 10;   // [2]
-    uint64_t* s_full = bars + 12;    // [2] S(s) ready
-    uint64_t* p_full = bars + 14;    // [2] P(s) stored by all softmax threads
-    uint64_t* o_full = bars + 16;    // O of an item complete
-    uint64_t* o_empty = bars + 17;   // O of an item read out (all softmax threads)
-    uint64_t* pv_done = bars + 18;   // PV(s) retired (only waited for on the rare O-rescale path)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
-
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // group of this warp: softmax warps 0..15 by eights, then producers 16, 17 and MMA issuers 18, 19
+    const int g = (warp < SM_WARPS) ? warp / GROUP_WARPS : (warp - SM_WARPS) & 1;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR) + g * BARS_PER_GROUP;
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* k_full = bars + 2;
+    uint64_t* k_empty = bars + 3;
+    uint64_t* v_full = bars + 4;
+    uint64_t* v_empty = bars + 5;
+    uint64_t* s_full = bars + 6;     // S(s) ready
+    uint64_t* p_full = bars + 7;     // P(s) stored by all softmax threads of the group
+    uint64_t* o_full = bars + 8;     // O of an item complete
+    uint64_t* o_empty = bars + 9;    // O of an item read out (all softmax threads of the group)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + GROUPS * BARS_PER_GROUP * 8);
+    uint8_t* gsm = smem + g * GROUP_BYTES;
+
     const int N = p.N, H = p.H, KB = p.KB, nb = p.nb;
     const int qtiles = (N + 127) >> 7;
     const int n_items = p.B * H * qtiles;
-    const int my_items = (static_cast<int>(blockIdx.x) < n_items) ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+    // items of this (CTA, group): global index (GROUPS * blockIdx + g) + i * GROUPS * gridDim
+    const int first = GROUPS * static_cast<int>(blockIdx.x) + g, stride = GROUPS * static_cast<int>(gridDim.x);
+    const int my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
     const bool has_bias = p.key_bias != nullptr;
     const int D = H * HD;
     const uint32_t kv_bytes = static_cast<uint32_t>(KB) * 128u;
     auto item_of = [&](int i) {
-        const int it = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        const int it = first + i * stride;
         return p.reverse ? n_items - 1 - it : it;
     };
 
-    if (warp == SM_WARPS + 1) {
+    if (warp == SM_WARPS + GROUPS) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmKV);
-            for (int i = 0; i < 19; ++i) mbar_init(bars + i, (i == 14 || i == 15 || i == 17) ? SM_WARPS * 32 : 1);
+            uint64_t* all = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+            for (int gg = 0; gg < GROUPS; ++gg)
+                for (int i = 0; i < BARS_PER_GROUP; ++i) mbar_init(all + gg * BARS_PER_GROUP + i, (i == 7 || i == 9) ? GROUP_WARPS * 32 : 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -224,9 +236,9 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = *tmem_ptr + g * REGION_COLS;
 
-    if (warp == SM_WARPS) {
+    if (warp >= SM_WARPS && warp < SM_WARPS + GROUPS) {
         // ---------------- producer ----------------
         const float inv_scale = 1.0f / p.scale;
         uint32_t step = 0;
@@ -235,13 +247,12 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int qt = it % qtiles;
             const int bh = it / qtiles;
             const int b = bh / H, h = bh - b * H;
-            const int qs = i & 1;
             const float* kb = has_bias ? p.key_bias + static_cast<size_t>(b) * N : nullptr;
-            if (lane == 0) mbar_wait(&q_empty[qs], ((i >> 1) & 1) ^ 1);
+            if (lane == 0) mbar_wait_fast(q_empty, (i & 1) ^ 1);
             __syncwarp();
             if (has_bias) {
                 // no-swizzle K-major core matrices: 8 rows x 16 B, LBO (K direction) 128 B, SBO (8-row groups) 256 B
-                uint8_t* qa = smem + OFF_QAUG + qs * QAUG_BYTES;
+                uint8_t* qa = gsm + OFF_QAUG;
                 for (int r = lane; r < 128; r += 32) {
                     const int row = qt * 128 + r;
                     const float flag = (row < N && kb[row] == 0.f) ? 1.0f : 0.0f;
@@ -253,16 +264,15 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 __syncwarp();
             }
             if (lane == 0) {
-                mbar_arrive_expect_tx(&q_full[qs], Q_BYTES);
-                tma_load_3d(smem + OFF_Q + qs * Q_BYTES, &tmQ, &q_full[qs], h * HD, qt * 128, b);
+                mbar_arrive_expect_tx(q_full, Q_BYTES);
+                tma_load_3d(gsm + OFF_Q, &tmQ, q_full, h * HD, qt * 128, b);
             }
             for (int j = 0; j < nb; ++j, ++step) {
-                const int st = step & 1;
-                const uint32_t ph = (step >> 1) & 1;
-                if (lane == 0) mbar_wait(&k_empty[st], ph ^ 1);
+                const uint32_t ph = step & 1;
+                if (lane == 0) mbar_wait_fast(k_empty, ph ^ 1);
                 __syncwarp();
                 if (has_bias) {
-                    uint8_t* ka = smem + OFF_KAUG + st * KAUG_BYTES;
+                    uint8_t* ka = gsm + OFF_KAUG;
                     for (int r = lane; r < KB; r += 32) {
                         const int key = j * KB + r;
                         const float v = (key < N) ? kb[key] * inv_scale : 0.f;
@@ -274,77 +284,80 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(&k_full[st], kv_bytes);
-                    tma_load_3d(smem + OFF_K + st * KV_BYTES, &tmKV, &k_full[st], D + h * HD, j * KB, b);
-                    mbar_wait(&v_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&v_full[st], kv_bytes);
-                    tma_load_3d(smem + OFF_V + st * KV_BYTES, &tmKV, &v_full[st], 2 * D + h * HD, j * KB, b);
+                    mbar_arrive_expect_tx(k_full, kv_bytes);
+                    tma_load_3d(gsm + OFF_K, &tmKV, k_full, D + h * HD, j * KB, b);
+                    mbar_wait_fast(v_empty, ph ^ 1);
+                    mbar_arrive_expect_tx(v_full, kv_bytes);
+                    tma_load_3d(gsm + OFF_V, &tmKV, v_full, 2 * D + h * HD, j * KB, b);
                 }
                 __syncwarp();
             }
         }
-    } else if (warp == SM_WARPS + 1) {
-        // ---------------- MMA issuer: QK(s), PV(s-1), QK(s+1), PV(s), ... ----------------
+    } else if (warp >= SM_WARPS + GROUPS) {
+        // ---------------- MMA issuer: QK(s) -> [softmax] -> PV(s) -> QK(s+1) ... ----------------
         if (lane == 0) {
             const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
             const uint32_t idesc_m0 = make_idesc_bf16(128, 16, 0, 0);
-            const int total = my_items * nb;
-            for (int s = 0; s <= total; ++s) {
-                if (s < total) {
-                    const int i = s / nb, j = s - i * nb;
-                    const int st = s & 1;
-                    if (j == 0) mbar_wait(&q_full[i & 1], (i >> 1) & 1);
-                    mbar_wait(&k_full[st], (s >> 1) & 1);
-                    tc_fence_after();
+            const uint32_t q_addr = smem_u32(gsm + OFF_Q), k_addr = smem_u32(gsm + OFF_K), v_addr = smem_u32(gsm + OFF_V);
+            const uint32_t qa_addr = smem_u32(gsm + OFF_QAUG), ka_addr = smem_u32(gsm + OFF_KAUG);
+            if (g == 1 && static_cast<int>(blockIdx.x) * GROUPS < n_items) {
+                // start the two groups out of phase: group 1 takes off when group 0 has finished its first softmax
+                uint64_t* p_full0 = reinterpret_cast<uint64_t*>(smem + OFF_BAR) + 7;
+                mbar_wait_fast(p_full0, 0);
+            }
+            uint32_t step = 0;
+            for (int i = 0; i < my_items; ++i) {
+                mbar_wait_fast(q_full, i & 1);
+                for (int j = 0; j < nb; ++j, ++step) {
+                    const uint32_t ph = step & 1;
                     const int vj = min(KB, N - j * KB);
                     const int nmma = (vj + 15) & ~15;
+                    const int nch = (vj + 31) >> 5;
+                    // the S columns are free: PV(s-1) was issued by this thread (in-order pipe).  A new item also overwrites the m0
+                    // slot and (single-block layout) the O columns, which the softmax warps must have read out first
+                    unsigned long long* tr = (p.trace && step < 64) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + step) * (SM_WARPS + GROUPS) + SM_WARPS + g) * 8 : nullptr;
+                    auto stamp = [&](int slot) {
+                        if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
+                    };
+                    stamp(0);
+                    if (j == 0 && i > 0) mbar_wait_fast(o_empty, (i - 1) & 1);
+                    stamp(1);
+                    mbar_wait_fast(k_full, ph);
+                    tc_fence_after();
+                    stamp(2);
                     const uint32_t idesc_s = make_idesc_bf16(128, nmma, 0, 0);
-                    const uint32_t q_addr = smem_u32(smem + OFF_Q + (i & 1) * Q_BYTES);
-                    const uint32_t k_addr = smem_u32(smem + OFF_K + st * KV_BYTES);
-                    const uint32_t qa_addr = smem_u32(smem + OFF_QAUG + (i & 1) * QAUG_BYTES);
-                    const uint32_t ka_addr = smem_u32(smem + OFF_KAUG + st * KAUG_BYTES);
-                    // S buffer (s & 1) is free: PV(s-2), which read P out of it, was issued earlier by this thread
-                    const uint32_t d = tmem_base + st * S_COLS;
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
-                        umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s,
+                        umma_bf16(tmem_base, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s,
                                   k != 0 ? 1u : 0u);
-                    if (has_bias) umma_bf16(d, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_s, 1u);
+                    if (has_bias) umma_bf16(tmem_base, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_s, 1u);
                     if (j == 0) {
-                        // the first 16 keys once more, into a slot nobody overwrites: both column halves derive the same m0
-                        const uint32_t dm = tmem_base + M0_COL + (i & 1) * 16;
+                        // the first 16 keys once more, into a slot no softmax warp overwrites: both column halves derive the same m0
 #pragma unroll
                         for (int k = 0; k < HD / 16; ++k)
-                            umma_bf16(dm, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16),
+                            umma_bf16(tmem_base + M0_COL, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16),
                                       idesc_m0, k != 0 ? 1u : 0u);
-                        if (has_bias) umma_bf16(dm, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_m0, 1u);
+                        if (has_bias) umma_bf16(tmem_base + M0_COL, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_m0, 1u);
                     }
-                    umma_commit(&s_full[st]);
-                    umma_commit(&k_empty[st]);
-                    if (j == nb - 1) umma_commit(&q_empty[i & 1]);
-                }
-                if (s > 0) {
-                    const int sp = s - 1;
-                    const int i = sp / nb, j = sp - i * nb;
-                    const int st = sp & 1;
-                    mbar_wait(&p_full[st], (sp >> 1) & 1);
-                    if (j == 0 && i > 0) mbar_wait(o_empty, (i - 1) & 1);
-                    mbar_wait(&v_full[st], (sp >> 1) & 1);
+                    umma_commit(s_full);
+                    umma_commit(k_empty);
+                    if (j == nb - 1) umma_commit(q_empty);
+                    // ---- O (+)= P(s) V(s)
+                    stamp(3);
+                    mbar_wait_fast(p_full, ph);
+                    stamp(4);
+                    mbar_wait_fast(v_full, ph);
                     tc_fence_after();
-                    const int vj = min(KB, N - j * KB);
-                    const int ksteps = (vj + 15) >> 4;
-                    const int nch = (vj + 31) >> 5;
-                    const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
-                    const uint32_t pa = tmem_base + st * S_COLS;
+                    stamp(5);
+                    const int ksteps = nmma >> 4;
                     int part = 0, pb = 0, pe = part_begin(1, nch);     // chunk range [pb, pe) of the column part that owns k-step ks
                     for (int ks = 0; ks < ksteps; ++ks) {
                         while ((ks >> 1) >= pe) { ++part; pb = pe; pe = part_begin(part + 1, nch); }
                         // every part packs its bf16 P from its own first S column on: chunk c of part q sits at column 32 pb + 16 (c - pb)
-                        umma_bf16_ts(tmem_base + O_COL, pa + 8 * ks + pb * 16, make_smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), idesc_o,
+                        umma_bf16_ts(tmem_base + O_COL, tmem_base + 8 * ks + pb * 16, make_smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), idesc_o,
                                      (j | ks) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&v_empty[st]);
-                    umma_commit(pv_done);
+                    umma_commit(v_empty);
                     if (j == nb - 1) umma_commit(o_full);
                 }
             }
@@ -352,44 +365,14 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
     } else {
         // ---------------- softmax warps ----------------
-        const int part = warp >> 2;
+        const int part = (warp >> 2) % PARTS;
         const int quarter = warp & 3;
         const int r_local = quarter * 32 + lane;
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const float sc = p.scale_log2;
-        float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);
-        float* cls_s = reinterpret_cast<float*>(smem + OFF_CLS);
-        // deferred epilogue of the previous item
-        bool pending = false;
-        int pend_i = 0, pend_row = 0, pend_b = 0, pend_h = 0;
-        float pend_inv = 0.f;
-        bool pend_active = false;
-        auto epilogue = [&]() {
-            mbar_wait(o_full, pend_i & 1);
-            tc_fence_after();
-            if (pend_active) {
-                uint32_t o[OCOLS];
-                tmem_ld_cols(t_lane + O_COL + part * OCOLS, o);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(o_empty);
-                if (pend_row < N) {
-                    __nv_bfloat16* dst = p.out + (static_cast<size_t>(pend_b) * N + pend_row) * D + pend_h * HD + part * OCOLS;
-                    const float inv = pend_inv;
-#pragma unroll
-                    for (int g4 = 0; g4 < OCOLS / 8; ++g4)
-                        st_u4(dst + 8 * g4, make_uint4(pack_bf16x2(__uint_as_float(o[8 * g4]) * inv, __uint_as_float(o[8 * g4 + 1]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 2]) * inv, __uint_as_float(o[8 * g4 + 3]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 4]) * inv, __uint_as_float(o[8 * g4 + 5]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 6]) * inv, __uint_as_float(o[8 * g4 + 7]) * inv)));
-                }
-            } else {
-                tc_fence_before();
-                mbar_arrive(o_empty);
-            }
-            pending = false;
-        };
-
+        float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH) + g * PARTS * 128;
+        float* cls_buf = reinterpret_cast<float*>(smem + OFF_CLS) + g * NMAX;
+        const uint32_t row_bar = 1 + g * 4 + quarter;           // named barrier of the PARTS warps that share these rows
         int s = 0;
         for (int i = 0; i < my_items; ++i) {
             const int it = item_of(i);
@@ -400,29 +383,26 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const bool warp_active = (qt * 128 + quarter * 32) < N;
             const bool cls_warp = (qt == 0) && (quarter == 0) && (p.cls_rows != nullptr);
             const bool cls_thread = cls_warp && lane == 0;
-            float* cls_buf = cls_s + (i & 1) * NMAX;
             float m = 0.f;
             uint64_t sum2 = pack2(0.f, 0.f);
             float inv = 0.f;
             for (int j = 0; j < nb; ++j, ++s) {
-                const int st = s & 1;
                 const int vj = min(KB, N - j * KB);
                 const int nch = (vj + 31) >> 5;
                 const int c0 = part_begin(part, nch), c1 = part_begin(part + 1, nch);      // my 32-key chunks of this block
-                const uint32_t t_s = t_lane + st * S_COLS;
                 const uint32_t t_p = t_s + c0 * 32;                                        // my P area: on top of S columns I have consumed
-                unsigned long long* tr = (p.trace && s < 64 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + s) * SM_WARPS + warp) * 8 : nullptr;
+                unsigned long long* tr = (p.trace && s < 64 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + s) * (SM_WARPS + GROUPS) + warp) * 8 : nullptr;
                 auto stamp = [&](int slot) {
                     if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
                 };
                 stamp(0);
-                mbar_wait(&s_full[st], (s >> 1) & 1);
+                mbar_wait_fast(s_full, s & 1);
                 tc_fence_after();
                 stamp(1);
                 if (warp_active) {
                     if (j == 0) {
                         uint32_t f8[8];
-                        tmem_ld_32x32b_x8(t_lane + M0_COL + (i & 1) * 16, f8);
+                        tmem_ld_32x32b_x8(t_s + M0_COL, f8);
                         tmem_ld_wait();
                         float m0 = __uint_as_float(f8[0]);            // key 0 (CLS) always exists and is never masked
 #pragma unroll
@@ -445,14 +425,15 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     // ---- the warps that share these rows agree on the row maximum (and, at the end, on the row sum)
                     float s0, s1;
                     unpack2(sum2, s0, s1);
-                    xch[(st * PARTS + part) * 128 + r_local] = make_float2(m, s0 + s1);
-                    named_bar_sync(1 + quarter, 32 * PARTS);
+                    named_bar_sync(row_bar, 32 * PARTS);           // everybody is done with the previous block's exchange slots
+                    xch[part * 128 + r_local] = make_float2(m, s0 + s1);
+                    named_bar_sync(row_bar, 32 * PARTS);
                     stamp(3);
                     float2 other[PARTS];
                     float m_blk = m;
 #pragma unroll
                     for (int q = 0; q < PARTS; ++q) {
-                        other[q] = xch[(st * PARTS + q) * 128 + r_local];
+                        other[q] = xch[q * 128 + r_local];
                         m_blk = fmaxf(m_blk, other[q].x);
                     }
                     if (__any_sync(0xffffffffu, m < m_blk)) {       // rare: another part raised the maximum further than I did
@@ -463,11 +444,10 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         m = m_blk;
                     }
                     if (j > 0 && __any_sync(0xffffffffu, m_blk > m_start)) {      // rare: earlier key blocks were accumulated against a lower m
-                        mbar_wait(pv_done, (s - 1) & 1);
-                        tc_fence_after();
+                        // PV(s-1) has retired: S(s) was committed behind it on the in-order tensor pipe
                         const float f = pow2_neg(static_cast<int>(m_blk - m_start));
 #pragma unroll
-                        for (int q = 0; q < OCOLS / 16; ++q) rescale_f16(t_lane + O_COL + part * OCOLS + q * 16, f);
+                        for (int q = 0; q < OCOLS / 16; ++q) rescale_f16(t_s + O_COL + part * OCOLS + q * 16, f);
                     }
                     tmem_st_wait();
                     if (j == nb - 1) {
@@ -478,10 +458,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&p_full[st]);
+                mbar_arrive(p_full);
                 stamp(4);
-                if (pending) epilogue();
-                stamp(5);
             }
             if (cls_warp && part == 0) {
                 // P[b,h,0,:] = 2^(x - m) / rowsum from the staged logits of all parts (visible after the row barrier)
@@ -489,15 +467,38 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 float* dst = p.cls_rows + (static_cast<size_t>(b) * H + h) * N;
                 for (int jj = lane; jj < N; jj += 32) dst[jj] = ex2_approx(fmaf(cls_buf[jj], sc, -m0)) * inv0;
             }
-            pending = true;
-            pend_i = i; pend_row = row; pend_b = b; pend_h = h; pend_inv = inv; pend_active = warp_active;
+            // ---- epilogue: O / rowsum -> bf16 (the other group owns the TMEM port meanwhile)
+            unsigned long long* tre = (p.trace && s - 1 < 64 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + (s - 1)) * (SM_WARPS + GROUPS) + warp) * 8 : nullptr;
+            mbar_wait_fast(o_full, i & 1);
+            if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tre[5] = tt; }
+            tc_fence_after();
+            if (warp_active) {
+                uint32_t o[OCOLS];
+                tmem_ld_cols(t_s + O_COL + part * OCOLS, o);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(o_empty);
+                if (row < N) {
+                    __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * D + h * HD + part * OCOLS;
+#pragma unroll
+                    for (int g4 = 0; g4 < OCOLS / 8; ++g4)
+                        st_u4(dst + 8 * g4, make_uint4(pack_bf16x2(__uint_as_float(o[8 * g4]) * inv, __uint_as_float(o[8 * g4 + 1]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 2]) * inv, __uint_as_float(o[8 * g4 + 3]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 4]) * inv, __uint_as_float(o[8 * g4 + 5]) * inv),
+                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 6]) * inv, __uint_as_float(o[8 * g4 + 7]) * inv)));
+                }
+            } else {
+                tc_fence_before();
+                mbar_arrive(o_empty);
+            }
+            if (cls_warp) named_bar_sync(row_bar, 32 * PARTS);     // the CLS staging buffer may be overwritten by the next item
+            if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tre[6] = tt; }
         }
-        if (pending) epilogue();
     }
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == SM_WARPS + 1) tmem_dealloc(tmem_base, 512);
+    if (warp == SM_WARPS + GROUPS) tmem_dealloc(*tmem_ptr, 512);
 }
 }  // namespace acs
 
@@ -544,7 +545,8 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
         configured = true;
     }
     const int items = batch * heads * cdiv(n_tokens, 128);
-    const int grid = items < device_sm_count() ? items : device_sm_count();
+    int grid = cdiv(items, GROUPS);
+    if (grid > device_sm_count()) grid = device_sm_count();
     attention_cs_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
     VTC_CHECK_LAUNCH();
     return VTC_OK;

@@ -163,6 +163,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Low-latency wait for the hand-offs on a kernel's critical path (attention: softmax <-> MMA issuer): the suspend-time
+// hint is short, so a waiting thread re-polls every few hundred nanoseconds instead of being parked.
+#ifndef VTC_MBAR_FAST_HINT_NS
+#define VTC_MBAR_FAST_HINT_NS 64u
+#endif
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(VTC_MBAR_FAST_HINT_NS)
+            : "memory");
+        if (ok) return;
+        if (++spins > (VTC_MBAR_SPIN_LIMIT << 8)) {
+            printf("vtc: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
+            __trap();
+        }
+    }
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
