@@ -69,3 +69,22 @@ def test_extract_cams_single_rank(env):
     out = pipeline.extract_cams_sharded(env["model"], get, n_items=7, batch=3)
     assert out["cam"].shape == (7, 20, 14, 14) and out["rollout"].shape == (7, 196) and out["hwp_logits"].shape == (7, 20)
     assert bool(torch.isfinite(out["cam"]).all()) and float(out["cam"].max()) <= 1.0 + 1e-6
+
+
+def test_device_feeder_overlapped_ingest_equals_direct(env):
+    """Pinned-host batches streamed through DeviceFeeder (copy of batch i+1 on a side stream during batch i) give exactly
+    the results of device-resident batches, in order, for more batches than buffers."""
+    from vision_transformer_cam_b200 import pipeline as PIPE
+    VF, dev, model = env["VF"], env["dev"], env["model"]
+    host = [VF.make_images(4 * i, 4).pin_memory() for i in range(5)]
+    direct = [model.forward_cam(h.to(dev), mask_norm="image").logits.clone() for h in host]
+    fed = []
+    for x in PIPE.DeviceFeeder(dev).stream(iter(host)):
+        assert x.is_cuda
+        fed.append(model.forward_cam(x, mask_norm="image").logits.clone())
+    assert len(fed) == 5 and all(torch.equal(a, b) for a, b in zip(fed, direct))
+    mixed = list(PIPE.DeviceFeeder(dev).stream([host[0], host[1].to(dev), host[2]]))
+    assert len(mixed) == 3 and torch.equal(mixed[1].cpu(), host[1])
+    out = PIPE.extract_cams_sharded(model, lambda lo, hi: torch.cat(host)[lo:hi].pin_memory(), 20, batch=6, with_rollout=False)
+    ref = PIPE.extract_cams_sharded(model, lambda lo, hi: torch.cat(host)[lo:hi].to(dev), 20, batch=6, with_rollout=False)
+    assert torch.equal(out["cam"], ref["cam"]) and out["cam"].shape[0] == 20

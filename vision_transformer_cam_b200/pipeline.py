@@ -7,13 +7,78 @@ normalised image tensors [B,3,S,S] (the output of the reference's transforms, pr
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, Optional, Tuple
+from typing import Callable, Dict, Iterable, Iterator, Optional, Tuple
 
 import torch
 
 from . import cam as CAM
 from . import dist as D
 from .vit_model import VisionTransformer
+
+
+class DeviceFeeder:
+    """Host -> device ingest overlapped with compute: batch i+1 is copied from (pinned) host memory on a side stream into
+    the second of two device buffers while batch i runs through the forward on the caller's stream.
+
+        for x in DeviceFeeder(device).stream(host_batches):     # x: device tensor, valid until the next iteration
+            out = model.forward_cam(x)
+
+    Batches that already live on the device are passed through untouched."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bufs: list = [None] * depth
+        self.ready = [torch.cuda.Event() for _ in range(depth)]      # copy into buffer k finished
+        self.free = [torch.cuda.Event() for _ in range(depth)]       # compute on buffer k finished
+
+    def _start_copy(self, k: int, host: torch.Tensor, used_before: bool) -> torch.Tensor:
+        buf = self.bufs[k]
+        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+            buf = self.bufs[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+            # the caching allocator may hand out a block whose previous owner still has kernels queued on the compute stream:
+            # reuse is only ordered on THAT stream, so the first copy into a new buffer waits for it
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.copy_stream):
+            if used_before:
+                self.copy_stream.wait_event(self.free[k])
+            buf.copy_(host, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        return buf
+
+    def stream(self, batches: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
+        it = iter(batches)
+        compute = torch.cuda.current_stream(self.device)
+        pending = []                                   # [(slot or None, tensor)] copies in flight, oldest first
+        n = 0
+
+        def launch() -> bool:
+            nonlocal n
+            try:
+                b = next(it)
+            except StopIteration:
+                return False
+            if b.is_cuda:
+                pending.append((None, b))
+            else:
+                k = n % self.depth
+                pending.append((k, self._start_copy(k, b, n >= self.depth)))
+                n += 1
+            return True
+
+        for _ in range(self.depth - 1):
+            launch()
+        while True:
+            launch()                                   # keep `depth - 1` copies ahead of the batch being consumed
+            if not pending:
+                return
+            k, x = pending.pop(0)
+            if k is not None:
+                compute.wait_event(self.ready[k])
+            yield x
+            if k is not None:
+                self.free[k].record(compute)
 
 
 @dataclass
@@ -79,14 +144,16 @@ class Validator:
 def extract_cams_sharded(model: VisionTransformer, get_images: Callable[[int, int], torch.Tensor], n_items: int, batch: int = 256,
                          with_rollout: bool = True, gather: bool = True) -> Dict[str, torch.Tensor]:
     """BASELINE config 3: CAM (+ rollout) extraction over an `n_items`-image set, batch-sharded over the ranks of the
-    process group.  `get_images(lo, hi)` returns the normalised images [hi-lo,3,S,S] of global indices [lo,hi) on this
-    rank's GPU.  Returns (on every rank when `gather`) cam [n,C,g,g], rollout [n,g*g] and hwp_logits [n,C] in global
-    image order; collectives: one all_gather per output, outside the forward."""
+    process group.  `get_images(lo, hi)` returns the normalised images [hi-lo,3,S,S] of global indices [lo,hi), either on
+    this rank's GPU or in (pinned) host memory -- host batches are copied in on a side stream while the previous batch
+    computes (`DeviceFeeder`).  Returns (on every rank when `gather`) cam [n,C,g,g], rollout [n,g*g] and hwp_logits [n,C]
+    in global image order; collectives: one all_gather per output, outside the forward."""
     rank, world = D.rank_world()
     lo, hi = D.shard_range(n_items, rank, world)
     cams, rolls, hwps = [], [], []
-    for b0, b1 in D.batches(lo, hi, batch):
-        o = model.forward_cam(get_images(b0, b1), attn_mean=with_rollout)
+    device = next(model.parameters()).device
+    for x in DeviceFeeder(device).stream(get_images(b0, b1) for b0, b1 in D.batches(lo, hi, batch)):
+        o = model.forward_cam(x, attn_mean=with_rollout)
         cams.append(CAM.classic_cam(o.tokens_last, model.head1.weight.data))
         hwps.append(o.hwp_logits)
         if with_rollout:
