@@ -38,6 +38,18 @@ FLOP_IMAGE = FLOP_PATCH + L * (FLOP_QKV + FLOP_ATTN + FLOP_PROJ + 2 * FLOP_FC) +
 GEMM_FLOP_IMAGE = FLOP_PATCH + L * (FLOP_QKV + FLOP_PROJ + 2 * FLOP_FC)
 
 
+def gemm_traffic():
+    """DRAM bytes per GEMM launch (launch-weighted mean over the qkv / proj / fc1 / fc2 GEMMs of a layer) from the committed
+    ncu --set full capture, profiles/r01_traffic.json; None if the file is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        ks = ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2")
+        return sum(t[k]["dram_read"] + t[k]["dram_write"] for k in ks) / len(ks)
+    except Exception:
+        return None
+
+
 def peaks():
     p = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
     try:
@@ -270,7 +282,8 @@ def main():
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "peak_kind": f"bf16_tflops_sustained of {pk['source']} (kernel timed inside a long step); burst {pk['bf16_tflops']}",
                 "frac_of_burst": achieved / pk["bf16_tflops"], "launches_per_step": gemm_n, "ms_per_step": gemm_ms,
-                "share_of_step": gemm_ms / total_ms, "traffic": None,
+                "share_of_step": gemm_ms / total_ms, "traffic": gemm_traffic(),
+                "traffic_note": "mean DRAM bytes per GEMM launch (qkv, proj, fc1, fc2), one ncu --set full capture: profiles/r01_traffic.json",
                 "whole_step_tflops": FLOP_IMAGE * B / (ms / K / 1e3) / 1e12,
                 "whole_step_frac_of_burst": FLOP_IMAGE * B / (ms / K / 1e3) / 1e12 / pk["bf16_tflops"]}
         flops = {"gemm_patch": FLOP_PATCH, "gemm_qkv": L * FLOP_QKV, "gemm_proj": L * FLOP_PROJ, "gemm_fc1": L * FLOP_FC,
