@@ -17,8 +17,9 @@
 //                      next block is fetched while the current one is in the softmax; they also write the mask operands
 //   warps 18, 19       MMA issuers (one elected thread each): QK(s) -> [softmax] -> PV(s) -> QK(s+1) ...
 // TMEM region of a group (256 columns): S at 0..207, the O accumulator at 192..255 (it is written by PV only after the
-// softmax has consumed S), and at 208..223 a 16-column slot that receives Q . K[0:16]^T of an item's first block: the
-// initial row maximum both column halves agree on without talking to each other.
+// softmax has consumed S).  The bf16 P of a column half is stored 16 columns into that half's own S range, so S columns
+// 0..15 of a block stay intact during the softmax: both halves read the scores of the first 8 keys from there and derive
+// the same initial row maximum without talking to each other.
 //
 // Softmax: single pass over S, exponentials taken against a running maximum m that starts at ceil(max of the first 8
 // keys) and is raised, by whole octaves only, when a chunk exceeds it by more than 2^8 -- the stored bf16 P chunks, the
@@ -49,7 +50,7 @@ constexpr int THREADS = (SM_WARPS + 2 * GROUPS) * 32;
 constexpr int OCOLS = 64 / PARTS;          // O columns each part normalises and stores
 constexpr int REGION_COLS = 256;
 constexpr int O_COL = 192;
-constexpr int M0_COL = 208;
+constexpr int P_SHIFT = 16;                // P areas start 16 columns into the owner's S range: S columns 0..15 of a block survive the softmax
 constexpr float RESCALE_THRESHOLD = 8.0f;
 constexpr int Q_BYTES = 128 * 128;
 constexpr int QAUG_BYTES = 128 * 32;
@@ -68,7 +69,7 @@ constexpr int BARS_PER_GROUP = 10;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && KV_BYTES % 1024 == 0 && GROUP_BYTES % 1024 == 0, "swizzle atoms need 1024-byte tiles");
 static_assert(SMEM_BYTES <= 232448, "attention_cs smem budget");
-static_assert(KBLONG <= O_COL && M0_COL + 16 <= REGION_COLS && KBMAX <= M0_COL, "TMEM region layout");
+static_assert(KBLONG <= O_COL && KBMAX + 16 <= REGION_COLS, "TMEM region layout");
 
 struct Params {
     const float* key_bias;   // [B,N] or null
@@ -297,7 +298,6 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---------------- MMA issuer: QK(s) -> [softmax] -> PV(s) -> QK(s+1) ... ----------------
         if (lane == 0) {
             const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
-            const uint32_t idesc_m0 = make_idesc_bf16(128, 16, 0, 0);
             const uint32_t q_addr = smem_u32(gsm + OFF_Q), k_addr = smem_u32(gsm + OFF_K), v_addr = smem_u32(gsm + OFF_V);
             const uint32_t qa_addr = smem_u32(gsm + OFF_QAUG), ka_addr = smem_u32(gsm + OFF_KAUG);
             if (g == 1 && static_cast<int>(blockIdx.x) * GROUPS < n_items) {
@@ -313,8 +313,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int vj = min(KB, N - j * KB);
                     const int nmma = (vj + 15) & ~15;
                     const int nch = (vj + 31) >> 5;
-                    // the S columns are free: PV(s-1) was issued by this thread (in-order pipe).  A new item also overwrites the m0
-                    // slot and (single-block layout) the O columns, which the softmax warps must have read out first
+                    // the S columns are free: PV(s-1) was issued by this thread (in-order pipe).  In the single-block layout a new
+                    // item's S also covers the O columns, which the softmax warps must have read out first
                     unsigned long long* tr = (p.trace && step < 64) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + step) * (SM_WARPS + GROUPS) + SM_WARPS + g) * 8 : nullptr;
                     auto stamp = [&](int slot) {
                         if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
@@ -331,14 +331,6 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         umma_bf16(tmem_base, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s,
                                   k != 0 ? 1u : 0u);
                     if (has_bias) umma_bf16(tmem_base, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_s, 1u);
-                    if (j == 0) {
-                        // the first 16 keys once more, into a slot no softmax warp overwrites: both column halves derive the same m0
-#pragma unroll
-                        for (int k = 0; k < HD / 16; ++k)
-                            umma_bf16(tmem_base + M0_COL, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16),
-                                      idesc_m0, k != 0 ? 1u : 0u);
-                        if (has_bias) umma_bf16(tmem_base + M0_COL, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_m0, 1u);
-                    }
                     umma_commit(s_full);
                     umma_commit(k_empty);
                     if (j == nb - 1) umma_commit(q_empty);
@@ -353,9 +345,10 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     int part = 0, pb = 0, pe = part_begin(1, nch);     // chunk range [pb, pe) of the column part that owns k-step ks
                     for (int ks = 0; ks < ksteps; ++ks) {
                         while ((ks >> 1) >= pe) { ++part; pb = pe; pe = part_begin(part + 1, nch); }
-                        // every part packs its bf16 P from its own first S column on: chunk c of part q sits at column 32 pb + 16 (c - pb)
-                        umma_bf16_ts(tmem_base + O_COL, tmem_base + 8 * ks + pb * 16, make_smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), idesc_o,
-                                     (j | ks) != 0 ? 1u : 0u);
+                        // every part packs its bf16 P from (16 columns past) its own first S column on: chunk c of part q sits at
+                        // column 32 pb + 16 (c - pb) + 16
+                        umma_bf16_ts(tmem_base + O_COL, tmem_base + P_SHIFT + 8 * ks + pb * 16, make_smem_desc_sw128(v_addr + ks * 2048, 1024, 1024),
+                                     idesc_o, (j | ks) != 0 ? 1u : 0u);
                     }
                     umma_commit(v_empty);
                     if (j == nb - 1) umma_commit(o_full);
@@ -390,7 +383,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const int vj = min(KB, N - j * KB);
                 const int nch = (vj + 31) >> 5;
                 const int c0 = part_begin(part, nch), c1 = part_begin(part + 1, nch);      // my 32-key chunks of this block
-                const uint32_t t_p = t_s + c0 * 32;                                        // my P area: on top of S columns I have consumed
+                const uint32_t t_p = t_s + c0 * 32 + P_SHIFT;                              // my P area: on top of S columns I have consumed
                 unsigned long long* tr = (p.trace && s < 64 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + s) * (SM_WARPS + GROUPS) + warp) * 8 : nullptr;
                 auto stamp = [&](int slot) {
                     if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
@@ -402,7 +395,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (warp_active) {
                     if (j == 0) {
                         uint32_t f8[8];
-                        tmem_ld_32x32b_x8(t_s + M0_COL, f8);
+                        tmem_ld_32x32b_x8(t_s, f8);              // S columns 0..7 are never overwritten by P (P_SHIFT)
                         tmem_ld_wait();
                         float m0 = __uint_as_float(f8[0]);            // key 0 (CLS) always exists and is never masked
 #pragma unroll
