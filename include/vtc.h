@@ -155,6 +155,12 @@ VTC_API size_t vtc_workspace_bytes(const vtc_model* m, int32_t batch, const vtc_
 VTC_API int vtc_forward(vtc_model* m, const float* x, int32_t batch, const vtc_outputs* outs, const vtc_forcing* forcing,
                 void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* The same forward fed with decoded images (the step right before the path, predict.py:72-75 /
+ * validate.py:80-84): x uint8 [B,S,S,3] HWC on the device, mean / std HOST arrays of 3 floats (Normalize); ToTensor and
+ * Normalize are applied inside the patch-matrix kernel, bit-identically to the fp32 path.  4x fewer input bytes. */
+VTC_API int vtc_forward_u8(vtc_model* m, const uint8_t* x, const float* mean, const float* std, int32_t batch, const vtc_outputs* outs,
+                   const vtc_forcing* forcing, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
 /* ---- per-kernel timing of the forward (bench.py's roofline numbers) -----------------------------
  * When enabled, vtc_forward brackets every kernel launch with CUDA events on the launch stream;
  * vtc_model_profile_read synchronises on them and ADDS the elapsed milliseconds / launch counts per kind
@@ -189,6 +195,12 @@ VTC_API int vtc_split_bf16(const float* src, void* dst, size_t rows, size_t cols
 VTC_API int vtc_patchify_split(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream);
 VTC_API int vtc_layernorm_split(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim,
                         float eps, void* stream);
+
+/* vtc_patchify for decoded images: x uint8 [B,S,S,3] HWC; mean / std: HOST arrays of 3 floats.  Computes
+ * ((u8 / 255) - mean) / std with the reference's two fp32 operations (ToTensor + Normalize, predict.py:72-75), so the
+ * patch matrix is bit-identical to vtc_patchify of the normalised fp32 tensor.  split != 0: (hi | lo) halves. */
+VTC_API int vtc_patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int32_t batch, int32_t img,
+                    int32_t patch, int32_t split, void* stream);
 
 /* fp32 -> bf16 (weight packing, also used by tests) */
 VTC_API int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream);
@@ -262,6 +274,15 @@ VTC_API int vtc_hwp_cos_vote(const float* hwp_logits, const float* head1_w, cons
  * [up(bg_map[b]) >= bg_thresh]; patches voting -1 count as background. out [B,H,W] u8. */
 VTC_API int vtc_hwp_seg(const float* cos, const int32_t* patch_to_cls, const float* bg_map, float cos_thresh, float bg_thresh,
                 uint8_t* out, int32_t batch, int32_t k, int32_t g, int32_t out_h, int32_t out_w, void* stream);
+/* compute_mAP (utils.py:248-262): per-image sklearn average_precision_score over the C class scores, on the device.
+ * labels [B,C] multi-hot fp32, scores [B,C] fp32 -> ap [B] fp64 (-1 for images without a positive label, which the
+ * reference skips; may be NULL) and acc[0] += sum of APs, acc[1] += number of scored images (may be NULL). */
+VTC_API int vtc_average_precision(const float* labels, const float* scores, int32_t batch, int32_t classes, double* ap, double* acc,
+                          void* stream);
+/* patch-token similarity of predict.py:191-199 (viz): F.normalize with its default dim=1 on [1,N,D] normalises every
+ * feature column across the tokens; sim [B,N,N] is the gram matrix of the result.  scratch: [B,D] floats. */
+VTC_API int vtc_patch_similarity(const float* tokens, float* scratch, float* sim, int32_t batch, int32_t n_tokens, int32_t dim,
+                         void* stream);
 /* ConfusionMatrix.update (utils.py:35-45): mat [n,n] int64 += bincount(n*gt + pred) over gt in [0,n). */
 VTC_API int vtc_confmat_update(const uint8_t* gt, const uint8_t* pred, size_t count, int32_t n, int64_t* mat, void* stream);
 

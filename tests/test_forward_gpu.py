@@ -235,3 +235,18 @@ def test_fp32_mode_matches_reference_golden(env):
         assert agree >= 0.999
     finally:
         model.set_precision("bf16")
+
+
+def test_uint8_image_ingest_equals_fp32_forward(env):
+    """forward_cam_u8 on decoded uint8 HWC images == forward_cam on Normalize(ToTensor(images)), bit for bit."""
+    model = load(env, "peaked")
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (3, 224, 224, 3), generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = img.permute(0, 3, 1, 2).float().div(255)
+    x = ((x - torch.tensor(mean)[None, :, None, None]) / torch.tensor(std)[None, :, None, None]).contiguous()
+    a = model.forward_cam(x.to(env["dev"]), bg=True)
+    b = model.forward_cam_u8(img.to(env["dev"]), mean, std, bg=True)
+    assert torch.equal(a.logits, b.logits) and torch.equal(a.tokens, b.tokens) and torch.equal(a.bg, b.bg)
+    with pytest.raises(ValueError):
+        model.forward_cam_u8(x.to(env["dev"]))

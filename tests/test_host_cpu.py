@@ -119,7 +119,7 @@ D.reduce_counters(c)
 assert c.tolist() == [3, 30]
 assert D.max_over_ranks(float(rank), "cpu") == 1.0
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\n" % rank); sys.stdout.flush()
 '''
 
 

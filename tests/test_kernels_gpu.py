@@ -415,3 +415,49 @@ def test_attention_split(dev, B, N, H, masked):
     print(f"split attention N={N}: O relerr {eo:.2e}, P abs err {ep:.2e}")
     assert eo < 3e-5, eo          # bf16 attention: ~5e-3
     assert ep < 2e-5 and float((cls.double() - ref_p[:, :, 0, :]).abs().max()) < 2e-5
+
+
+# ----------------------------------------------------------------- the rows either side of the path
+def test_patchify_u8_is_bit_identical_to_the_fp32_transform_path(dev):
+    """uint8 HWC ingest: ToTensor (/255) + Normalize inside the im2col kernel == patchify(Normalize(ToTensor(img)))."""
+    from vision_transformer_cam_b200 import ops
+    g = torch.Generator().manual_seed(90)
+    img = torch.randint(0, 256, (3, 64, 64, 3), generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = img.permute(0, 3, 1, 2).float().div(255)                       # ToTensor
+    x = (x - torch.tensor(mean)[None, :, None, None]) / torch.tensor(std)[None, :, None, None]     # Normalize
+    ref = ops.patchify(x.contiguous().to(dev), 16)
+    out = ops.patchify_u8(img.to(dev), 16, mean, std)
+    assert torch.equal(out, ref)
+    out2 = ops.patchify_u8(img.to(dev), 16, mean, std, split=True)
+    assert float((ops.merge_split(out2) - ops.merge_split(ops.patchify(x.contiguous().to(dev), 16, split=True))).abs().max()) == 0.0
+
+
+def test_average_precision_matches_sklearn(dev):
+    """On-device AP == sklearn.metrics.average_precision_score (what utils.py:258 calls), incl. tied scores and rows
+    without positives (skipped by the reference, utils.py:256)."""
+    from sklearn.metrics import average_precision_score
+    from vision_transformer_cam_b200 import ops
+    g = torch.Generator().manual_seed(91)
+    B, C = 64, 20
+    y = (torch.rand((B, C), generator=g) < 0.15).float()
+    s = torch.rand((B, C), generator=g)
+    s[:, ::3] = (s[:, ::3] * 4).round() / 4          # ties
+    y[5] = 0
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    ap = ops.average_precision(y.to(dev), s.to(dev), acc).cpu()
+    want = [average_precision_score(y[i].numpy(), s[i].numpy()) if y[i].sum() > 0 else -1.0 for i in range(B)]
+    assert float((ap - torch.tensor(want, dtype=torch.float64)).abs().max()) < 1e-12
+    valid = [w for w in want if w >= 0]
+    assert abs(float(acc[0]) - sum(valid)) < 1e-9 and int(acc[1]) == len(valid)
+
+
+def test_patch_similarity_reproduces_the_reference_normalize_quirk(dev):
+    """predict.py:194-197: F.normalize(x) on [1,N,D] uses dim=1 (across tokens); sim = that . that^T."""
+    from vision_transformer_cam_b200 import ops
+    x = _rand((2, 197, 768), 92, dev)
+    sim = ops.patch_similarity(x)
+    for b in range(2):
+        f = F.normalize(x[b:b + 1]).squeeze(0)
+        ref = f.mm(f.t())
+        assert float((sim[b] - ref).abs().max()) < 1e-5 * float(ref.abs().max())

@@ -35,7 +35,7 @@ D.reduce_counters(c)
 assert int(c) == world * (world + 1) // 2
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\n" % rank); sys.stdout.flush()
 '''
 
 

@@ -70,12 +70,16 @@ SIGNATURES = {
     "vtc_model_pack_weights": (C.c_int, [_P, C.POINTER(Weights), _P, _Z, _P]),
     "vtc_workspace_bytes": (_Z, [_P, _I, C.POINTER(Outputs)]),
     "vtc_forward": (C.c_int, [_P, _P, _I, C.POINTER(Outputs), C.POINTER(Forcing), _P, _Z, _U, _P]),
+    "vtc_forward_u8": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, C.POINTER(Outputs), C.POINTER(Forcing), _P, _Z, _U, _P]),
     "vtc_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vtc_model_set_precision": (C.c_int, [_P, _I]),
     "vtc_gemm_split": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vtc_split_bf16": (C.c_int, [_P, _P, _Z, _Z, _P]),
     "vtc_patchify_split": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "vtc_layernorm_split": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "vtc_patchify_u8": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _I, _I, _I, _I, _P]),
+    "vtc_average_precision": (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
+    "vtc_patch_similarity": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "vtc_cast_bf16": (C.c_int, [_P, _P, _Z, _P]),
     "vtc_patchify": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "vtc_cls_token_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -8,11 +8,16 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 
 from . import ops
 from .vit_model import CamForward
+
+
+def patch_similarity(tokens: torch.Tensor) -> torch.Tensor:
+    """predict.py:191-199 (viz): `F.normalize(x).squeeze(0) @ ....t()` for block outputs x [B,N,D]; F.normalize's default
+    dim=1 normalises every feature column across the tokens (reproduced as is).  -> [B,N,N]."""
+    return ops.patch_similarity(tokens.float().contiguous())
 
 
 # ---- attention rollout (predict.py:189-247) --------------------------------------------------------------------
@@ -113,20 +118,14 @@ class ConfusionMatrix:
             ["{:.1f}".format(i) for i in (iu * 100).tolist()], iu.nanmean().item() * 100)
 
 
-def average_precision(y_true: np.ndarray, y_score: np.ndarray) -> float:
-    """sklearn.metrics.average_precision_score for one binary row (called per image by utils.py:258): host-side, 20 values."""
-    y_true = np.asarray(y_true, dtype=np.float64)
-    y_score = np.asarray(y_score, dtype=np.float64)
-    order = np.argsort(-y_score, kind="mergesort")
-    y_true, y_score = y_true[order], y_score[order]
-    idx = np.r_[np.where(np.diff(y_score))[0], y_true.size - 1]
-    tps = np.cumsum(y_true)[idx]
-    precision = tps / (1.0 + idx)
-    recall = tps / tps[-1]
-    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+def average_precision(labels: torch.Tensor, scores: torch.Tensor, acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sklearn.metrics.average_precision_score per image (what utils.py:258 calls on the host), computed on the GPU:
+    labels / scores [B,C] -> ap [B] fp64, -1 for images without a positive label.  `acc` (fp64 [2] on the device)
+    accumulates (sum of APs, number of scored images) without any device->host traffic."""
+    return ops.average_precision(labels.float().contiguous(), scores.float().contiguous(), acc)
 
 
 def compute_mAP(labels: torch.Tensor, outputs: torch.Tensor) -> List[float]:
     """utils.py:248-262: per-image AP over the class scores, for images with at least one positive label."""
-    y_true, y_pred = labels.detach().cpu().numpy(), outputs.detach().cpu().numpy()
-    return [average_precision(y_true[i], y_pred[i]) for i in range(y_true.shape[0]) if y_true[i].sum() > 0]
+    ap = average_precision(labels.to(outputs.device), outputs)
+    return [a for a in ap.tolist() if a >= 0.0]

@@ -121,6 +121,72 @@ int patchify(const float* x, void* patches, int batch, int in_c, int img, int pa
     return VTC_OK;
 }
 
+// ---- patchify from decoded uint8 images -----------------------------------------------
+// The reference feeds PIL images through ToTensor (u8 / 255) and Normalize ((x - mean) / std) on the host
+// (predict.py:72-75, validate.py:80-84) and ships fp32 NCHW to the GPU.  Here the decoded u8 HWC pixels are shipped (4x
+// fewer bytes over PCIe and out of HBM) and normalised in the im2col pass, with the same two IEEE fp32 operations, so the
+// bf16 patch matrix is bit-identical to patchify(Normalize(ToTensor(img))).
+struct NormParams {
+    float mean[3];
+    float std[3];
+};
+
+template <bool SPLIT>
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int S, int p, size_t total8, NormParams nm) {
+    const int g = S / p;
+    const int kdim = 3 * p * p;
+    const int xg_per_row = S / 8;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8; i += stride) {
+        // i indexes 8 consecutive pixels (24 bytes, 8-byte aligned) of image row y
+        const int xg = static_cast<int>(i % xg_per_row);
+        size_t r = i / xg_per_row;
+        const int y = static_cast<int>(r % S);
+        const size_t b = r / S;
+        const uint2* src = reinterpret_cast<const uint2*>(x + i * 24);
+        const uint2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        const uint32_t w[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+        const int x0 = xg * 8;
+        const int py = y / p, kh = y - py * p;
+        const int px = x0 / p, kw = x0 - px * p;
+        const size_t row = (b * g + py) * g + px;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int byte = q * 3 + c;
+                const uint32_t u = (w[byte >> 2] >> ((byte & 3) * 8)) & 0xffu;
+                v[q] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), nm.mean[c]), nm.std[c]);
+            }
+            uint4 hi, lo;
+            split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+            __nv_bfloat16* dst = out + row * kdim * (SPLIT ? 2 : 1) + (c * p + kh) * p + kw;
+            st_u4(dst, hi);
+            if (SPLIT) st_u4(dst + kdim, lo);
+        }
+    }
+}
+
+int patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, cudaStream_t stream, int split) {
+    VTC_REQUIRE(x && mean && std && patches, VTC_ERR_ARG, "patchify_u8: null pointer");
+    VTC_REQUIRE(batch > 0 && img > 0 && patch > 0, VTC_ERR_SHAPE, "patchify_u8: bad shape");
+    VTC_REQUIRE(img % patch == 0 && patch % 8 == 0, VTC_ERR_SHAPE, "patchify_u8: img %d / patch %d unsupported (patch %% 8 == 0 required)", img, patch);
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0, VTC_ERR_ARG, "patchify_u8: image pointer must be 8-byte aligned");
+    for (int c = 0; c < 3; ++c) VTC_REQUIRE(std[c] != 0.f, VTC_ERR_ARG, "patchify_u8: std[%d] is zero", c);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    NormParams nm{{mean[0], mean[1], mean[2]}, {std[0], std[1], std[2]}};
+    const size_t total8 = static_cast<size_t>(batch) * img * img / 8;
+    size_t blocks = (total8 + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    if (split) patchify_u8_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), img, patch, total8, nm);
+    else patchify_u8_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), img, patch, total8, nm);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 // ---- CLS token rows ---------------------------------------------------------------------------------
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ tokens,
                                 int n_tokens, int dim) {
@@ -232,6 +298,10 @@ int vtc_patchify(const float* x, void* patches, int32_t batch, int32_t in_c, int
 }
 int vtc_patchify_split(const float* x, void* patches, int32_t batch, int32_t in_c, int32_t img, int32_t patch, void* stream) {
     return vtc::patchify(x, patches, batch, in_c, img, patch, static_cast<cudaStream_t>(stream), 1);
+}
+int vtc_patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int32_t batch, int32_t img, int32_t patch,
+                     int32_t split, void* stream) {
+    return vtc::patchify_u8(x, mean, std, patches, batch, img, patch, static_cast<cudaStream_t>(stream), split);
 }
 int vtc_layernorm_split(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t dim, float eps,
                         void* stream) {

@@ -92,9 +92,18 @@ struct Span {
         if ((rc = (call)) != VTC_OK) return rc;    \
     } while (0)
 
-static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, const vtc_forcing* f, void* workspace, size_t ws_bytes,
+// Image input of the forward: normalised fp32 NCHW (the reference's tensor) or decoded uint8 HWC + Normalize constants.
+struct ImageInput {
+    const float* f32 = nullptr;
+    const uint8_t* u8 = nullptr;
+    const float* mean = nullptr;   // host, 3 floats
+    const float* std = nullptr;    // host, 3 floats
+};
+
+static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs* o, const vtc_forcing* f, void* workspace, size_t ws_bytes,
                    uint32_t flags, cudaStream_t st) {
-    VTC_REQUIRE(m && x && o && workspace, VTC_ERR_ARG, "forward: null pointer");
+    VTC_REQUIRE(m && (in.f32 || (in.u8 && in.mean && in.std)) && o && workspace, VTC_ERR_ARG, "forward: null pointer");
+    VTC_REQUIRE(!in.u8 || m->cfg.in_c == 3, VTC_ERR_SHAPE, "forward: uint8 HWC input needs in_c == 3");
     VTC_REQUIRE(m->packed, VTC_ERR_ARG, "forward: vtc_model_pack_weights has not been called");
     VTC_REQUIRE(B > 0, VTC_ERR_SHAPE, "forward: batch %d", B);
     VTC_REQUIRE(o->logits && o->hwp_logits && o->hwp_tokens, VTC_ERR_ARG, "forward: logits / hwp_logits / hwp_tokens are required outputs");
@@ -120,7 +129,8 @@ static int forward(vtc_model* m, const float* x, int B, const vtc_outputs* o, co
 
     // ---- patch embedding + token assembly (vit_model.py:306-314)
     float* t_cur = ws.tok;
-    VTC_STEP(VTC_PROF_PATCHIFY, patchify(x, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st, sp));
+    if (in.u8) VTC_STEP(VTC_PROF_PATCHIFY, patchify_u8(in.u8, in.mean, in.std, ws.patches, B, m->cfg.img_size, m->cfg.patch_size, st, sp));
+    else VTC_STEP(VTC_PROF_PATCHIFY, patchify(in.f32, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st, sp));
     VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));
     VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st, sp));
     VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * L, st));
@@ -298,7 +308,18 @@ size_t vtc_workspace_bytes(const vtc_model* m, int32_t batch, const vtc_outputs*
 
 int vtc_forward(vtc_model* m, const float* x, int32_t batch, const vtc_outputs* outs, const vtc_forcing* forcing, void* workspace,
                 size_t workspace_bytes, uint32_t flags, void* stream) {
-    return vtc::forward(m, x, batch, outs, forcing, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
+    vtc::ImageInput in;
+    in.f32 = x;
+    return vtc::forward(m, in, batch, outs, forcing, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
+}
+
+int vtc_forward_u8(vtc_model* m, const uint8_t* x, const float* mean, const float* std, int32_t batch, const vtc_outputs* outs,
+                   const vtc_forcing* forcing, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+    vtc::ImageInput in;
+    in.u8 = x;
+    in.mean = mean;
+    in.std = std;
+    return vtc::forward(m, in, batch, outs, forcing, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
 }
 
 int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,

@@ -13,6 +13,9 @@ int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
 // fp32 [rows,cols] -> (hi | lo) bf16 halves [rows, 2*cols], x ~= hi + lo (16 mantissa bits)
 int split_bf16(const float* src, void* dst, size_t rows, size_t cols, cudaStream_t stream);
 int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream, int split = 0);
+// decoded u8 HWC images [B,S,S,3] -> normalised bf16 patch matrix; mean / std are HOST arrays of 3 floats
+int patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, cudaStream_t stream,
+                int split = 0);
 int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int batch, int n_tokens, int dim, cudaStream_t stream);
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream,
                    int split = 0, int reverse = 0);

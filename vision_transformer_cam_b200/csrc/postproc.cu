@@ -485,9 +485,108 @@ int confmat_update(const uint8_t* gt, const uint8_t* pred, size_t count, int n, 
     return VTC_OK;
 }
 
+// ---- per-image average precision (utils.py:248-262 -> sklearn.metrics.average_precision_score) --------------------------
+// AP = sum over the distinct score thresholds t (descending) of (R(t) - R(prev)) * P(t), with P = tp / #(score >= t) and
+// R = tp / #positives.  C is tiny (20): one thread per image, O(C^2), fp64 like the numpy path.  Images without a positive
+// label are skipped (utils.py:256); acc[0] += AP, acc[1] += 1 for the others.
+__global__ void average_precision_kernel(const float* __restrict__ labels, const float* __restrict__ scores, int B, int C,
+                                         double* __restrict__ ap, double* __restrict__ acc) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* y = labels + static_cast<size_t>(b) * C;
+    const float* sc = scores + static_cast<size_t>(b) * C;
+    double npos = 0.0;
+    for (int j = 0; j < C; ++j) npos += (y[j] != 0.f) ? 1.0 : 0.0;
+    if (npos == 0.0) {
+        if (ap) ap[b] = -1.0;
+        return;
+    }
+    double total = 0.0;
+    for (int i = 0; i < C; ++i) {
+        const float t = sc[i];
+        bool first = true;                      // one term per distinct threshold
+        for (int j = 0; j < i; ++j) first = first && (sc[j] != t);
+        if (!first) continue;
+        double tp = 0.0, tp_above = 0.0, cnt = 0.0;
+        for (int j = 0; j < C; ++j) {
+            const double pos = (y[j] != 0.f) ? 1.0 : 0.0;
+            if (sc[j] >= t) { tp += pos; cnt += 1.0; }
+            if (sc[j] > t) tp_above += pos;
+        }
+        total += ((tp - tp_above) / npos) * (tp / cnt);
+    }
+    if (ap) ap[b] = total;
+    if (acc) {
+        atomicAdd(&acc[0], total);
+        atomicAdd(&acc[1], 1.0);
+    }
+}
+
+int average_precision(const float* labels, const float* scores, int batch, int classes, double* ap, double* acc, cudaStream_t stream) {
+    VTC_REQUIRE(labels && scores && (ap || acc), VTC_ERR_ARG, "average_precision: null pointer");
+    VTC_REQUIRE(batch > 0 && classes > 0, VTC_ERR_SHAPE, "average_precision: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    average_precision_kernel<<<cdiv(batch, 128), 128, 0, stream>>>(labels, scores, batch, classes, ap, acc);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// ---- patch-token similarity matrix of predict.py:191-199 ------------------------------------------------------------------
+// The reference calls F.normalize on a [1,N,D] tensor with the default dim=1, i.e. every FEATURE column is L2-normalised
+// across the N tokens (not every token across its features), then takes the N x N gram matrix.  Reproduced as is
+// (faithful quirk): sim[b,i,j] = sum_d x[b,i,d] x[b,j,d] / max(||x[b,:,d]||, 1e-12)^2.
+__global__ void feature_norm_kernel(const float* __restrict__ x, float* __restrict__ inv_sq, int N, int D) {
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const float* src = x + static_cast<size_t>(b) * N * D + d;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) { const float v = src[static_cast<size_t>(n) * D]; s = fmaf(v, v, s); }
+    const float nrm = fmaxf(sqrtf(s), 1e-12f);
+    inv_sq[static_cast<size_t>(b) * D + d] = 1.0f / (nrm * nrm);
+}
+// grid (N, B), block 256: row i of image b against every row j; x_i * inv_sq staged in smem
+__global__ void patch_similarity_kernel(const float* __restrict__ x, const float* __restrict__ inv_sq, float* __restrict__ sim, int N, int D) {
+    extern __shared__ float xi[];     // [D]
+    const int i = blockIdx.x, b = blockIdx.y;
+    const float* xb = x + static_cast<size_t>(b) * N * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) xi[d] = xb[static_cast<size_t>(i) * D + d] * inv_sq[static_cast<size_t>(b) * D + d];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < N; j += nwarps) {
+        const float* xj = xb + static_cast<size_t>(j) * D;
+        float s = 0.f;
+        for (int d = lane * 4; d < D; d += 128) {
+            const float4 v = ldg_f4(xj + d);
+            s = fmaf(v.x, xi[d], fmaf(v.y, xi[d + 1], fmaf(v.z, xi[d + 2], fmaf(v.w, xi[d + 3], s))));
+        }
+        s = warp_sum(s);
+        if (lane == 0) sim[(static_cast<size_t>(b) * N + i) * N + j] = s;
+    }
+}
+
+int patch_similarity(const float* tokens, float* scratch, float* sim, int batch, int n_tokens, int dim, cudaStream_t stream) {
+    VTC_REQUIRE(tokens && scratch && sim, VTC_ERR_ARG, "patch_similarity: null pointer");
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && n_tokens > 0 && dim > 0 && dim % 128 == 0 && dim * 4 <= 48 * 1024, VTC_ERR_SHAPE, "patch_similarity: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    feature_norm_kernel<<<dim3(cdiv(dim, 128), batch), 128, 0, stream>>>(tokens, scratch, n_tokens, dim);
+    VTC_CHECK_LAUNCH();
+    patch_similarity_kernel<<<dim3(n_tokens, batch), 256, sizeof(float) * dim, stream>>>(tokens, scratch, sim, n_tokens, dim);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 }  // namespace vtc
 
 extern "C" {
+int vtc_average_precision(const float* labels, const float* scores, int32_t batch, int32_t classes, double* ap, double* acc, void* stream) {
+    return vtc::average_precision(labels, scores, batch, classes, ap, acc, static_cast<cudaStream_t>(stream));
+}
+int vtc_patch_similarity(const float* tokens, float* scratch, float* sim, int32_t batch, int32_t n_tokens, int32_t dim, void* stream) {
+    return vtc::patch_similarity(tokens, scratch, sim, batch, n_tokens, dim, static_cast<cudaStream_t>(stream));
+}
 int vtc_rollout(const float* attn_mean, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream) {
     return vtc::rollout(attn_mean, row, layers, batch, n_tokens, static_cast<cudaStream_t>(stream));
 }

@@ -241,3 +241,33 @@ def confmat_update(mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor) -> t
     _lib.call("vtc_confmat_update", _ptr(gt, torch.uint8, "gt"), _ptr(pred, torch.uint8, "pred"), gt.numel(), n,
               _ptr(mat, torch.int64, "mat"), _stream())
     return mat
+
+
+def average_precision(labels: torch.Tensor, scores: torch.Tensor, acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-image sklearn-style AP on the device: labels / scores [B,C] fp32 -> ap [B] fp64 (-1 = no positive label);
+    `acc` (fp64 [2], optional) accumulates (sum of APs, number of scored images)."""
+    B, C = scores.shape
+    ap = torch.empty((B,), dtype=torch.float64, device=scores.device)
+    _lib.call("vtc_average_precision", _ptr(labels, torch.float32, "labels"), _ptr(scores, torch.float32, "scores"), B, C, _ptr(ap),
+              _ptr(acc, torch.float64, "acc"), _stream())
+    return ap
+
+
+def patch_similarity(tokens: torch.Tensor) -> torch.Tensor:
+    """predict.py:191-199: gram matrix of F.normalize(tokens) (default dim=1: per feature, across tokens).  [B,N,D] -> [B,N,N]."""
+    B, N, D = tokens.shape
+    scratch = torch.empty((B, D), dtype=torch.float32, device=tokens.device)
+    sim = torch.empty((B, N, N), dtype=torch.float32, device=tokens.device)
+    _lib.call("vtc_patch_similarity", _ptr(tokens, torch.float32, "tokens"), _ptr(scratch), _ptr(sim), B, N, D, _stream())
+    return sim
+
+
+def patchify_u8(x: torch.Tensor, patch: int, mean, std, split: bool = False) -> torch.Tensor:
+    """uint8 [B,S,S,3] -> normalised bf16 patch matrix [B*g*g, 3*patch*patch] (x 2 when split)."""
+    import ctypes
+    B, S, S2, Cin = x.shape
+    assert S == S2 and Cin == 3 and x.dtype == torch.uint8
+    g = S // patch
+    out = torch.empty((B * g * g, 3 * patch * patch * (2 if split else 1)), dtype=torch.bfloat16, device=x.device)
+    _lib.call("vtc_patchify_u8", _ptr(x), (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std), _ptr(out), B, S, patch, int(split), _stream())
+    return out

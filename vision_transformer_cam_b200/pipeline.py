@@ -110,9 +110,8 @@ class Validator:
         self.model = model
         self.num_classes = num_classes
         self.confmat = CAM.ConfusionMatrix(num_classes, device=device)
-        self.ap_sum = 0.0
-        self.ap_count = 0
         self.device = torch.device(device)
+        self.ap_acc = torch.zeros(2, dtype=torch.float64, device=self.device)     # (sum of APs, scored images), on the GPU
 
     @torch.no_grad()
     def step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, seg_labels: Optional[torch.Tensor] = None,
@@ -124,15 +123,13 @@ class Validator:
         seg = CAM.hwp_pseudo_seg(o, self.model.head1.weight.data, out_hw)
         if seg_labels is not None:
             self.confmat.update(seg_labels.to(self.device), seg)
-        if target is not None:
-            aps = CAM.compute_mAP(target, torch.sigmoid(o.hwp_logits))
-            self.ap_sum += float(sum(aps))
-            self.ap_count += len(aps)
+        if target is not None:      # per-image AP on the device (validate.py:266-273 does it on the host through sklearn)
+            CAM.average_precision(target.to(self.device), torch.sigmoid(o.hwp_logits), self.ap_acc)
         return seg
 
     def finalize(self) -> Dict[str, object]:
         """All-reduce the counters (NCCL / gloo) and compute global accuracy, per-class IoU, mIoU and mAP."""
-        stats = torch.tensor([self.ap_sum, float(self.ap_count)], dtype=torch.float64, device=self.confmat.mat.device)
+        stats = self.ap_acc.clone()
         D.reduce_counters(self.confmat.mat)
         D.reduce_counters(stats)
         acc_global, acc, iu = self.confmat.compute()

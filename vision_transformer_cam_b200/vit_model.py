@@ -282,7 +282,8 @@ class _Engine:
         self._keep = (layers, w)
 
     def run(self, model: "VisionTransformer", x: torch.Tensor, tokens_layers: int, attn_layers: int, attn_mean: bool, bg: bool,
-            cls_map: bool, mask_norm: str, forced_bg: Optional[Dict[int, torch.Tensor]], forced_topk: Optional[torch.Tensor]) -> CamForward:
+            cls_map: bool, mask_norm: str, forced_bg: Optional[Dict[int, torch.Tensor]], forced_topk: Optional[torch.Tensor],
+            norm: Optional[Tuple[Tuple[float, float, float], Tuple[float, float, float]]] = None) -> CamForward:
         dev = x.device
         cfg = self.cfg
         B = x.shape[0]
@@ -331,9 +332,15 @@ class _Engine:
             flags = _lib.FWD_MASK_NORM_IMAGE if mask_norm == "image" else 0
             if self.precision == "fp32":
                 flags |= _lib.FWD_FP32_SPLIT
-            _lib.check(self.lib.vtc_forward(self.handle, x.data_ptr(), B, ctypes.byref(o),
-                                            ctypes.byref(forcing) if forcing is not None else None, self.ws.data_ptr(),
-                                            self.ws.numel(), flags, torch.cuda.current_stream(dev).cuda_stream), "vtc_forward")
+            fptr = ctypes.byref(forcing) if forcing is not None else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if norm is None:
+                _lib.check(self.lib.vtc_forward(self.handle, x.data_ptr(), B, ctypes.byref(o), fptr, self.ws.data_ptr(),
+                                                self.ws.numel(), flags, stream), "vtc_forward")
+            else:
+                mean, std = (ctypes.c_float * 3)(*norm[0]), (ctypes.c_float * 3)(*norm[1])
+                _lib.check(self.lib.vtc_forward_u8(self.handle, x.data_ptr(), mean, std, B, ctypes.byref(o), fptr, self.ws.data_ptr(),
+                                                   self.ws.numel(), flags, stream), "vtc_forward_u8")
             del keep
         return out
 
@@ -431,6 +438,24 @@ class VisionTransformer(nn.Module):
         if self._engine is None:
             self._engine = _Engine(self)
         return self._engine.run(self, x, tokens_layers, attn_layers, attn_mean, bg, cls_map, mask_norm, forced_bg, forced_topk)
+
+    @torch.no_grad()
+    def forward_cam_u8(self, x: torch.Tensor, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), **kw) -> CamForward:
+        """`forward_cam` fed with decoded images: x uint8 [B,S,S,3] (HWC, what PIL / cv2 decode to) on the GPU.  ToTensor
+        (/255) and Normalize(mean, std) of the reference's transforms (predict.py:72-75, validate.py:80-84) run inside the
+        patch-matrix kernel with the same fp32 operations, so the result equals forward_cam(Normalize(ToTensor(x))) bit for
+        bit while moving 4x fewer input bytes."""
+        if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[-1] != 3:
+            raise ValueError(f"forward_cam_u8 expects uint8 [B,S,S,3], got {x.dtype} {tuple(x.shape)}")
+        isz = self.patch_embed.img_size
+        assert x.shape[1] == isz[0] and x.shape[2] == isz[1], f"Input image size ({x.shape[1]}*{x.shape[2]}) doesn't match model ({isz[0]}*{isz[1]})."
+        _require_cuda(x, "VisionTransformer")
+        kw.setdefault("tokens_layers", 1)
+        if self._engine is None:
+            self._engine = _Engine(self)
+        return self._engine.run(self, x.detach().contiguous(), kw.pop("tokens_layers"), kw.pop("attn_layers", 0), kw.pop("attn_mean", False),
+                                kw.pop("bg", False), kw.pop("cls_map", False), kw.pop("mask_norm", "batch"), kw.pop("forced_bg", None),
+                                kw.pop("forced_topk", None), norm=(tuple(mean), tuple(std)))
 
     def kernel_profile(self, enable: Optional[bool] = None):
         """enable/disable CUDA-event timing of every kernel of the fused forward, or (no argument) read the accumulated
