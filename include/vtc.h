@@ -202,6 +202,25 @@ VTC_API int vtc_layernorm_split(const float* x, const float* gamma, const float*
 VTC_API int vtc_patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int32_t batch, int32_t img,
                     int32_t patch, int32_t split, void* stream);
 
+/* ---- LayerNorm fused into the GEMMs either side of it (what vtc_forward runs in bf16 mode) ---------------------------
+ * The pre-norm block computes x + f(LN(x)) twice (vit_model.py:189-198).  Instead of a LayerNorm kernel per call, the GEMM
+ * that updates the residual stream also emits what the next LayerNorm needs, and the GEMM that consumes LN(x) applies the
+ * normalisation in its epilogue:
+ *   LN(t).W^T + b = rstd (bf16(t).W'^T - mean g) + c,  W' = gamma * W,  g[n] = sum_k W'[n,k],  c[n] = b[n] + sum_k beta[k] W[n,k].
+ * Row statistics travel as partial (sum, sum of squares) pairs per 128-column slice: stats [M, D/128, 2] fp32.
+ *
+ * vtc_gemm_resid_ln: out = residual + A.W^T + bias (fp32, out may alias residual), out_bf16 = bf16(out), stats of out.
+ * vtc_gemm_lnfold:   out (bf16) = [GELU](rstd (A.W'^T - mean g) + c) with mean / rstd from `stats` (K = D columns), eps = LN eps.
+ * vtc_residual_prep: x fp32 [rows,D] -> bf16 copy + stats (for a residual stream that did not come out of vtc_gemm_resid_ln).
+ * vtc_fold_ln:       W fp32 [Nout,K], gamma / beta [K], bias [Nout] -> W' bf16 [Nout,K], g [Nout], c [Nout]. */
+VTC_API int vtc_gemm_resid_ln(const void* A, const void* W, const float* bias, const float* residual, float* out, void* out_bf16,
+                      float* stats, int32_t M, int32_t Nout, int32_t K, void* stream);
+VTC_API int vtc_gemm_lnfold(const void* A, const void* W, const float* c, const float* g, const float* stats, float eps, void* out,
+                    int32_t M, int32_t Nout, int32_t K, int32_t gelu, void* stream);
+VTC_API int vtc_residual_prep(const float* x, void* xb, float* stats, int32_t rows, int32_t dim, void* stream);
+VTC_API int vtc_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* g, float* c,
+                int32_t Nout, int32_t K, void* stream);
+
 /* fp32 -> bf16 (weight packing, also used by tests) */
 VTC_API int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 /* NCHW fp32 image -> bf16 patch matrix [B*P, in_c*p*p] (k = c*p*p + kh*p + kw), the im2col of the k=s=p conv

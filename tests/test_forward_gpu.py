@@ -250,3 +250,33 @@ def test_uint8_image_ingest_equals_fp32_forward(env):
     assert torch.equal(a.logits, b.logits) and torch.equal(a.tokens, b.tokens) and torch.equal(a.bg, b.bg)
     with pytest.raises(ValueError):
         model.forward_cam_u8(x.to(env["dev"]))
+
+
+LN_FUSED_WORKER = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import vision_transformer_cam_b200 as V
+from oracle import vit_forward as VF
+gold = np.load(os.path.join(sys.argv[1], "tests", "golden", "default_b2.npz"))
+torch.manual_seed(0)
+model = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).to("cuda:0").eval()
+o = model.forward_cam(VF.make_images(0, 2).to("cuda:0"), tokens_layers=12)
+ref = torch.from_numpy(gold["logits"]).double()
+e = float((o.logits.double().cpu() - ref).abs().max() / ref.abs().max())
+et = float((o.tokens[:, :, 0, :].double().cpu() - torch.from_numpy(gold["x_cls"]).double()).abs().max() / np.abs(gold["x_cls"]).max())
+print("LNFUSED logits %.3e tokens %.3e" % (e, et))
+assert e <= 1e-2 and et <= 1e-2
+'''
+
+
+def test_ln_fused_forward_matches_reference_golden(tmp_path):
+    """VTC_LN_FUSION=1: the forward without LayerNorm kernels (LayerNorm folded into the GEMMs, gemm.cu) meets the same bf16
+    bar against the reference golden.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = tmp_path / "w.py"
+    script.write_text(LN_FUSED_WORKER)
+    r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600, env={**os.environ, "VTC_LN_FUSION": "1"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "LNFUSED" in r.stdout

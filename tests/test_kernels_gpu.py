@@ -461,3 +461,46 @@ def test_patch_similarity_reproduces_the_reference_normalize_quirk(dev):
         f = F.normalize(x[b:b + 1]).squeeze(0)
         ref = f.mm(f.t())
         assert float((sim[b] - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+
+
+# ------------------------------------------------------------------------------ LayerNorm fused into the GEMMs
+@pytest.mark.parametrize("M", [300, 1000])
+def test_layernorm_fused_gemms(dev, M):
+    """x1 = x + a.Wp^T + bp (residual GEMM that also emits bf16(x1) and the row statistics), then
+    gelu(LN(x1).W1^T + b1) evaluated on bf16(x1) with the normalisation folded into the epilogue -- against fp64 torch."""
+    from vision_transformer_cam_b200 import ops
+    D, HID = 768, 3072
+    x = _rand((M, D), 100, dev, 1.5) + 0.3
+    a = _rand((M, D), 101, dev).bfloat16()
+    wp = _rand((D, D), 102, dev, 0.03).bfloat16()
+    bp = _rand((D,), 103, dev, 0.1)
+    x1_ref = x.double() + a.double() @ wp.double().T + bp.double()
+    x1, x1b, stats = ops.gemm_resid_ln(a, wp, bp, x)
+    assert relerr(x1, x1_ref) < 1e-5
+    assert torch.equal(x1b, x1.bfloat16())
+    s = stats.double().sum(1)
+    assert relerr(s[:, 0], x1.double().sum(1)) < 1e-5 and relerr(s[:, 1], (x1.double() ** 2).sum(1)) < 1e-5
+    # in place (out aliases residual) gives the same bits
+    x_copy = x.clone()
+    y1, y1b, st2 = ops.gemm_resid_ln(a, wp, bp, x_copy, out=x_copy)
+    assert torch.equal(y1, x1) and torch.equal(y1b, x1b) and torch.equal(st2, stats)
+    # residual_prep produces the same side outputs from an existing stream
+    pb, pst = ops.residual_prep(x1)
+    assert torch.equal(pb, x1b) and relerr(pst.double().sum(1), s) < 1e-6
+    # folded LayerNorm + GEMM (+GELU)
+    w1 = _rand((HID, D), 104, dev, 0.03)
+    b1 = _rand((HID,), 105, dev, 0.1)
+    gamma, beta = 1.0 + _rand((D,), 106, dev, 0.2), _rand((D,), 107, dev, 0.2)
+    wf, g, c = ops.fold_ln(w1, gamma, beta, b1)
+    assert torch.equal(wf, (w1 * gamma).bfloat16()) and relerr(g, wf.double().sum(1)) < 1e-5
+    assert relerr(c, b1.double() + w1.double() @ beta.double()) < 1e-5
+    ln = F.layer_norm(x1.double(), (D,), gamma.double(), beta.double(), 1e-6)
+    for gelu in (False, True):
+        ref = ln @ w1.double().T + b1.double()
+        ref = F.gelu(ref) if gelu else ref
+        out = ops.gemm_lnfold(x1b, wf, c, g, stats, 1e-6, gelu=gelu)
+        # the unfused path for scale: LayerNorm kernel -> bf16 GEMM
+        base = ops.gemm_bf16(ops.layernorm_bf16(x1, gamma, beta, 1e-6), w1.bfloat16(), b1, 1 if gelu else 0)
+        e, e0 = relerr(out.float(), ref), relerr(base.float(), ref)
+        print(f"LN-folded GEMM gelu={gelu}: relerr {e:.2e} (separate LayerNorm kernel: {e0:.2e})")
+        assert e < 8e-3 and e < 2.0 * e0 + 1e-3

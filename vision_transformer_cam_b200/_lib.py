@@ -80,6 +80,10 @@ SIGNATURES = {
     "vtc_patchify_u8": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _I, _I, _I, _I, _P]),
     "vtc_average_precision": (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "vtc_patch_similarity": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "vtc_gemm_resid_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "vtc_gemm_lnfold": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P]),
+    "vtc_residual_prep": (C.c_int, [_P, _P, _P, _I, _I, _P]),
+    "vtc_fold_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "vtc_cast_bf16": (C.c_int, [_P, _P, _Z, _P]),
     "vtc_patchify": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "vtc_cls_token_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -284,9 +284,95 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* 
     return VTC_OK;
 }
 
+// ---- LayerNorm fusion helpers (bf16 mode, see gemm.cu) -------------------------------------------------------------------
+// residual_prep: what the EPI_RESID_LN epilogue leaves behind, for a residual stream that did not come out of that epilogue
+// (the patch-embedding output feeding block 0): bf16 copy + per-row partial (sum, sum of squares) of every 128-column slice.
+template <int NV>
+__global__ void __launch_bounds__(256) residual_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats,
+                                                            int rows) {
+    constexpr int D = NV * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* src = x + static_cast<size_t>(row) * D;
+    __nv_bfloat16* dst = xb + static_cast<size_t>(row) * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {          // slice i = columns [128 i, 128 i + 128): one float4 per lane
+        const float4 v = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+        *reinterpret_cast<uint2*>(dst + i * 128 + lane * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        const float s1 = warp_sum((v.x + v.y) + (v.z + v.w));
+        const float s2 = warp_sum(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))));
+        if (lane == 0) *reinterpret_cast<float2*>(stats + (static_cast<size_t>(row) * NV + i) * 2) = make_float2(s1, s2);
+    }
+}
+
+int residual_prep(const float* x, void* xb, float* stats, int rows, int dim, cudaStream_t stream) {
+    VTC_REQUIRE(x && xb && stats, VTC_ERR_ARG, "residual_prep: null pointer");
+    VTC_REQUIRE(rows > 0, VTC_ERR_SHAPE, "residual_prep: rows=%d", rows);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int grid = cdiv(rows, 8);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(xb);
+    switch (dim) {
+        case 256: residual_prep_kernel<2><<<grid, 256, 0, stream>>>(x, out, stats, rows); break;
+        case 512: residual_prep_kernel<4><<<grid, 256, 0, stream>>>(x, out, stats, rows); break;
+        case 768: residual_prep_kernel<6><<<grid, 256, 0, stream>>>(x, out, stats, rows); break;
+        case 1024: residual_prep_kernel<8><<<grid, 256, 0, stream>>>(x, out, stats, rows); break;
+        case 1280: residual_prep_kernel<10><<<grid, 256, 0, stream>>>(x, out, stats, rows); break;
+        default:
+            set_last_error("residual_prep: dim %d unsupported (256/512/768/1024/1280)", dim);
+            return VTC_ERR_SHAPE;
+    }
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// fold_ln: W'[n,:] = bf16(gamma * W[n,:]), g[n] = sum_k W'[n,k] (of the ROUNDED values: rstd (t.W'^T - mean g) is then exactly
+// rstd ((t - mean).W'^T)), c[n] = bias[n] + sum_k beta[k] W[n,k].  One warp per output row.
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wf, float* __restrict__ g,
+                                                      float* __restrict__ c, int N, int K) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    const float* src = W + static_cast<size_t>(n) * K;
+    __nv_bfloat16* dst = Wf + static_cast<size_t>(n) * K;
+    float sg = 0.f, sc = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 w = ldg_f4(src + k), ga = ldg_f4(gamma + k), be = ldg_f4(beta + k);
+        const uint32_t p0 = pack_bf16x2(w.x * ga.x, w.y * ga.y), p1 = pack_bf16x2(w.z * ga.z, w.w * ga.w);
+        *reinterpret_cast<uint2*>(dst + k) = make_uint2(p0, p1);
+        sg += (__uint_as_float(p0 << 16) + __uint_as_float(p0 & 0xffff0000u)) + (__uint_as_float(p1 << 16) + __uint_as_float(p1 & 0xffff0000u));
+        sc = fmaf(w.x, be.x, fmaf(w.y, be.y, fmaf(w.z, be.z, fmaf(w.w, be.w, sc))));
+    }
+    sg = warp_sum(sg);
+    sc = warp_sum(sc);
+    if (lane == 0) {
+        g[n] = sg;
+        c[n] = bias[n] + sc;
+    }
+}
+
+int fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* g, float* c, int N, int K, cudaStream_t stream) {
+    VTC_REQUIRE(W && gamma && beta && bias && Wf && g && c, VTC_ERR_ARG, "fold_ln: null pointer");
+    VTC_REQUIRE(N > 0 && K > 0 && K % 128 == 0, VTC_ERR_SHAPE, "fold_ln: K must be a multiple of 128");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    fold_ln_kernel<<<cdiv(N, 8), 256, 0, stream>>>(W, gamma, beta, bias, static_cast<__nv_bfloat16*>(Wf), g, c, N, K);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 }  // namespace vtc
 
 extern "C" {
+int vtc_residual_prep(const float* x, void* xb, float* stats, int32_t rows, int32_t dim, void* stream) {
+    return vtc::residual_prep(x, xb, stats, rows, dim, static_cast<cudaStream_t>(stream));
+}
+int vtc_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* g, float* c, int32_t N, int32_t K,
+                void* stream) {
+    return vtc::fold_ln(W, gamma, beta, bias, Wf, g, c, N, K, static_cast<cudaStream_t>(stream));
+}
 int vtc_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
     return vtc::cast_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
 }

@@ -234,38 +234,60 @@ namespace gemm2 {
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 5;
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;     // 16 KB: this CTA's half of the W tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int OUT_BUF_BYTES = 128 * 128;       // 128 rows x 128 B staging tile
-constexpr int OFF_OUT = STAGES * STAGE_BYTES;  // [2 halves][2 buffers]
-constexpr int OFF_BAR = OFF_OUT + 4 * OUT_BUF_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(SMEM_BYTES <= 232448, "gemm2 smem budget");
+constexpr int EPI_RESID_LN = 4;                // internal epilogue id (see below); the public ids are VTC_EPI_*
+__host__ __device__ constexpr int stages_of(int) { return 5; }
+__host__ __device__ constexpr int out_bufs_of(int) { return 4; }       // [2 halves][2 buffers]
+__host__ __device__ constexpr int off_out_of(int epi) { return stages_of(epi) * STAGE_BYTES; }
+__host__ __device__ constexpr int off_bar_of(int epi) { return off_out_of(epi) + out_bufs_of(epi) * OUT_BUF_BYTES; }
+__host__ __device__ constexpr int smem_bytes_of(int epi) { return off_bar_of(epi) + 256; }
+static_assert(smem_bytes_of(0) <= 232448 && smem_bytes_of(EPI_RESID_LN) <= 232448, "gemm2 smem budget");
 
 struct Params {
-    const float* bias;
+    const float* bias;     // [N]; LayerNorm-folded GEMMs: c[n] = bias[n] + sum_k beta[k] W[n,k]
     int M, N, K;
     int split;     // see gemm::Params::split; bf16 outputs are then written as (hi | lo) halves [M, 2N]
     int reverse;   // walk the tiles from the last row block to the first (see model.cu: alternating sweep direction)
+    // LayerNorm fusion (bf16 mode).  Row statistics travel as partial (sum, sum of squares) pairs per 128-column slice of
+    // the residual stream: stats[row][slice][2], `nslices` = D / 128.
+    const float* g;        // folded GEMM: g[n] = sum_k W'[n,k] with W' = bf16(gamma * W)
+    float* stats;          // folded GEMM: read; residual epilogue: written
+    int nslices;
+    float eps;
+    __nv_bfloat16* out_bf16;   // residual epilogue: bf16 copy of the new residual stream [M,N]
 };
 }  // namespace gemm2
 
-template <int EPI, bool SPLIT>
+// LayerNorm fusion (bf16 mode): the separate LayerNorm kernel (a full read of the fp32 residual stream + a bf16 write per
+// call, 24 calls per forward) is folded into the GEMMs either side of it.
+//   EPI_RESID_LN (proj, fc2): t_new = residual + A.W^T + bias is formed in registers -- the fp32 residual chunk is fetched by
+//     TMA into the staging tile while the accumulator is still being computed -- and leaves the SM three ways: fp32 t_new
+//     (TMA store), bf16(t_new) (TMA store: the A operand of the next GEMM) and per-row partial sums (sum, sum of squares)
+//     of this CTA's 128 columns.
+//   FOLD (qkv, fc1): LN(t).W^T = rstd (t.W'^T - mean g) + c with W' = gamma * W, g[n] = sum_k W'[n,k],
+//     c[n] = bias[n] + sum_k beta[k] W[n,k]: the GEMM runs on bf16(t) and the epilogue applies the two row scalars.
+template <int EPI, bool SPLIT, bool FOLD>
 __global__ void __launch_bounds__(gemm2::THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmO, const gemm2::Params p) {
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                  const __grid_constant__ CUtensorMap tmH, const gemm2::Params p) {
     using namespace gemm2;
+    constexpr int STAGES = stages_of(EPI);
+    constexpr int OFF_OUT = off_out_of(EPI);
+    constexpr int OFF_BAR = off_bar_of(EPI);
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // used in the leader CTA only
     uint64_t* empty_bar = full_bar + STAGES;                             // per CTA
     uint64_t* tfull_bar = empty_bar + STAGES;                            // per CTA
     uint64_t* tempty_bar = tfull_bar + 2;                                // used in the leader CTA only
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;                                  // [2 halves][2 buffers] residual chunk landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -276,6 +298,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
+        if (EPI == EPI_RESID_LN) tma_prefetch_desc(&tmR);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -286,6 +309,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], 2 * EPI_WARPS);     // epilogue warps of BOTH CTAs
         }
+        for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_ptr, 512);
@@ -358,19 +382,125 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int r_local = quarter * 32 + lane;
         const bool issuer = (quarter == 0) && (lane == 0);
         const uint32_t bar_id = 1 + half;
-        uint8_t* stage_out = smem + OFF_OUT + half * 2 * OUT_BUF_BYTES;
-        constexpr int CHUNK_COLS = (EPI == VTC_EPI_BIAS_RESIDUAL) ? 32 : 64;     // 128-byte rows
+        uint8_t* stage_out = smem + OFF_OUT + half * (out_bufs_of(EPI) / 2) * OUT_BUF_BYTES;
+        constexpr int CHUNK_COLS = (EPI == VTC_EPI_BIAS_RESIDUAL || EPI == EPI_RESID_LN) ? 32 : 64;     // 128-byte rows
         constexpr int NCHUNK = 128 / CHUNK_COLS;
         int as = 0;
         uint32_t aph = 0;
         int buf = 0;
+        uint32_t res_ph[2] = {0, 0};      // EPI_RESID_LN: phases of this half's two residual buffers
         for (int t_ = pair; t_ < num_tiles; t_ += npairs) {
             const int tile = p.reverse ? num_tiles - 1 - t_ : t_;
             const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
             const int n0 = (tile % num_n) * BN;
+            if constexpr (EPI == EPI_RESID_LN) {
+                // Residual chunks 0 and 1 of this tile are fetched while the tensor core is still accumulating.  The staging tiles
+                // are free once the bulk stores issued from them for the previous tile have been read.
+                if (issuer) {
+                    tma_store_wait_read<0>();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        mbar_arrive_expect_tx(&res_bar[half * 2 + c], OUT_BUF_BYTES);
+                        tma_load_2d(stage_out + c * OUT_BUF_BYTES, &tmR, &res_bar[half * 2 + c], n0 + half * 128 + c * 32, m0);
+                    }
+                    // pull the residual of the NEXT tile of this CTA into L2 now: only two chunks fit in shared memory, and an HBM
+                    // round trip per chunk would make this epilogue latency-bound
+                    if (t_ + npairs < num_tiles) {
+                        const int nt = p.reverse ? num_tiles - 1 - (t_ + npairs) : t_ + npairs;
+                        const int nm0 = (nt / num_n) * (2 * BM) + rank * BM, nn0 = (nt % num_n) * BN + half * 128;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) tma_prefetch_2d(&tmR, nn0 + c * 32, nm0);
+                    }
+                }
+            }
+            // row scalars of the folded LayerNorm: mean and rstd from the partial sums of the producer GEMM (fetched while the
+            // tensor core is still accumulating this tile)
+            float ln_rs = 1.f, ln_nrm = 0.f;      // rstd and -rstd * mean
+            if constexpr (FOLD) {
+                const int row = m0 + r_local;
+                if (row < p.M) {
+                    const float2* st2 = reinterpret_cast<const float2*>(p.stats) + static_cast<size_t>(row) * p.nslices;
+                    float a = 0.f, b = 0.f;
+                    for (int i = 0; i < p.nslices; ++i) {
+                        const float2 v = __ldg(st2 + i);
+                        a += v.x;
+                        b += v.y;
+                    }
+                    const float invd = 1.0f / static_cast<float>(p.K);
+                    const float mean = a * invd;
+                    const float var = fmaxf(fmaf(-mean, mean, b * invd), 0.f);
+                    ln_rs = rsqrtf(var + p.eps);
+                    ln_nrm = -ln_rs * mean;
+                }
+            }
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * 128;
+            if constexpr (EPI == EPI_RESID_LN) {
+                const int row = m0 + r_local;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int pr = 0; pr < 2; ++pr) {
+#pragma unroll
+                for (int fb = 0; fb < 2; ++fb) {                   // fb = staging buffer of chunk c (static: hb stays in registers)
+                    const int c = pr * 2 + fb;
+                    const int col0 = half * 128 + c * 32;
+                    uint8_t* frow = stage_out + fb * OUT_BUF_BYTES + r_local * 128;
+                    uint32_t acc[32];
+                    uint32_t hb[16];                              // bf16(t_new) of this chunk
+                    tmem_ld_32x32b_x32(t_row + c * 32, acc);
+                    mbar_wait(&res_bar[half * 2 + fb], res_ph[fb]);
+                    res_ph[fb] ^= 1;
+                    tmem_ld_wait();
+                    if (c == 3) {                                 // the accumulator is in registers: hand the TMEM stage back early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+                    }
+                    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0);
+#pragma unroll
+                    for (int g8 = 0; g8 < 8; ++g8) {
+                        float4* slot = reinterpret_cast<float4*>(frow + ((g8 ^ (r_local & 7)) * 16));
+                        const float4 r4 = *slot;
+                        const float4 b4 = __ldg(bias4 + g8);
+                        float4 v;
+                        v.x = (__uint_as_float(acc[4 * g8 + 0]) + b4.x) + r4.x;
+                        v.y = (__uint_as_float(acc[4 * g8 + 1]) + b4.y) + r4.y;
+                        v.z = (__uint_as_float(acc[4 * g8 + 2]) + b4.z) + r4.z;
+                        v.w = (__uint_as_float(acc[4 * g8 + 3]) + b4.w) + r4.w;
+                        *slot = v;
+                        s1 += (v.x + v.y) + (v.z + v.w);
+                        s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+                        hb[2 * g8] = pack_bf16x2(v.x, v.y);
+                        hb[2 * g8 + 1] = pack_bf16x2(v.z, v.w);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
+                        tma_store_2d(&tmO, stage_out + fb * OUT_BUF_BYTES, n0 + col0, m0);
+                        tma_store_commit();
+                    }
+                    if (row < p.M) {
+                        // bf16(t_new): 64 contiguous bytes per row straight from registers (the fp32 copy goes through the TMA store)
+                        __nv_bfloat16* hdst = p.out_bf16 + static_cast<size_t>(row) * p.N + n0 + col0;
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) st_u4(hdst + 8 * g4, make_uint4(hb[4 * g4], hb[4 * g4 + 1], hb[4 * g4 + 2], hb[4 * g4 + 3]));
+                    }
+                    if (c < 2 && issuer) {
+                        // refill this fp32 buffer with chunk c+2 once its store has been read
+                        tma_store_wait_read<0>();
+                        mbar_arrive_expect_tx(&res_bar[half * 2 + fb], OUT_BUF_BYTES);
+                        tma_load_2d(stage_out + fb * OUT_BUF_BYTES, &tmR, &res_bar[half * 2 + fb], n0 + half * 128 + (c + 2) * 32, m0);
+                    }
+                }
+                }
+                if (row < p.M) {
+                    float* dst = p.stats + (static_cast<size_t>(row) * p.nslices + (n0 >> 7) + half) * 2;
+                    *reinterpret_cast<float2*>(dst) = make_float2(s1, s2);
+                }
+                if (++as == 2) { as = 0; aph ^= 1; }
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
                 const int col0 = half * 128 + c * CHUNK_COLS;
@@ -398,10 +528,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const float4 b4 = __ldg(bias4 + j);
                         const float4 c4 = __ldg(bias4 + 8 + j);
                         float v0, v1, v2, v3, w0, w1, w2, w3;
-                        unpack2(add2(pack2u(r0[4 * j + 0], r0[4 * j + 1]), pack2(b4.x, b4.y)), v0, v1);
-                        unpack2(add2(pack2u(r0[4 * j + 2], r0[4 * j + 3]), pack2(b4.z, b4.w)), v2, v3);
-                        unpack2(add2(pack2u(r1[4 * j + 0], r1[4 * j + 1]), pack2(c4.x, c4.y)), w0, w1);
-                        unpack2(add2(pack2u(r1[4 * j + 2], r1[4 * j + 3]), pack2(c4.z, c4.w)), w2, w3);
+                        if constexpr (FOLD) {
+                            // rstd * acc + (-rstd * mean) * g[n] + c[n]
+                            const float4* g4 = reinterpret_cast<const float4*>(p.g + n0 + col0);
+                            const float4 ga = __ldg(g4 + j), gb = __ldg(g4 + 8 + j);
+                            const uint64_t rs2 = pack2(ln_rs, ln_rs), nm2 = pack2(ln_nrm, ln_nrm);
+                            unpack2(fma2(pack2u(r0[4 * j + 0], r0[4 * j + 1]), rs2, fma2(nm2, pack2(ga.x, ga.y), pack2(b4.x, b4.y))), v0, v1);
+                            unpack2(fma2(pack2u(r0[4 * j + 2], r0[4 * j + 3]), rs2, fma2(nm2, pack2(ga.z, ga.w), pack2(b4.z, b4.w))), v2, v3);
+                            unpack2(fma2(pack2u(r1[4 * j + 0], r1[4 * j + 1]), rs2, fma2(nm2, pack2(gb.x, gb.y), pack2(c4.x, c4.y))), w0, w1);
+                            unpack2(fma2(pack2u(r1[4 * j + 2], r1[4 * j + 3]), rs2, fma2(nm2, pack2(gb.z, gb.w), pack2(c4.z, c4.w))), w2, w3);
+                        } else {
+                            unpack2(add2(pack2u(r0[4 * j + 0], r0[4 * j + 1]), pack2(b4.x, b4.y)), v0, v1);
+                            unpack2(add2(pack2u(r0[4 * j + 2], r0[4 * j + 3]), pack2(b4.z, b4.w)), v2, v3);
+                            unpack2(add2(pack2u(r1[4 * j + 0], r1[4 * j + 1]), pack2(c4.x, c4.y)), w0, w1);
+                            unpack2(add2(pack2u(r1[4 * j + 2], r1[4 * j + 3]), pack2(c4.z, c4.w)), w2, w3);
+                        }
                         if (EPI == VTC_EPI_BIAS_GELU) {
                             if (SPLIT) {      // fp32 mode: exact erf instead of the 4e-7 polynomial
                                 v0 = gelu_erf_exact(v0); v1 = gelu_erf_exact(v1); v2 = gelu_erf_exact(v2); v3 = gelu_erf_exact(v3);
@@ -464,11 +605,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-template <int EPI, bool SPLIT>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const gemm2::Params& p, cudaStream_t stream) {
+template <int EPI, bool SPLIT, bool FOLD = false>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const gemm2::Params& p, cudaStream_t stream,
+                        const CUtensorMap* tmR = nullptr, const CUtensorMap* tmH = nullptr) {
     static bool configured = false;
     if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI, SPLIT, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::smem_bytes_of(EPI)));
         configured = true;
     }
     const int tiles = cdiv(p.M, 2 * gemm2::BM) * (p.N / gemm2::BN);
@@ -477,7 +619,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(gemm2::THREADS);
-    cfg.dynamicSmemBytes = gemm2::SMEM_BYTES;
+    cfg.dynamicSmemBytes = gemm2::smem_bytes_of(EPI);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -487,7 +629,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     note_launch();
-    VTC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<EPI, SPLIT>, tmA, tmB, tmO, p));
+    VTC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<EPI, SPLIT, FOLD>, tmA, tmB, tmO, tmR ? *tmR : tmO, tmH ? *tmH : tmO, p));
     return VTC_OK;
 }
 
@@ -540,7 +682,7 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
         }
     }
     CUtensorMap tmO;
-    gemm2::Params p2{bias, M, N, K, split, reverse};
+    gemm2::Params p2{bias, M, N, K, split, reverse, nullptr, nullptr, 0, 0.f, nullptr};
     if (epilogue == VTC_EPI_BIAS_RESIDUAL) {
         // out = residual + A.W^T + bias, with the add done by the TMA reduction into `out`
         if (out != static_cast<const void*>(residual))
@@ -564,7 +706,60 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
     return split ? launch_gemm2<VTC_EPI_BIAS_GELU, true>(tmA, tmB, tmO, p2, stream) : launch_gemm2<VTC_EPI_BIAS_GELU, false>(tmA, tmB, tmO, p2, stream);
 }
 
+// ---- LayerNorm-fused GEMMs (bf16 mode) -------------------------------------------------------------------------------------
+static int make_ab_maps(CUtensorMap* tmA, CUtensorMap* tmB, const void* A, const void* W, int M, int N, int K) {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {gemm::BK, 128};
+    int rc = make_tmap_bf16(tmA, A, 2, dims, strides, box);
+    if (rc != VTC_OK) return rc;
+    uint64_t dimsb[2] = {(uint64_t)K, (uint64_t)N};
+    return make_tmap_bf16(tmB, W, 2, dimsb, strides, box);
+}
+
+int gemm_resid_ln(const void* A, const void* W, const float* bias, const float* residual, float* out, void* out_bf16, float* stats, int M, int N,
+                  int K, cudaStream_t stream, int reverse) {
+    VTC_REQUIRE(A && W && bias && residual && out && out_bf16 && stats, VTC_ERR_ARG, "gemm_resid_ln: null pointer");
+    VTC_REQUIRE(M > 0 && N > 0 && K > 0 && K % gemm::BK == 0 && N % gemm::BN == 0, VTC_ERR_SHAPE, "gemm_resid_ln: unsupported %dx%dx%d", M, N, K);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    CUtensorMap tmA, tmB, tmO, tmR;
+    if ((rc = make_ab_maps(&tmA, &tmB, A, W, M, N, K)) != VTC_OK) return rc;
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)N * 4};
+    uint32_t box[2] = {32, 128};
+    if ((rc = make_tmap_f32(&tmO, out, 2, dims, strides, box)) != VTC_OK) return rc;
+    if ((rc = make_tmap_f32(&tmR, residual, 2, dims, strides, box)) != VTC_OK) return rc;
+    gemm2::Params p{bias, M, N, K, 0, reverse, nullptr, stats, N / 128, 0.f, static_cast<__nv_bfloat16*>(out_bf16)};
+    return launch_gemm2<gemm2::EPI_RESID_LN, false, false>(tmA, tmB, tmO, p, stream, &tmR, nullptr);
+}
+
+int gemm_lnfold(const void* A, const void* W, const float* c, const float* g, const float* stats, float eps, void* out, int M, int N, int K,
+                int gelu, cudaStream_t stream, int reverse) {
+    VTC_REQUIRE(A && W && c && g && stats && out, VTC_ERR_ARG, "gemm_lnfold: null pointer");
+    VTC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 128 == 0 && N % gemm::BN == 0, VTC_ERR_SHAPE, "gemm_lnfold: unsupported %dx%dx%d", M, N, K);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    CUtensorMap tmA, tmB, tmO;
+    if ((rc = make_ab_maps(&tmA, &tmB, A, W, M, N, K)) != VTC_OK) return rc;
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)N * 2};
+    uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap_bf16(&tmO, out, 2, dims, strides, box)) != VTC_OK) return rc;
+    gemm2::Params p{c, M, N, K, 0, reverse, g, const_cast<float*>(stats), K / 128, eps, nullptr};
+    return gelu ? launch_gemm2<VTC_EPI_BIAS_GELU, false, true>(tmA, tmB, tmO, p, stream) : launch_gemm2<VTC_EPI_BIAS, false, true>(tmA, tmB, tmO, p, stream);
+}
+
 }  // namespace vtc
+
+extern "C" int vtc_gemm_resid_ln(const void* A, const void* W, const float* bias, const float* residual, float* out, void* out_bf16,
+                                 float* stats, int32_t M, int32_t Nout, int32_t K, void* stream) {
+    return vtc::gemm_resid_ln(A, W, bias, residual, out, out_bf16, stats, M, Nout, K, static_cast<cudaStream_t>(stream), 0);
+}
+extern "C" int vtc_gemm_lnfold(const void* A, const void* W, const float* c, const float* g, const float* stats, float eps, void* out,
+                               int32_t M, int32_t Nout, int32_t K, int32_t gelu, void* stream) {
+    return vtc::gemm_lnfold(A, W, c, g, stats, eps, out, M, Nout, K, gelu, static_cast<cudaStream_t>(stream), 0);
+}
 
 extern "C" int vtc_gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out,
                              int32_t M, int32_t Nout, int32_t K, int32_t epilogue, int32_t tokens, void* stream) {

@@ -14,7 +14,11 @@ struct vtc_model {
     std::vector<vtc_layer_weights> lw;
     // packed bf16 GEMM weights (inside the caller's packed buffer)
     const __nv_bfloat16* patch_w = nullptr;
-    struct LayerPacked { const __nv_bfloat16 *qkv, *proj, *fc1, *fc2; };
+    struct LayerPacked {
+        const __nv_bfloat16 *qkv, *proj, *fc1, *fc2;
+        // bf16 mode: qkv / fc1 hold gamma * W (LayerNorm folded in), with the two epilogue vectors of the fold (gemm.cu)
+        const float *qkv_g, *qkv_c, *fc1_g, *fc1_c;
+    };
     std::vector<LayerPacked> lp;
     bool packed = false;
     bool split = false;          // fp32 mode: GEMM operands and activations as (hi | lo) bf16 halves
@@ -29,14 +33,25 @@ namespace vtc {
 
 static size_t seg(size_t elems, size_t elem_bytes) { return align_up(elems * elem_bytes, 256); }
 
+// VTC_LN_FUSION=1 (bf16 mode only) runs the forward without LayerNorm kernels: LayerNorm folded into the GEMMs either side
+// of it (gemm.cu).  Measured on B200 at B = 256: 2 % faster over a 10-step burst (10.21 vs 10.44 ms), no gain once the run
+// is long enough to sit at the 1 kW power cap (10.66 vs 10.65 ms over 20 steps: the LayerNorm kernels are low-power
+// phases, and the GEMM epilogues that absorb them stretch the high-power ones).  The default therefore keeps the separate
+// LayerNorm, whose bf16 rounding is also independent of the row mean.
+static bool ln_fusion_enabled(const vtc_model* m) {
+    static const bool on = []() { const char* e = getenv("VTC_LN_FUSION"); return e && e[0] == '1'; }();
+    return !m->split && on;
+}
+
 static size_t packed_bytes(const vtc_model* m) {
     const size_t D = m->D, HID = m->HID, eb = m->split ? 4 : 2;
-    return seg(D * m->KP, eb) + m->L * (seg(3 * D * D, eb) + seg(D * D, eb) + 2 * seg(HID * D, eb));
+    const size_t fold = ln_fusion_enabled(m) ? 2 * (seg(3 * D, 4) + seg(HID, 4)) : 0;      // g, c of the LayerNorm-folded qkv / fc1 GEMMs
+    return seg(D * m->KP, eb) + m->L * (seg(3 * D * D, eb) + seg(D * D, eb) + 2 * seg(HID * D, eb) + fold);
 }
 
 struct Workspace {
     __nv_bfloat16 *hbuf, *patches, *y, *qkv, *ao;
-    float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp;
+    float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp, *stats;
     size_t bytes;
 };
 
@@ -61,6 +76,7 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     ws.cls_map = (o && o->cls_map) ? nullptr : reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->P, 4));
     ws.key_bias = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N, 4));
     ws.gmax = reinterpret_cast<float*>(take(m->L, 4));
+    ws.stats = reinterpret_cast<float*>(take(M * (D / 128) * 2, 4));       // LayerNorm row statistics (bf16 mode)
     const bool need_tmp = o && o->attn_mean && !(o->attn && o->attn_layers >= m->L);
     ws.attn_tmp = need_tmp ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N * N, 4)) : nullptr;
     ws.bytes = off;
@@ -138,6 +154,10 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
 
     bool have_bias = false;
     float* last_map = nullptr;
+    // bf16 mode: no LayerNorm kernels, see gemm.cu (the split-precision mode keeps the separate LayerNorm)
+    const bool ln_fused = ln_fusion_enabled(m);
+    static const bool fuse_proj = []() { const char* e = getenv("VTC_LN_FUSE_PROJ"); return !(e && e[0] == '0'); }();
+    if (ln_fused) VTC_STEP(VTC_PROF_LAYERNORM, residual_prep(t_cur, ws.y, ws.stats, M, D, st));
     // Alternating sweep direction: every kernel of the chain walks its rows / images in the opposite order of its
     // predecessor, so it starts on the data the predecessor wrote last, which is still in the 126 MB L2 (the activations
     // of one layer, 77-310 MB each at B = 256, do not fit as a whole: a same-direction sweep would miss on everything).
@@ -156,15 +176,30 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
         if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
         else if (o->attn_mean) attn_l = ws.attn_tmp;
 
-        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
-        VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp, next_dir()));
-        const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
-        if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
-        else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
-        VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
-        VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
-        VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st, sp, next_dir()));
-        VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
+        if (ln_fused) {
+            // LayerNorm lives inside the GEMMs: ws.y = bf16(residual stream), ws.stats = its row statistics (gemm.cu)
+            VTC_STEP(VTC_PROF_GEMM_QKV, gemm_lnfold(ws.y, pw.qkv, pw.qkv_c, pw.qkv_g, ws.stats, m->cfg.ln_eps, ws.qkv, M, 3 * D, D, 0, st, next_dir()));
+            const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                   // vit_model.py:118
+            VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
+            if (fuse_proj) {
+                VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_resid_ln(ws.ao, pw.proj, w.proj_b, t_in, t_out, ws.y, ws.stats, M, D, D, st, next_dir()));
+            } else {      // A/B: proj through the L2 reduction + a row pass that produces bf16(t) and its statistics
+                VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, 0, next_dir()));
+                VTC_STEP(VTC_PROF_LAYERNORM, residual_prep(t_out, ws.y, ws.stats, M, D, st));
+            }
+            VTC_STEP(VTC_PROF_GEMM_FC1, gemm_lnfold(ws.y, pw.fc1, pw.fc1_c, pw.fc1_g, ws.stats, m->cfg.ln_eps, ws.hbuf, M, HID, D, 1, st, next_dir()));
+            VTC_STEP(VTC_PROF_GEMM_FC2, gemm_resid_ln(ws.hbuf, pw.fc2, w.fc2_b, t_out, t_out, ws.y, ws.stats, M, D, HID, st, next_dir()));
+        } else {
+            VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
+            VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp, next_dir()));
+            const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
+            if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
+            else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
+            VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
+            VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
+            VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st, sp, next_dir()));
+            VTC_STEP(VTC_PROF_GEMM_FC2, gemm_bf16(ws.hbuf, pw.fc2, w.fc2_b, t_out, nullptr, t_out, M, D, HID, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
+        }
         t_cur = t_out;
 
         if (o->attn_mean) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));
@@ -283,10 +318,30 @@ int vtc_model_pack_weights(vtc_model* m, const vtc_weights* w, void* packed, siz
         const vtc_layer_weights& lw = m->lw[l];
         VTC_REQUIRE(lw.norm1_w && lw.norm1_b && lw.norm2_w && lw.norm2_b && lw.qkv_b && lw.proj_b && lw.fc1_b && lw.fc2_b, VTC_ERR_ARG,
                     "pack_weights: layer %d misses a vector parameter", l);
-        if ((rc = pack(lw.qkv_w, 3 * D, D, &m->lp[l].qkv)) != VTC_OK) return rc;
-        if ((rc = pack(lw.proj_w, D, D, &m->lp[l].proj)) != VTC_OK) return rc;
-        if ((rc = pack(lw.fc1_w, HID, D, &m->lp[l].fc1)) != VTC_OK) return rc;
-        if ((rc = pack(lw.fc2_w, D, HID, &m->lp[l].fc2)) != VTC_OK) return rc;
+        if (!ln_fusion_enabled(m)) {
+            if ((rc = pack(lw.qkv_w, 3 * D, D, &m->lp[l].qkv)) != VTC_OK) return rc;
+            if ((rc = pack(lw.proj_w, D, D, &m->lp[l].proj)) != VTC_OK) return rc;
+            if ((rc = pack(lw.fc1_w, HID, D, &m->lp[l].fc1)) != VTC_OK) return rc;
+            if ((rc = pack(lw.fc2_w, D, HID, &m->lp[l].fc2)) != VTC_OK) return rc;
+        } else {
+            // qkv and fc1 sit behind a LayerNorm: gamma folded into the weights, beta / mean handled by two epilogue vectors
+            auto fold = [&](const float* W, const float* gamma, const float* beta, const float* bias, size_t rows, const __nv_bfloat16** dst,
+                            const float** g, const float** c) -> int {
+                VTC_REQUIRE(W != nullptr, VTC_ERR_ARG, "pack_weights: missing GEMM weight");
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(base + off);
+                off += seg(rows * D, 2);
+                float* gp = reinterpret_cast<float*>(base + off);
+                off += seg(rows, 4);
+                float* cp = reinterpret_cast<float*>(base + off);
+                off += seg(rows, 4);
+                *dst = d; *g = gp; *c = cp;
+                return fold_ln(W, gamma, beta, bias, d, gp, cp, static_cast<int>(rows), static_cast<int>(D), st);
+            };
+            if ((rc = fold(lw.qkv_w, lw.norm1_w, lw.norm1_b, lw.qkv_b, 3 * D, &m->lp[l].qkv, &m->lp[l].qkv_g, &m->lp[l].qkv_c)) != VTC_OK) return rc;
+            if ((rc = pack(lw.proj_w, D, D, &m->lp[l].proj)) != VTC_OK) return rc;
+            if ((rc = fold(lw.fc1_w, lw.norm2_w, lw.norm2_b, lw.fc1_b, HID, &m->lp[l].fc1, &m->lp[l].fc1_g, &m->lp[l].fc1_c)) != VTC_OK) return rc;
+            if ((rc = pack(lw.fc2_w, D, HID, &m->lp[l].fc2)) != VTC_OK) return rc;
+        }
     }
     m->packed = true;
     m->packed_split = split;

@@ -9,6 +9,13 @@ namespace vtc {
 // split != 0 ("fp32 mode"): A [M,2K] and W [N,2K] hold (hi | lo) bf16 halves, bf16 outputs are written as [M,2N] halves
 int gemm_bf16(const void* A, const void* W, const float* bias, const float* residual, const float* pos, void* out, int M,
               int N, int K, int epilogue, int tokens, cudaStream_t stream, int split = 0, int reverse = 0);
+// LayerNorm-fused GEMMs of the bf16 forward (gemm.cu): stats = [M][D/128][2] partial (sum, sum of squares) per 128-column slice
+int gemm_resid_ln(const void* A, const void* W, const float* bias, const float* residual, float* out, void* out_bf16, float* stats, int M, int N,
+                  int K, cudaStream_t stream, int reverse = 0);
+int gemm_lnfold(const void* A, const void* W, const float* c, const float* g, const float* stats, float eps, void* out, int M, int N, int K,
+                int gelu, cudaStream_t stream, int reverse = 0);
+int residual_prep(const float* x, void* xb, float* stats, int rows, int dim, cudaStream_t stream);
+int fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* g, float* c, int N, int K, cudaStream_t stream);
 int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
 // fp32 [rows,cols] -> (hi | lo) bf16 halves [rows, 2*cols], x ~= hi + lo (16 mantissa bits)
 int split_bf16(const float* src, void* dst, size_t rows, size_t cols, cudaStream_t stream);

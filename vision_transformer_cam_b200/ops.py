@@ -271,3 +271,48 @@ def patchify_u8(x: torch.Tensor, patch: int, mean, std, split: bool = False) -> 
     out = torch.empty((B * g * g, 3 * patch * patch * (2 if split else 1)), dtype=torch.bfloat16, device=x.device)
     _lib.call("vtc_patchify_u8", _ptr(x), (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std), _ptr(out), B, S, patch, int(split), _stream())
     return out
+
+
+# ---- LayerNorm fused into the GEMMs (bf16 forward) -------------------------------------------------------------------------
+def fold_ln(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """nn.Linear weight [N,K] behind a LayerNorm(gamma, beta) -> (W' bf16 [N,K], g [N], c [N]), see include/vtc.h."""
+    N, K = w.shape
+    wf = torch.empty((N, K), dtype=torch.bfloat16, device=w.device)
+    g = torch.empty((N,), dtype=torch.float32, device=w.device)
+    c = torch.empty((N,), dtype=torch.float32, device=w.device)
+    _lib.call("vtc_fold_ln", _ptr(w, torch.float32, "w"), _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(bias, torch.float32),
+              _ptr(wf), _ptr(g), _ptr(c), N, K, _stream())
+    return wf, g, c
+
+
+def residual_prep(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [rows,D] -> (bf16 copy, stats [rows, D/128, 2])."""
+    rows, D = x.shape
+    xb = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((rows, D // 128, 2), dtype=torch.float32, device=x.device)
+    _lib.call("vtc_residual_prep", _ptr(x, torch.float32, "x"), _ptr(xb), _ptr(stats), rows, D, _stream())
+    return xb, stats
+
+
+def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """out = residual + a.w^T + bias (fp32), bf16(out), stats of out."""
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ob = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    stats = torch.empty((M, N // 128, 2), dtype=torch.float32, device=a.device)
+    _lib.call("vtc_gemm_resid_ln", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32), _ptr(residual, torch.float32),
+              _ptr(out, torch.float32), _ptr(ob), _ptr(stats), M, N, K, _stream())
+    return out, ob, stats
+
+
+def gemm_lnfold(a: torch.Tensor, wf: torch.Tensor, c: torch.Tensor, g: torch.Tensor, stats: torch.Tensor, eps: float, gelu: bool = False) -> torch.Tensor:
+    """bf16 [M,N] = [GELU](LN(t).W^T + b) evaluated as rstd (a.W'^T - mean g) + c with a = bf16(t)."""
+    M, K = a.shape
+    N = wf.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _lib.call("vtc_gemm_lnfold", _ptr(a, torch.bfloat16, "a"), _ptr(wf, torch.bfloat16, "wf"), _ptr(c, torch.float32), _ptr(g, torch.float32),
+              _ptr(stats, torch.float32), eps, _ptr(out), M, N, K, int(gelu), _stream())
+    return out
