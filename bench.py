@@ -162,7 +162,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
 
     import torch
@@ -174,6 +174,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -305,7 +307,7 @@ def main():
                 "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
                 "tensor_frac_of_burst_peak": FLOP_IMAGE * value / world / 1e12 / peaks()["bf16_tflops"]}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -26,10 +26,12 @@ n = 10
 out = pipeline.extract_cams_sharded(model, get, n_items=n, batch=1)
 assert out["cam"].shape[0] == n and out["rollout"].shape == (n, 196)
 if rank == 0:
-    ref = torch.cat([pipeline.extract_cams_sharded(model, get, n_items=1, batch=1, gather=False)["cam"] if False else
-                     __import__("vision_transformer_cam_b200").cam.classic_cam(model.forward_cam(get(i, i + 1)).tokens_last, model.head1.weight.data)
-                     for i in range(n)])
+    # the same per-image calls on one rank (same outputs requested => same kernels => same bits)
+    from vision_transformer_cam_b200 import cam as CAM
+    fwd = [model.forward_cam(get(i, i + 1), attn_mean=True) for i in range(n)]
+    ref = torch.cat([CAM.classic_cam(o.tokens_last, model.head1.weight.data) for o in fwd])
     assert torch.equal(ref, out["cam"]), float((ref - out["cam"]).abs().max())
+    assert torch.equal(torch.cat([CAM.rollout_row(o.attn_mean) for o in fwd]), out["rollout"])
 c = torch.tensor([rank + 1], dtype=torch.int64, device=dev)
 D.reduce_counters(c)
 assert int(c) == world * (world + 1) // 2
