@@ -193,10 +193,13 @@ def main():
         cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)
         return o, cam
 
+    from vision_transformer_cam_b200 import dist as VD
+    gatherer = VD.SideStreamGather(dev) if world > 1 else None
+
     def step(x):
         o, cam = local_step(x)
-        if world > 1:       # gather of the CAM maps + reduction of the counters: the only collectives (never inside the forward)
-            dist.all_gather_into_tensor(gathered, cam)
+        if world > 1:       # gather of the CAM maps + reduction of the counters: the only collectives (never inside the forward);
+            gatherer.gather(gathered, cam)      # on a side stream: the gather of step i overlaps the forward of step i+1
         return o, cam
 
     def barrier():
@@ -211,6 +214,7 @@ def main():
         for _ in range(iters):
             fn()
         if world > 1:
+            gatherer.wait()
             dist.all_reduce(counters)
         e1.record()
         barrier()
@@ -254,6 +258,7 @@ def main():
     e0.record()
     e2e_run(K)
     if world > 1:
+        gatherer.wait()
         dist.all_reduce(counters)
     e1.record()
     barrier()

@@ -32,6 +32,17 @@ if rank == 0:
     ref = torch.cat([CAM.classic_cam(o.tokens_last, model.head1.weight.data) for o in fwd])
     assert torch.equal(ref, out["cam"]), float((ref - out["cam"]).abs().max())
     assert torch.equal(torch.cat([CAM.rollout_row(o.attn_mean) for o in fwd]), out["rollout"])
+# side-stream gather: same result as the in-stream collective, for several steps in flight
+g = D.SideStreamGather(dev)
+outs = [torch.empty((world * 3, 5), device=dev) for _ in range(4)]
+for k in range(4):
+    local = torch.full((3, 5), float(10 * k + rank), device=dev)
+    g.gather(outs[k], local)
+    del local
+g.wait()
+for k in range(4):
+    want = torch.cat([torch.full((3, 5), float(10 * k + r)) for r in range(world)])
+    assert torch.equal(outs[k].cpu(), want)
 c = torch.tensor([rank + 1], dtype=torch.int64, device=dev)
 D.reduce_counters(c)
 assert int(c) == world * (world + 1) // 2

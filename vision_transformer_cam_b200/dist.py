@@ -82,6 +82,30 @@ def gather_shards(local: torch.Tensor, n_items: int) -> torch.Tensor:
     return torch.cat([out[r, :sizes[r]] for r in range(world)])
 
 
+class SideStreamGather:
+    """All-gather of per-step results on a side stream, so the collective of step i overlaps the forward of step i+1
+    (collectives outside the forward, on a side stream).  `gather(local)` enqueues
+    all_gather_into_tensor(out, local) behind everything already enqueued on the caller's stream; `wait()` makes the
+    caller's stream wait for all gathers issued so far (call it before reading `out`)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def gather(self, out: torch.Tensor, local: torch.Tensor) -> None:
+        if rank_world()[1] == 1:
+            out.copy_(local)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(out, local)
+        local.record_stream(self.stream)       # `local` may be freed by the caller while the collective still reads it
+
+    def wait(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 def reduce_counters(counters: torch.Tensor) -> torch.Tensor:
     """Sum int64 counters (21x21 confusion matrix, AP sum / count, top-1 hits ...) over all ranks, in place."""
     if rank_world()[1] > 1:
