@@ -239,6 +239,13 @@ VTC_API int vtc_layernorm_bf16(const float* x, const float* gamma, const float* 
  * cls_rows [B,H,N] fp32 (P[b,h,0,:]) or NULL; attn [B,H,N,N] fp32 full P or NULL. */
 VTC_API int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
                   int32_t n_tokens, int32_t heads, float scale, void* stream);
+/* vtc_attention + the head mean of P, attn_mean [B,N,N] = mean_h P[b,h] (what the rollout consumes, predict.py:189-190),
+ * without materialising [B,H,N,N] fp32: the kernel writes the bf16 exponentials it feeds to P.V and 1/rowsum into
+ * `scratch` (256-byte aligned, >= vtc_attention_mean_scratch_bytes), a second kernel reduces them over the heads in a
+ * fixed order.  n_tokens <= 208 (VTC_ERR_SHAPE otherwise: use vtc_attention's full P + vtc_head_mean). */
+VTC_API size_t vtc_attention_mean_scratch_bytes(int32_t batch, int32_t n_tokens, int32_t heads);
+VTC_API int vtc_attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch,
+                       size_t scratch_bytes, int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream);
 /* The KV-blocked kernel behind vtc_attention for n_tokens > 256 (ViT-B/16-448: 785 tokens, ViT-L/16-384: 577 tokens),
  * callable directly for any n_tokens <= 2048.  Same arguments and outputs as vtc_attention.
  *   split != 0 ("fp32 mode"): operands are (hi, lo) bf16 pairs, x ~= hi + lo: qkv is [B,N,2,3,H,64] (all hi parts of a

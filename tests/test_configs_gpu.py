@@ -108,3 +108,27 @@ def test_vit_l16_384_forward_cam(lib_built):
     assert ep <= 1.5 * PEAKED_TOL        # 24 layers of the 25x more sensitive softmax instead of 12 (see PEAKED_TOL)
     out = model(x.to("cuda:0"))
     assert len(out[1]) == 12 and out[1][0].shape == (1, 16, 577, 577) and len(out[2]) == 12 and out[5].shape == (1, 16, 1024)
+
+
+def test_patch32_factory_with_pre_logits(lib_built):
+    """vit_base_patch32_224_in21k(has_logits=True): 50 tokens, 32 px patches (K = 3072 patch GEMM) and the tanh pre_logits
+    layer in front of the head (vit_model.py:267-273) -- the remaining factory variants of the reference."""
+    import vision_transformer_cam_b200 as V
+    from vision_transformer_cam_b200 import cam as CAM
+    from oracle import vit_forward as VF, postproc as PP
+    cfg = VF.VitConfig(patch_size=32, representation_size=768)
+    torch.manual_seed(0)
+    model = V.vit_base_patch32_224_in21k(num_classes=20, has_logits=True)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert "pre_logits.fc.weight" in sd and sd["pos_embed"].shape == (1, 50, 768)
+    model = model.to("cuda:0").eval()
+    x = VF.make_images(0, 3)
+    ref = VF.forward(sd, x, cfg)
+    o = model.forward_cam(x.to("cuda:0"), attn_mean=True)
+    e = relerr(o.logits, ref["logits"])
+    c_cam = cosine(CAM.classic_cam(o.tokens_last, model.head1.weight.data), PP.classic_cam(ref["X"][-1], sd["head1.weight"]))
+    c_roll = cosine(CAM.rollout_row(o.attn_mean), PP.rollout_dense(ref["P"]))
+    print(f"B/32-224 + pre_logits: logits relerr {e:.2e} CAM cos {c_cam:.6f} rollout cos {c_roll:.6f}")
+    assert e <= LOGIT_TOL and c_cam >= 0.999 and c_roll >= 0.999
+    out = model(x.to("cuda:0"))
+    assert out[1][0].shape == (3, 12, 50, 50) and out[5].shape == (3, 16, 768)

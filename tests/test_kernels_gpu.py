@@ -504,3 +504,26 @@ def test_layernorm_fused_gemms(dev, M):
         e, e0 = relerr(out.float(), ref), relerr(base.float(), ref)
         print(f"LN-folded GEMM gelu={gelu}: relerr {e:.2e} (separate LayerNorm kernel: {e0:.2e})")
         assert e < 8e-3 and e < 2.0 * e0 + 1e-3
+
+
+@pytest.mark.parametrize("B,N,H,masked", [(3, 197, 12, True), (2, 197, 12, False), (5, 50, 3, True), (2, 208, 2, False), (300, 197, 1, False)])
+def test_attention_fused_head_mean(dev, B, N, H, masked):
+    """Head mean of P from the packed bf16 P of the fast attention kernel (vtc_attention_mean: the rollout's input,
+    predict.py:189-190) == mean over heads of the fp32 softmax; P enters as the bf16 values the P.V product uses, so the
+    bar is bf16-level: 1 % of the largest entry."""
+    from vision_transformer_cam_b200 import ops
+    qkv = _rand((B, N, 3 * H * 64), 110, dev, 1.5).bfloat16()
+    kb = None
+    if masked:
+        g = torch.Generator().manual_seed(111)
+        kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+        kb[:, 0] = 0
+        kb = kb.to(dev)
+    ref_o, ref_p = _attn_ref(qkv, H, 0.125, kb)
+    out, cls, mean = ops.attention_mean(qkv, H, 0.125, key_bias=kb)
+    ref_m = ref_p.mean(1)
+    assert float((mean - ref_m).abs().max()) <= 1e-2 * float(ref_m.max()), float((mean - ref_m).abs().max())
+    assert float((mean.sum(-1) - 1).abs().max()) < 5e-3
+    assert relerr(out.float(), ref_o) < 1e-2 and float((cls - ref_p[:, :, 0, :]).abs().max()) < 5e-6
+    out2, cls2, mean2 = ops.attention_mean(qkv, H, 0.125, key_bias=kb)
+    assert torch.equal(mean, mean2) and torch.equal(out, out2)            # fixed accumulation order

@@ -89,6 +89,8 @@ SIGNATURES = {
     "vtc_cls_token_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "vtc_layernorm_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vtc_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "vtc_attention_mean_scratch_bytes": (_Z, [_I, _I, _I]),
+    "vtc_attention_mean": (C.c_int, [_P, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _F, _P]),
     "vtc_attention_kv": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
     "vtc_head_mean": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "vtc_cls_stat": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -42,8 +42,10 @@ constexpr int OFF_P = 0;                              // overlays Q + K
 constexpr int OFF_V = 4 * P_KBLOCK_BYTES;             // 64 KB
 constexpr int OFF_QAUG = OFF_V + KV_BYTES;            // 128 rows x 32 B, no swizzle
 constexpr int OFF_KAUG = OFF_QAUG + 128 * 32;         // 256 rows x 32 B, no swizzle
-constexpr int OFF_CLS = OFF_KAUG + MAXN * 32;         // CLS row staging [256] floats
-constexpr int OFF_BAR = OFF_CLS + MAXN * 4;
+constexpr int OFF_SCRATCH = OFF_QAUG;                 // full-P output: 4 x 4 KB transpose scratch on top of the (dead) mask operands
+constexpr int OFF_CLS = OFF_SCRATCH;                  // CLS row staging [256] floats: first KB of warp 0's scratch (written out before warp 0 transposes)
+constexpr int OFF_BAR = OFF_SCRATCH + 4 * 4096;
+static_assert(OFF_KAUG + MAXN * 32 <= OFF_BAR, "mask operands fit under the transpose scratch");
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int THREADS = 160;
 static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two attention CTAs per SM");
@@ -320,29 +322,31 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             else softmax_pass2<false>(t_s, nchunks, N, sc, neg_m, p_row, r_local, cls_s, false, sum, t_s, ts);
             if (p.ts_mode) tmem_st_wait();
             inv = 1.0f / sum;
-            if (p.attn != nullptr) {
-                // pass 3 (on request): normalised fp32 P rows; CTA-uniform branch, only the stores are predicated
-                const bool wr = row < N;
-                float* dst = p.attn + ((static_cast<size_t>(b) * p.H + h) * N + (wr ? row : 0)) * N;
-                for (int c = 0; c < nchunks; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_s + c * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        if (wr && col < N) dst[col] = ex2_approx(fmaf(__uint_as_float(r[j]), sc, neg_m)) * inv;
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
             if (cls_warp) {
                 const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
                 __syncwarp();
                 float* dst = p.cls_rows + (static_cast<size_t>(b) * p.H + h) * N;
                 for (int j = lane; j < N; j += 32) dst[j] = cls_s[j] * inv0;
+                __syncwarp();          // the staging area is the first KB of this warp's transpose scratch
             }
+            if (p.attn != nullptr) {
+                // pass 3 (on request): normalised fp32 P rows; CTA-uniform branch, only the stores are predicated
+                // (the S = Q K^T MMAs have retired, so the mask operands under the scratch are dead)
+                float* scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH) + quarter * 1024;
+                const int row0 = mt * 128 + quarter * 32;
+                float* dst = p.attn + ((static_cast<size_t>(b) * p.H + h) * N + row0) * N;
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_s + c * 32, r);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sc, neg_m)) * inv;
+                    store_rows_coalesced(scratch, pv, dst + c * 32, static_cast<size_t>(N), N - row0, N - c * 32);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
         }
         if (threadIdx.x == 0) stamp(3);
         mbar_arrive(p_full);
@@ -445,6 +449,88 @@ int head_mean(const float* attn_in, float* mean, int batch, int heads, int n_tok
     return VTC_OK;
 }
 
+// ---- head mean of the packed P written by attention_cs: mean[b,r,:] = 1/H sum_h einv[b,h,r] * E[b,h,r,:] ------------------
+// One warp per (image, query row); a lane owns 8 consecutive keys (one 16-byte load per head).  Heads are added in order,
+// so the result is bit-reproducible.  The row leaves through a per-warp staging line because [B,N,N] rows (N odd) are not
+// 16-byte aligned: the global stores are 32 consecutive floats per instruction.
+constexpr int HMP_WARPS = 8;
+__global__ void __launch_bounds__(HMP_WARPS * 32)
+head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ einv, float* __restrict__ mean, int B, int H, int N, int lde) {
+    __shared__ float stage[HMP_WARPS][264];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vec_per_row = lde >> 3;                    // uint4 per row, <= 32
+    const int nrows = B * N;
+    const float invh = 1.0f / static_cast<float>(H);
+    float* st = stage[warp];
+    for (int rid = blockIdx.x * HMP_WARPS + warp; rid < nrows; rid += gridDim.x * HMP_WARPS) {
+        const int b = rid / N, r = rid - b * N;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const size_t row0 = static_cast<size_t>(b) * H * N + r;          // (b, h = 0, r); + h * N per head
+        if (lane < vec_per_row) {
+#pragma unroll 4
+            for (int h = 0; h < H; ++h) {
+                const size_t row = row0 + static_cast<size_t>(h) * N;
+                const float w = __ldg(einv + row);
+                const uint4 v = ld_stream_u4(e + row * vec_per_row + lane);
+                acc[0] = fmaf(w, __uint_as_float(v.x << 16), acc[0]);
+                acc[1] = fmaf(w, __uint_as_float(v.x & 0xffff0000u), acc[1]);
+                acc[2] = fmaf(w, __uint_as_float(v.y << 16), acc[2]);
+                acc[3] = fmaf(w, __uint_as_float(v.y & 0xffff0000u), acc[3]);
+                acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]);
+                acc[5] = fmaf(w, __uint_as_float(v.z & 0xffff0000u), acc[5]);
+                acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]);
+                acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
+            }
+            float4* s4 = reinterpret_cast<float4*>(st + lane * 8);
+            s4[0] = make_float4(acc[0] * invh, acc[1] * invh, acc[2] * invh, acc[3] * invh);
+            s4[1] = make_float4(acc[4] * invh, acc[5] * invh, acc[6] * invh, acc[7] * invh);
+        }
+        __syncwarp();
+        float* dst = mean + static_cast<size_t>(rid) * N;
+        for (int c = lane; c < N; c += 32) dst[c] = st[c];
+        __syncwarp();
+    }
+}
+
+int head_mean_packed(const void* e, const float* einv, float* mean, int batch, int heads, int n_tokens, int lde, cudaStream_t stream) {
+    VTC_REQUIRE(e && einv && mean, VTC_ERR_ARG, "head_mean_packed: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0 && lde >= n_tokens && lde % 8 == 0 && lde <= 256, VTC_ERR_SHAPE, "head_mean_packed: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int nrows = batch * n_tokens;
+    int blocks = cdiv(nrows, HMP_WARPS);
+    const int cap = device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    head_mean_packed_kernel<<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(e), einv, mean, batch, heads, n_tokens, lde);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+static size_t packed_e_bytes(int batch, int n_tokens, int heads) {
+    return align_up(static_cast<size_t>(batch) * heads * n_tokens * attention_packed_ld(n_tokens) * 2, 256);
+}
+size_t attention_mean_scratch_bytes(int batch, int n_tokens, int heads) {
+    if (batch <= 0 || n_tokens <= 0 || heads <= 0) return 0;
+    return packed_e_bytes(batch, n_tokens, heads) + align_up(static_cast<size_t>(batch) * heads * n_tokens * 4, 256);
+}
+
+int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
+                   int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse) {
+    VTC_REQUIRE(qkv && out && attn_mean && scratch, VTC_ERR_ARG, "attention_mean: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention_mean: bad shape");
+    VTC_REQUIRE(n_tokens <= kAttentionFusedMeanMaxTokens, VTC_ERR_SHAPE, "attention_mean: %d tokens > %d (use the full P of vtc_attention + vtc_head_mean)",
+                n_tokens, kAttentionFusedMeanMaxTokens);
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, VTC_ERR_WORKSPACE, "attention_mean: scratch must be 256-byte aligned");
+    VTC_REQUIRE(scratch_bytes >= attention_mean_scratch_bytes(batch, n_tokens, heads), VTC_ERR_WORKSPACE, "attention_mean: scratch %zu bytes < required %zu",
+                scratch_bytes, attention_mean_scratch_bytes(batch, n_tokens, heads));
+    float* einv = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + packed_e_bytes(batch, n_tokens, heads));
+    int rc = attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, scratch, einv);
+    if (rc != VTC_OK) return rc;
+    return head_mean_packed(scratch, einv, attn_mean, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream);
+}
+
 }  // namespace vtc
 
 extern "C" {
@@ -453,6 +539,14 @@ __attribute__((visibility("default"))) void vtc_debug_set_attention_trace(void* 
 int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch, int32_t n_tokens,
                   int32_t heads, float scale, void* stream) {
     return vtc::attention(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream), 0);
+}
+size_t vtc_attention_mean_scratch_bytes(int32_t batch, int32_t n_tokens, int32_t heads) {
+    return vtc::attention_mean_scratch_bytes(batch, n_tokens, heads);
+}
+int vtc_attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
+                       int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream) {
+    return vtc::attention_mean(qkv, key_bias, out, cls_rows, attn_mean, scratch, scratch_bytes, batch, n_tokens, heads, scale,
+                               static_cast<cudaStream_t>(stream), 0);
 }
 int vtc_head_mean(const float* attn, float* mean, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
     return vtc::head_mean(attn, mean, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));

@@ -75,6 +75,12 @@ struct Params {
     const float* key_bias;   // [B,N] or null
     __nv_bfloat16* out;      // [B,N,H*64]
     float* cls_rows;         // [B,H,N] or null
+    // Head-mean support (single-block N only): the un-normalised bf16 exponentials E the P V product consumed, exactly as
+    // they sit in TMEM, and 1 / rowsum -- P[b,h,r,:] = einv[b,h,r] * E[b,h,r,:].  head_mean_packed() reduces them over the
+    // heads; [B,H,N,N] fp32 is never written.
+    __nv_bfloat16* edump;    // [B,H,N,lde] or null
+    float* einv;             // [B,H,N]
+    int lde;                 // 32 * number of key chunks
     int B, N, H;
     int KB, nb;
     float scale, scale_log2;
@@ -217,9 +223,13 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool has_bias = p.key_bias != nullptr;
     const int D = H * HD;
     const uint32_t kv_bytes = static_cast<uint32_t>(KB) * 128u;
-    auto item_of = [&](int i) {
-        const int it = first + i * stride;
-        return p.reverse ? n_items - 1 - it : it;
+    auto decode = [&](int i, int& b, int& h, int& qt) {
+        int it = first + i * stride;
+        if (p.reverse) it = n_items - 1 - it;
+        qt = it % qtiles;
+        const int bh = it / qtiles;
+        b = bh / H;
+        h = bh - b * H;
     };
 
     if (warp == SM_WARPS + GROUPS) {
@@ -244,10 +254,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float inv_scale = 1.0f / p.scale;
         uint32_t step = 0;
         for (int i = 0; i < my_items; ++i) {
-            const int it = item_of(i);
-            const int qt = it % qtiles;
-            const int bh = it / qtiles;
-            const int b = bh / H, h = bh - b * H;
+            int b, h, qt;
+            decode(i, b, h, qt);
             const float* kb = has_bias ? p.key_bias + static_cast<size_t>(b) * N : nullptr;
             if (lane == 0) mbar_wait_fast(q_empty, (i & 1) ^ 1);
             __syncwarp();
@@ -368,10 +376,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t row_bar = 1 + g * 4 + quarter;           // named barrier of the PARTS warps that share these rows
         int s = 0;
         for (int i = 0; i < my_items; ++i) {
-            const int it = item_of(i);
-            const int qt = it % qtiles;
-            const int bh = it / qtiles;
-            const int b = bh / H, h = bh - b * H;
+            int b, h, qt;
+            decode(i, b, h, qt);
             const int row = qt * 128 + r_local;
             const bool warp_active = (qt * 128 + quarter * 32) < N;
             const bool cls_warp = (qt == 0) && (quarter == 0) && (p.cls_rows != nullptr);
@@ -469,6 +475,24 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 uint32_t o[OCOLS];
                 tmem_ld_cols(t_s + O_COL + part * OCOLS, o);
                 tmem_ld_wait();
+                if (p.edump != nullptr) {
+                    // the bf16 exponentials of my column range are still in TMEM (P V has retired): one 64-byte row segment per
+                    // 32-key chunk, two full 32-byte sectors per lane
+                    const int nch = (N + 31) >> 5;
+                    const int c0 = part_begin(part, nch), c1 = part_begin(part + 1, nch);
+                    const size_t erow_idx = (static_cast<size_t>(b) * H + h) * N + (row < N ? row : 0);
+                    __nv_bfloat16* erow = p.edump + erow_idx * p.lde + c0 * 32;
+                    for (int pc = 0; pc < c1 - c0; ++pc) {
+                        uint32_t q[16];
+                        tmem_ld_32x32b_x16(t_s + c0 * 32 + P_SHIFT + pc * 16, q);
+                        tmem_ld_wait();
+                        if (row < N) {
+                            st_u8(erow + pc * 32, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+                            st_u8(erow + pc * 32 + 16, q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
+                        }
+                    }
+                    if (part == 0 && row < N) p.einv[erow_idx] = inv;
+                }
                 tc_fence_before();
                 mbar_arrive(o_empty);
                 if (row < N) {
@@ -496,18 +520,22 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }  // namespace acs
 
 int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
-                 cudaStream_t stream, int reverse) {
+                 cudaStream_t stream, int reverse, void* edump, float* einv) {
     using namespace acs;
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
     VTC_REQUIRE(n_tokens <= NMAX, VTC_ERR_SHAPE, "attention: %d tokens > %d", n_tokens, NMAX);
+    VTC_REQUIRE(edump == nullptr || (n_tokens <= KBMAX && einv != nullptr), VTC_ERR_SHAPE, "attention: the packed-P output needs n_tokens <= %d", KBMAX);
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     Params p{};
     p.key_bias = key_bias;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.cls_rows = cls_rows;
+    p.edump = static_cast<__nv_bfloat16*>(edump);
+    p.einv = einv;
+    p.lde = attention_packed_ld(n_tokens);
     p.B = batch;
     p.N = n_tokens;
     p.H = heads;

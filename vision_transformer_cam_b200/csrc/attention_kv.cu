@@ -49,7 +49,8 @@ struct Cfg {
     static constexpr int OFF_CLS = 2 * GROUP_BYTES;             // [2][NMAX] floats: staged CLS row
     static constexpr int OFF_KB = OFF_CLS + 2 * NMAX * 4;       // [2][NMAX] floats: key bias, log2 domain
     static constexpr int OFF_BAR = OFF_KB + 2 * NMAX * 4;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int OFF_SCRATCH = OFF_BAR + 256;           // full-P output: 8 x 4 KB transpose scratch (not in split mode: no room)
+    static constexpr int SMEM_BYTES = OFF_SCRATCH + (SPLIT ? 0 : 8 * 4096);
     static constexpr int PLO_COL = 128;                         // SPLIT: low halves of P
     static_assert(SMEM_BYTES <= 232448, "attention_kv smem budget");
     static_assert(GROUP_BYTES % 1024 == 0 && OFF_K % 1024 == 0 && OFF_V % 1024 == 0, "swizzle atoms need 1024-byte tiles");
@@ -218,16 +219,25 @@ __device__ __forceinline__ void chunk_sweep1(uint32_t (&cur)[32], int c_in_blk, 
 }
 
 // One 32-key chunk of sweep 2: normalised probabilities of this thread's row -> global fp32.
+// scratch != null: the 32 x 32 block of this warp goes out through the coalescing transpose (dst_blk -> element (warp row 0,
+// col0), rows_left = valid rows from there); scratch == null (split mode: no shared memory left): row-wise scalar stores.
 template <bool BIAS>
 __device__ __forceinline__ void chunk_sweep2(const uint32_t (&cur)[32], int col0, int N, float sc, float rb, const float* kb_s, float negm,
-                                             float inv, float* dst_row, bool wr) {
+                                             float inv, float* dst_row, bool wr, float* scratch, float* dst_blk, int rows_left) {
     const int nvalid = N - col0;
+    float pv[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(cur[j]) * sc;
         if (BIAS) x = fmaf(kb_s[(j < nvalid) ? col0 + j : col0], rb, x);
-        const float pv = ex2_approx(x + negm) * inv;
-        if (wr && j < nvalid) dst_row[col0 + j] = pv;
+        pv[j] = ex2_approx(x + negm) * inv;
+    }
+    if (scratch != nullptr) {
+        store_rows_coalesced(scratch, pv, dst_blk + col0, static_cast<size_t>(N), rows_left, nvalid);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (wr && j < nvalid) dst_row[col0 + j] = pv[j];
     }
 }
 
@@ -485,6 +495,9 @@ attention_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const float negm = -st.m;
                 const bool wr = row < N;
                 float* dst_row = p.attn + ((static_cast<size_t>(b) * H + h) * N + (wr ? row : 0)) * N;
+                const int row0 = qt * 128 + quarter * 32;
+                float* scratch = SPLIT ? nullptr : reinterpret_cast<float*>(smem + C::OFF_SCRATCH) + warp * 1024;
+                float* dst_blk = p.attn + ((static_cast<size_t>(b) * H + h) * N + row0) * N;
                 for (int j = 0; j < nb; ++j, ++step) {
                     const int vj = min(KB, N - j * KB);
                     const int nch = (vj + 31) >> 5;
@@ -495,8 +508,8 @@ attention_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             uint32_t r[32];
                             tmem_ld_32x32b_x32(t_s + c * 32, r);
                             tmem_ld_wait();
-                            if (has_bias) chunk_sweep2<true>(r, j * KB + c * 32, N, sc, rb, kb_s, negm, inv, dst_row, wr);
-                            else chunk_sweep2<false>(r, j * KB + c * 32, N, sc, rb, kb_s, negm, inv, dst_row, wr);
+                            if (has_bias) chunk_sweep2<true>(r, j * KB + c * 32, N, sc, rb, kb_s, negm, inv, dst_row, wr, scratch, dst_blk, N - row0);
+                            else chunk_sweep2<false>(r, j * KB + c * 32, N, sc, rb, kb_s, negm, inv, dst_row, wr, scratch, dst_blk, N - row0);
                         }
                     }
                     tc_fence_before();

@@ -498,6 +498,23 @@ __device__ __forceinline__ void gelu2(float x0, float x1, float& g0, float& g1) 
     unpack2(r, g0, g1);
 }
 
+// ---- row-per-lane block -> coalesced global rows ---------------------------------------------------
+// A warp holds a 32 x 32 fp32 block one ROW per lane (v[j] = element (lane, j)), the layout tcgen05.ld 32x32b produces.
+// Storing it row by row from the owning lanes would touch 32 different cache lines per instruction; instead the block is
+// transposed through a 4 KB per-warp shared-memory scratch (XOR swizzle, conflict free both ways) and every store
+// instruction writes 32 consecutive floats of one row.  dst -> element (0, 0); ld = row stride in floats.
+__device__ __forceinline__ void store_rows_coalesced(float* scratch, const float (&v)[32], float* dst, size_t ld, int nrows, int ncols) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * 32 + (j ^ lane)] = v[j];
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+        if (r < nrows && lane < ncols) dst[static_cast<size_t>(r) * ld + lane] = scratch[r * 32 + (lane ^ r)];
+    }
+    __syncwarp();
+}
+
 // ---- vectorised global access -------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
@@ -505,8 +522,20 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st_u4(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+// 32-byte global store (sm_100: st.global.v8.b32), p 32-byte aligned: one full sector per lane and instruction
+__device__ __forceinline__ void st_u8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                      uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+                 "r"(a6), "r"(a7)
+                 : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace vtc

@@ -49,9 +49,18 @@ static size_t packed_bytes(const vtc_model* m) {
     return seg(D * m->KP, eb) + m->L * (seg(3 * D * D, eb) + seg(D * D, eb) + 2 * seg(HID * D, eb) + fold);
 }
 
+// short sequences, bf16 mode: the head mean of P comes from the packed bf16 P of the fast attention kernel
+// (attention_mean, attention.cu) instead of a [B,H,N,N] fp32 round trip
+static bool fused_mean_ok(const vtc_model* m) {
+    static const bool off = []() { const char* e = getenv("VTC_NO_FUSED_MEAN"); return e && e[0] == '1'; }();
+    return !off && !m->split && m->N <= kAttentionFusedMeanMaxTokens;
+}
+
 struct Workspace {
     __nv_bfloat16 *hbuf, *patches, *y, *qkv, *ao;
     float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp, *stats;
+    void* mean_scratch;          // packed P of attention_mean
+    size_t mean_scratch_bytes;
     size_t bytes;
 };
 
@@ -77,8 +86,10 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     ws.key_bias = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N, 4));
     ws.gmax = reinterpret_cast<float*>(take(m->L, 4));
     ws.stats = reinterpret_cast<float*>(take(M * (D / 128) * 2, 4));       // LayerNorm row statistics (bf16 mode)
-    const bool need_tmp = o && o->attn_mean && !(o->attn && o->attn_layers >= m->L);
-    ws.attn_tmp = need_tmp ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N * N, 4)) : nullptr;
+    const bool need_mean = o && o->attn_mean && !(o->attn && o->attn_layers >= m->L);       // some layer's mean is not a by-product of its full P
+    ws.attn_tmp = (need_mean && !fused_mean_ok(m)) ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N * N, 4)) : nullptr;
+    ws.mean_scratch_bytes = (need_mean && fused_mean_ok(m)) ? attention_mean_scratch_bytes(B, m->N, m->H) : 0;
+    ws.mean_scratch = ws.mean_scratch_bytes ? take(ws.mean_scratch_bytes, 1) : nullptr;
     ws.bytes = off;
     return ws;
 }
@@ -156,6 +167,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     float* last_map = nullptr;
     // bf16 mode: no LayerNorm kernels, see gemm.cu (the split-precision mode keeps the separate LayerNorm)
     const bool ln_fused = ln_fusion_enabled(m);
+    const bool fused_mean = fused_mean_ok(m);
     static const bool fuse_proj = []() { const char* e = getenv("VTC_LN_FUSE_PROJ"); return !(e && e[0] == '0'); }();
     if (ln_fused) VTC_STEP(VTC_PROF_LAYERNORM, residual_prep(t_cur, ws.y, ws.stats, M, D, st));
     // Alternating sweep direction: every kernel of the chain walks its rows / images in the opposite order of its
@@ -173,7 +185,9 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
         const bool want_map = (l >= m->cfg.mask_from) || (l == L - 1) || (o->cls_map != nullptr);
         float* cls_l = o->cls_rows ? o->cls_rows + static_cast<size_t>(l) * B * H * N : (want_map ? ws.cls_rows : nullptr);
         float* attn_l = nullptr;
+        float* mean_l = nullptr;          // head mean via the packed P (short sequences, bf16 mode)
         if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
+        else if (o->attn_mean && fused_mean) mean_l = o->attn_mean + static_cast<size_t>(l) * B * N * N;
         else if (o->attn_mean) attn_l = ws.attn_tmp;
 
         if (ln_fused) {
@@ -194,6 +208,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp, next_dir()));
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
             if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
+            else if (mean_l) VTC_STEP(VTC_PROF_ATTENTION, attention_mean(ws.qkv, kb, ws.ao, cls_l, mean_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
             else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
             VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
             VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
@@ -202,7 +217,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
         }
         t_cur = t_out;
 
-        if (o->attn_mean) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));
+        if (o->attn_mean && mean_l == nullptr) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));
         if (want_map) {
             float* map_l = o->cls_map ? o->cls_map + static_cast<size_t>(l) * B * P : ws.cls_map;
             VTC_STEP(VTC_PROF_CLS, cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st));

@@ -124,6 +124,19 @@ def attention(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[to
     return out, cls, attn
 
 
+def attention_mean(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Attention that also returns the head mean of P without a [B,H,N,N] round trip: (out, cls_rows, attn_mean [B,N,N])."""
+    B, N, D3 = qkv.shape
+    out = torch.empty((B, N, D3 // 3), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device)
+    mean = torch.empty((B, N, N), dtype=torch.float32, device=qkv.device)
+    nbytes = int(_lib.load().vtc_attention_mean_scratch_bytes(B, N, heads))
+    scratch = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
+    _lib.call("vtc_attention_mean", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), _ptr(mean),
+              _ptr(scratch), nbytes, B, N, heads, scale, _stream())
+    return out, cls, mean
+
+
 def attention_kv(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, want_cls: bool = True,
                  want_attn: bool = False, split: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     """The KV-blocked kernel called directly (any N <= 2048).  split: qkv [B,N,2*3*H*64] and out [B,N,2*H*64] hold
