@@ -186,9 +186,10 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
     }
     tmem_st_32x32b_x16(t_p + pc * 16, pk);
     if (cls_thread) {                                 // raw logits of the CLS row; normalised once the row is complete
+        // eight 16-byte stores (entries past nvalid are never read back)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) cls_dst[j] = __uint_as_float(cur[j]);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) st_u4(cls_dst + j, make_uint4(cur[j], cur[j + 1], cur[j + 2], cur[j + 3]));
     }
 }
 
@@ -208,9 +209,9 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* v_full = bars + 4;
     uint64_t* v_empty = bars + 5;
     uint64_t* s_full = bars + 6;     // S(s) ready
-    uint64_t* p_full = bars + 7;     // P(s) stored by all softmax threads of the group
+    uint64_t* p_full = bars + 7;     // P(s) stored by all softmax warps of the group
     uint64_t* o_full = bars + 8;     // O of an item complete
-    uint64_t* o_empty = bars + 9;    // O of an item read out (all softmax threads of the group)
+    uint64_t* o_empty = bars + 9;    // O of an item read out (all softmax warps of the group)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + GROUPS * BARS_PER_GROUP * 8);
     uint8_t* gsm = smem + g * GROUP_BYTES;
 
@@ -223,8 +224,12 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool has_bias = p.key_bias != nullptr;
     const int D = H * HD;
     const uint32_t kv_bytes = static_cast<uint32_t>(KB) * 128u;
+    // With an even number of query tiles per (image, head) the tile index of `first + i * stride` would be the same for every
+    // i, i.e. at 197 tokens group 0 would own all the full tiles (128 rows + the CLS row duty) and group 1 all the 69-row
+    // ones: the two groups of a CTA swap the members of their item pair on odd iterations instead.
+    const int pair_swap = (qtiles & 1) ? 0 : 1;
     auto decode = [&](int i, int& b, int& h, int& qt) {
-        int it = first + i * stride;
+        int it = (first + i * stride) ^ (i & pair_swap);
         if (p.reverse) it = n_items - 1 - it;
         qt = it % qtiles;
         const int bh = it / qtiles;
@@ -238,7 +243,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tma_prefetch_desc(&tmKV);
             uint64_t* all = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
             for (int gg = 0; gg < GROUPS; ++gg)
-                for (int i = 0; i < BARS_PER_GROUP; ++i) mbar_init(all + gg * BARS_PER_GROUP + i, (i == 7 || i == 9) ? GROUP_WARPS * 32 : 1);
+                for (int i = 0; i < BARS_PER_GROUP; ++i) mbar_init(all + gg * BARS_PER_GROUP + i, (i == 7 || i == 9) ? GROUP_WARPS : 1);      // p_full, o_empty: one arrival per softmax warp
             fence_barrier_init();
         }
         __syncwarp();
@@ -325,7 +330,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     // item's S also covers the O columns, which the softmax warps must have read out first
                     unsigned long long* tr = (p.trace && step < 64) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + step) * (SM_WARPS + GROUPS) + SM_WARPS + g) * 8 : nullptr;
                     auto stamp = [&](int slot) {
-                        if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
+                        if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tr[slot] = tt; }
                     };
                     stamp(0);
                     if (j == 0 && i > 0) mbar_wait_fast(o_empty, (i - 1) & 1);
@@ -350,14 +355,14 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tc_fence_after();
                     stamp(5);
                     const int ksteps = nmma >> 4;
-                    int part = 0, pb = 0, pe = part_begin(1, nch);     // chunk range [pb, pe) of the column part that owns k-step ks
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        while ((ks >> 1) >= pe) { ++part; pb = pe; pe = part_begin(part + 1, nch); }
-                        // every part packs its bf16 P from (16 columns past) its own first S column on: chunk c of part q sits at
-                        // column 32 pb + 16 (c - pb) + 16
-                        umma_bf16_ts(tmem_base + O_COL, tmem_base + P_SHIFT + 8 * ks + pb * 16, make_smem_desc_sw128(v_addr + ks * 2048, 1024, 1024),
+                    // every part packs its bf16 P from (16 columns past) its own first S column on: chunk c of the part that starts at
+                    // chunk pb sits at column 32 pb + 16 (c - pb) + 16, i.e. k-step ks reads column 16 + 8 ks + 16 pb
+                    static_assert(PARTS == 2, "the P address below assumes two column parts");
+                    const int ks1 = 2 * part_begin(1, nch);                // first k-step of part 1
+                    const uint64_t vdesc = make_smem_desc_sw128(v_addr, 1024, 1024);
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma_bf16_ts(tmem_base + O_COL, tmem_base + P_SHIFT + 8 * ks + (ks >= ks1 ? 8 * ks1 : 0), vdesc + static_cast<uint64_t>(ks * (2048 >> 4)),
                                      idesc_o, (j | ks) != 0 ? 1u : 0u);
-                    }
                     umma_commit(v_empty);
                     if (j == nb - 1) umma_commit(o_full);
                 }
@@ -392,7 +397,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t t_p = t_s + c0 * 32 + P_SHIFT;                              // my P area: on top of S columns I have consumed
                 unsigned long long* tr = (p.trace && s < 64 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + s) * (SM_WARPS + GROUPS) + warp) * 8 : nullptr;
                 auto stamp = [&](int slot) {
-                    if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tr[slot] = tt; }
+                    if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tr[slot] = tt; }
                 };
                 stamp(0);
                 mbar_wait_fast(s_full, s & 1);
@@ -457,7 +462,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(p_full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
                 stamp(4);
             }
             if (cls_warp && part == 0) {
@@ -469,7 +475,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // ---- epilogue: O / rowsum -> bf16 (the other group owns the TMEM port meanwhile)
             unsigned long long* tre = (p.trace && s - 1 < 64 && lane == 0) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + (s - 1)) * (SM_WARPS + GROUPS) + warp) * 8 : nullptr;
             mbar_wait_fast(o_full, i & 1);
-            if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tre[5] = tt; }
+            if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tre[5] = tt; }
             tc_fence_after();
             if (warp_active) {
                 uint32_t o[OCOLS];
@@ -494,7 +500,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (part == 0 && row < N) p.einv[erow_idx] = inv;
                 }
                 tc_fence_before();
-                mbar_arrive(o_empty);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_empty);
                 if (row < N) {
                     __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * D + h * HD + part * OCOLS;
 #pragma unroll
@@ -506,10 +513,11 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             } else {
                 tc_fence_before();
-                mbar_arrive(o_empty);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_empty);
             }
             if (cls_warp) named_bar_sync(row_bar, 32 * PARTS);     // the CLS staging buffer may be overwritten by the next item
-            if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); tre[6] = tt; }
+            if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tre[6] = tt; }
         }
     }
     __syncwarp();
