@@ -88,3 +88,93 @@ def test_device_feeder_overlapped_ingest_equals_direct(env):
     out = PIPE.extract_cams_sharded(model, lambda lo, hi: torch.cat(host)[lo:hi].pin_memory(), 20, batch=6, with_rollout=False)
     ref = PIPE.extract_cams_sharded(model, lambda lo, hi: torch.cat(host)[lo:hi].to(dev), 20, batch=6, with_rollout=False)
     assert torch.equal(out["cam"], ref["cam"]) and out["cam"].shape[0] == 20
+
+
+# ---- VOC12 ingest and the utils.py callers ---------------------------------------------------------------
+@pytest.fixture(scope="module")
+def voc(tmp_path_factory):
+    from voc_fixture import make_voc_tree
+    root = str(tmp_path_factory.mktemp("voc"))
+    list_path, npy_path, labels = make_voc_tree(root)
+    return dict(root=root, list=list_path, npy=npy_path, labels=labels)
+
+
+def _reference_loader(voc, seg=False):
+    """The reference's own pipeline (validate.py:80-101): torchvision transforms -> normalised fp32 NCHW."""
+    from torchvision import transforms
+    from vision_transformer_cam_b200 import voc12
+    t = transforms.Compose([transforms.Resize([224, 224]), transforms.ToTensor(),
+                            transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+    ds = voc12.VOC12ClsDataset(voc["list"], voc["root"], transform=t, seg_label_flag=seg, cls_labels_path=voc["npy"])
+    # label maps keep their own sizes, so (like validate.py:101) the segmentation loader runs at batch 1
+    return torch.utils.data.DataLoader(ds, batch_size=1 if seg else 3, shuffle=False, num_workers=0)
+
+
+def test_u8_loader_feeds_the_forward_bit_exactly(env, voc):
+    """decode -> pinned uint8 HWC -> forward_cam_u8 == the reference transforms -> forward_cam, bit for bit."""
+    from vision_transformer_cam_b200 import voc12
+    u8_loader = voc12.make_u8_loader(voc["list"], voc["root"], batch_size=3, cls_labels_path=voc["npy"], num_workers=2)
+    n = 0
+    for (names_a, u8, lab_a), (names_b, x, lab_b) in zip(u8_loader, _reference_loader(voc)):
+        assert list(names_a) == list(names_b) and torch.equal(lab_a, lab_b) and u8.is_pinned()
+        a = env["model"].forward_cam_u8(u8.to(env["dev"], non_blocking=True))
+        b = env["model"].forward_cam(x.to(env["dev"]))
+        assert torch.equal(a.logits, b.logits) and torch.equal(a.hwp_logits, b.hwp_logits) and torch.equal(a.tokens_last, b.tokens_last)
+        n += len(names_a)
+    assert n == 6
+
+
+def test_evaluate_matches_sklearn_on_the_reference_pipeline(env, voc):
+    """utils.evaluate (device-side AP, uint8 ingest) == utils.py:205-262 restated: sigmoid of the 6-tuple's logits through
+    sklearn.average_precision_score per image, mean over images with a positive label."""
+    from sklearn.metrics import average_precision_score
+    from vision_transformer_cam_b200 import utils as U, voc12
+    got = U.evaluate(env["model"], voc12.make_u8_loader(voc["list"], voc["root"], batch_size=4, cls_labels_path=voc["npy"], num_workers=0),
+                     env["dev"], epoch=0, num_classes=20)
+    got_f32 = U.evaluate(env["model"], _reference_loader(voc, seg=True), env["dev"])       # 4-tuple items of the reference loader
+    ap196, ap16 = [], []
+    for name, image, target, seg in _reference_loader(voc, seg=True):
+        # forward_cam = the kernels evaluate runs (the 6-tuple forward goes through the full-P attention kernel, whose bf16-level
+        # differences can swap two nearly tied class scores)
+        out = env["model"].forward_cam(image.to(env["dev"]))
+        p196, p16 = torch.sigmoid(out.logits).cpu().numpy(), torch.sigmoid(out.hwp_logits).cpu().numpy()
+        for i in range(target.shape[0]):
+            if target[i].sum() > 0:
+                ap196.append(average_precision_score(target[i].numpy(), p196[i]))
+                ap16.append(average_precision_score(target[i].numpy(), p16[i]))
+    want = (float(np.mean(ap196)), float(np.mean(ap16)))
+    print("evaluate:", got, "reference restated:", want)
+    # the uint8 run batches 4 images (=> another batch-global mask max, vit_model.py:335, than at batch 1): AP is a rank
+    # statistic, equal unless two class scores nearly tie
+    assert abs(got_f32[0] - want[0]) < 1e-9 and abs(got_f32[1] - want[1]) < 1e-9
+    assert abs(got[0] - want[0]) < 0.05 and abs(got[1] - want[1]) < 0.05
+
+
+def test_teacher_cams_during_training(env, voc):
+    """The no-grad CAM pass used while training: works with the module in train() mode, leaves the mode alone, follows weight
+    updates (packed weights are refreshed), and its per-image maps follow utils.py:100-120."""
+    from vision_transformer_cam_b200 import utils as U, cam as CAM
+    import copy
+    model = copy.deepcopy(env["model"]).train()
+    x = env["VF"].make_images(40, 3).to(env["dev"])
+    labels = torch.zeros((3, 20))
+    labels[0, [2, 7]] = 1
+    labels[1, 14] = 1
+    labels[2, [0, 5, 19]] = 1
+    t = U.teacher_cams(model, x, labels, out_hw=(96, 128))
+    assert model.training and t["cam"].shape == (3, 20, 14, 14) and t["syn_cam"].shape == (3, 14, 14)
+    assert t["pseudo_label"].shape == (3, 96, 128) and t["pseudo_label"].dtype == torch.uint8
+    ref = env["model"].forward_cam(x)
+    assert torch.equal(t["logits"], ref.logits)
+    cam = CAM.classic_cam(ref.tokens_last, env["model"].head1.weight.data)
+    assert torch.equal(t["cam"], cam)
+    for i in range(3):
+        cls = torch.nonzero(labels[i]).flatten().to(env["dev"])
+        assert torch.equal(t["syn_cam"][i], cam[i, cls].amax(0))
+        present = set(torch.unique(t["pseudo_label"][i]).tolist())
+        assert present <= {0} | {int(c) + 1 for c in cls.tolist()}
+    # an optimiser step changes the maps
+    with torch.no_grad():
+        model.head1.weight.mul_(-1.0)
+    t2 = U.teacher_cams(model, x, labels)
+    assert not torch.equal(t2["cam"], t["cam"]) and torch.equal(t2["logits"], t["logits"]) and "pseudo_label" not in t2
