@@ -242,7 +242,7 @@ VTC_API int vtc_attention(const void* qkv, const float* key_bias, void* out, flo
 /* vtc_attention + the head mean of P, attn_mean [B,N,N] = mean_h P[b,h] (what the rollout consumes, predict.py:189-190),
  * without materialising [B,H,N,N] fp32: the kernel writes the bf16 exponentials it feeds to P.V and 1/rowsum into
  * `scratch` (256-byte aligned, >= vtc_attention_mean_scratch_bytes), a second kernel reduces them over the heads in a
- * fixed order.  n_tokens <= 208 (VTC_ERR_SHAPE otherwise: use vtc_attention's full P + vtc_head_mean). */
+ * fixed order.  Any n_tokens <= 2048. */
 VTC_API size_t vtc_attention_mean_scratch_bytes(int32_t batch, int32_t n_tokens, int32_t heads);
 VTC_API int vtc_attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch,
                        size_t scratch_bytes, int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream);

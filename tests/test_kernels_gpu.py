@@ -506,7 +506,8 @@ def test_layernorm_fused_gemms(dev, M):
         assert e < 8e-3 and e < 2.0 * e0 + 1e-3
 
 
-@pytest.mark.parametrize("B,N,H,masked", [(3, 197, 12, True), (2, 197, 12, False), (5, 50, 3, True), (2, 208, 2, False), (300, 197, 1, False)])
+@pytest.mark.parametrize("B,N,H,masked", [(3, 197, 12, True), (2, 197, 12, False), (5, 50, 3, True), (2, 208, 2, False), (300, 197, 1, False),
+                                          (2, 577, 16, True), (1, 785, 12, False), (2, 300, 3, True), (1, 1030, 2, True)])
 def test_attention_fused_head_mean(dev, B, N, H, masked):
     """Head mean of P from the packed bf16 P of the fast attention kernel (vtc_attention_mean: the rollout's input,
     predict.py:189-190) == mean over heads of the fp32 softmax; P enters as the bf16 values the P.V product uses, so the
@@ -527,3 +528,25 @@ def test_attention_fused_head_mean(dev, B, N, H, masked):
     assert relerr(out.float(), ref_o) < 1e-2 and float((cls - ref_p[:, :, 0, :]).abs().max()) < 5e-6
     out2, cls2, mean2 = ops.attention_mean(qkv, H, 0.125, key_bias=kb)
     assert torch.equal(mean, mean2) and torch.equal(out, out2)            # fixed accumulation order
+
+
+@pytest.mark.parametrize("N,amp", [(197, 12.0), (577, 6.0), (785, 12.0)])
+def test_attention_fused_head_mean_large_dynamic_range(dev, N, amp):
+    """Peaked logits: the running maximum rises by many octaves inside a row (within a key block and from block to block),
+    so chunks of the packed P are stored against different reference maxima; the head mean must still be the softmax's."""
+    from vision_transformer_cam_b200 import ops
+    B, H = 2, 4
+    qkv = _rand((B, N, 3 * H * 64), 120, dev, 1.0)
+    qkv[:, :, : 2 * H * 64] *= amp
+    qkv = qkv.bfloat16()
+    g = torch.Generator().manual_seed(121)
+    kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+    kb[:, 0] = 0
+    kb = kb.to(dev)
+    for bias in (None, kb):
+        ref_o, ref_p = _attn_ref(qkv, H, 0.125, bias)
+        out, cls, mean = ops.attention_mean(qkv, H, 0.125, key_bias=bias)
+        ref_m = ref_p.mean(1)
+        assert float((mean - ref_m).abs().max()) <= 1e-2 * float(ref_m.max()), float((mean - ref_m).abs().max())
+        assert float((mean.sum(-1) - 1).abs().max()) < 5e-3
+        assert relerr(out.float(), ref_o) < 1.5e-2

@@ -449,86 +449,106 @@ int head_mean(const float* attn_in, float* mean, int batch, int heads, int n_tok
     return VTC_OK;
 }
 
-// ---- head mean of the packed P written by attention_cs: mean[b,r,:] = 1/H sum_h einv[b,h,r] * E[b,h,r,:] ------------------
-// One warp per (image, query row); a lane owns 8 consecutive keys (one 16-byte load per head).  Heads are added in order,
-// so the result is bit-reproducible.  The row leaves through a per-warp staging line because [B,N,N] rows (N odd) are not
-// 16-byte aligned: the global stores are 32 consecutive floats per instruction.
+// ---- head mean of the packed P written by attention_cs ---------------------------------------------------------------
+//   mean[b,r,k] = 1/H sum_h einv[b,h,r] * 2^(mtab[b,h,r,k/32] - mfin[b,h,r]) * E[b,h,r,k]
+// One warp per (image, query row); per 256-key segment a lane owns 8 consecutive keys (one 16-byte load per head).  Heads
+// are added in order, so the result is bit-reproducible.  A segment leaves through a per-warp staging line because
+// [B,N,N] rows (N odd) are not 16-byte aligned: the global stores are 32 consecutive floats per instruction.
 constexpr int HMP_WARPS = 8;
 __global__ void __launch_bounds__(HMP_WARPS * 32)
-head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ einv, float* __restrict__ mean, int B, int H, int N, int lde) {
-    __shared__ float stage[HMP_WARPS][264];
+head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ mtab, const float* __restrict__ mfin,
+                        const float* __restrict__ einv, float* __restrict__ mean, int B, int H, int N, int ld) {
+    __shared__ float stage[HMP_WARPS][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int vec_per_row = lde >> 3;                    // uint4 per row, <= 32
+    const int vec_per_row = ld >> 3;                     // uint4 per row
+    const int chunks_per_row = ld >> 5;
     const int nrows = B * N;
     const float invh = 1.0f / static_cast<float>(H);
     float* st = stage[warp];
     for (int rid = blockIdx.x * HMP_WARPS + warp; rid < nrows; rid += gridDim.x * HMP_WARPS) {
         const int b = rid / N, r = rid - b * N;
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         const size_t row0 = static_cast<size_t>(b) * H * N + r;          // (b, h = 0, r); + h * N per head
-        if (lane < vec_per_row) {
+        float* dst = mean + static_cast<size_t>(rid) * N;
+        for (int seg = 0; seg * 256 < N; ++seg) {
+            const int v = seg * 32 + lane;                // my uint4 of the row; keys 8 v .. 8 v + 7, chunk v / 4
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            if (v < vec_per_row) {
 #pragma unroll 4
-            for (int h = 0; h < H; ++h) {
-                const size_t row = row0 + static_cast<size_t>(h) * N;
-                const float w = __ldg(einv + row);
-                const uint4 v = ld_stream_u4(e + row * vec_per_row + lane);
-                acc[0] = fmaf(w, __uint_as_float(v.x << 16), acc[0]);
-                acc[1] = fmaf(w, __uint_as_float(v.x & 0xffff0000u), acc[1]);
-                acc[2] = fmaf(w, __uint_as_float(v.y << 16), acc[2]);
-                acc[3] = fmaf(w, __uint_as_float(v.y & 0xffff0000u), acc[3]);
-                acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]);
-                acc[5] = fmaf(w, __uint_as_float(v.z & 0xffff0000u), acc[5]);
-                acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]);
-                acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
+                for (int h = 0; h < H; ++h) {
+                    const size_t row = row0 + static_cast<size_t>(h) * N;
+                    const float w = __ldg(einv + row) * exp2f(__ldg(mtab + row * chunks_per_row + (v >> 2)) - __ldg(mfin + row));
+                    const uint4 q = ld_stream_u4(e + row * vec_per_row + v);
+                    acc[0] = fmaf(w, __uint_as_float(q.x << 16), acc[0]);
+                    acc[1] = fmaf(w, __uint_as_float(q.x & 0xffff0000u), acc[1]);
+                    acc[2] = fmaf(w, __uint_as_float(q.y << 16), acc[2]);
+                    acc[3] = fmaf(w, __uint_as_float(q.y & 0xffff0000u), acc[3]);
+                    acc[4] = fmaf(w, __uint_as_float(q.z << 16), acc[4]);
+                    acc[5] = fmaf(w, __uint_as_float(q.z & 0xffff0000u), acc[5]);
+                    acc[6] = fmaf(w, __uint_as_float(q.w << 16), acc[6]);
+                    acc[7] = fmaf(w, __uint_as_float(q.w & 0xffff0000u), acc[7]);
+                }
             }
             float4* s4 = reinterpret_cast<float4*>(st + lane * 8);
             s4[0] = make_float4(acc[0] * invh, acc[1] * invh, acc[2] * invh, acc[3] * invh);
             s4[1] = make_float4(acc[4] * invh, acc[5] * invh, acc[6] * invh, acc[7] * invh);
+            __syncwarp();
+            const int nseg = min(256, N - seg * 256);
+            for (int c = lane; c < nseg; c += 32) dst[seg * 256 + c] = st[c];
+            __syncwarp();
         }
-        __syncwarp();
-        float* dst = mean + static_cast<size_t>(rid) * N;
-        for (int c = lane; c < N; c += 32) dst[c] = st[c];
-        __syncwarp();
     }
 }
 
-int head_mean_packed(const void* e, const float* einv, float* mean, int batch, int heads, int n_tokens, int lde, cudaStream_t stream) {
-    VTC_REQUIRE(e && einv && mean, VTC_ERR_ARG, "head_mean_packed: null pointer");
-    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0 && lde >= n_tokens && lde % 8 == 0 && lde <= 256, VTC_ERR_SHAPE, "head_mean_packed: bad shape");
+int head_mean_packed(const PackedP& pk, float* mean, int batch, int heads, int n_tokens, int ld, cudaStream_t stream) {
+    VTC_REQUIRE(pk.e && pk.mtab && pk.mfin && pk.einv && mean, VTC_ERR_ARG, "head_mean_packed: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0 && ld >= n_tokens && ld % 32 == 0, VTC_ERR_SHAPE, "head_mean_packed: bad shape");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     const int nrows = batch * n_tokens;
     int blocks = cdiv(nrows, HMP_WARPS);
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    head_mean_packed_kernel<<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(e), einv, mean, batch, heads, n_tokens, lde);
+    head_mean_packed_kernel<<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(pk.e), pk.mtab, pk.mfin, pk.einv, mean, batch, heads,
+                                                                  n_tokens, ld);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
 
-static size_t packed_e_bytes(int batch, int n_tokens, int heads) {
-    return align_up(static_cast<size_t>(batch) * heads * n_tokens * attention_packed_ld(n_tokens) * 2, 256);
+// scratch layout of attention_mean: E | mtab | mfin | einv, every segment 256-byte aligned
+static PackedP carve_packed(void* scratch, int batch, int n_tokens, int heads, size_t* total) {
+    const size_t rows = static_cast<size_t>(batch) * heads * n_tokens, ld = attention_packed_ld(n_tokens);
+    uint8_t* base = static_cast<uint8_t*>(scratch);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* q = base ? base + off : nullptr; off += align_up(bytes, 256); return q; };
+    PackedP pk;
+    pk.e = take(rows * ld * 2);
+    pk.mtab = reinterpret_cast<float*>(take(rows * (ld / 32) * 4));
+    pk.mfin = reinterpret_cast<float*>(take(rows * 4));
+    pk.einv = reinterpret_cast<float*>(take(rows * 4));
+    *total = off;
+    return pk;
 }
 size_t attention_mean_scratch_bytes(int batch, int n_tokens, int heads) {
     if (batch <= 0 || n_tokens <= 0 || heads <= 0) return 0;
-    return packed_e_bytes(batch, n_tokens, heads) + align_up(static_cast<size_t>(batch) * heads * n_tokens * 4, 256);
+    size_t total = 0;
+    carve_packed(nullptr, batch, n_tokens, heads, &total);
+    return total;
 }
 
 int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
                    int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse) {
     VTC_REQUIRE(qkv && out && attn_mean && scratch, VTC_ERR_ARG, "attention_mean: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention_mean: bad shape");
-    VTC_REQUIRE(n_tokens <= kAttentionFusedMeanMaxTokens, VTC_ERR_SHAPE, "attention_mean: %d tokens > %d (use the full P of vtc_attention + vtc_head_mean)",
-                n_tokens, kAttentionFusedMeanMaxTokens);
+    VTC_REQUIRE(n_tokens <= kAttentionFusedMeanMaxTokens, VTC_ERR_SHAPE, "attention_mean: %d tokens > %d", n_tokens, kAttentionFusedMeanMaxTokens);
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, VTC_ERR_WORKSPACE, "attention_mean: scratch must be 256-byte aligned");
-    VTC_REQUIRE(scratch_bytes >= attention_mean_scratch_bytes(batch, n_tokens, heads), VTC_ERR_WORKSPACE, "attention_mean: scratch %zu bytes < required %zu",
-                scratch_bytes, attention_mean_scratch_bytes(batch, n_tokens, heads));
-    float* einv = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + packed_e_bytes(batch, n_tokens, heads));
-    int rc = attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, scratch, einv);
+    size_t need = 0;
+    const PackedP pk = carve_packed(scratch, batch, n_tokens, heads, &need);
+    VTC_REQUIRE(scratch_bytes >= need, VTC_ERR_WORKSPACE, "attention_mean: scratch %zu bytes < required %zu", scratch_bytes, need);
+    int rc = attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, &pk);
     if (rc != VTC_OK) return rc;
-    return head_mean_packed(scratch, einv, attn_mean, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream);
+    return head_mean_packed(pk, attn_mean, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream);
 }
 
 }  // namespace vtc

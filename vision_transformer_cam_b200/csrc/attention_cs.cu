@@ -75,12 +75,16 @@ struct Params {
     const float* key_bias;   // [B,N] or null
     __nv_bfloat16* out;      // [B,N,H*64]
     float* cls_rows;         // [B,H,N] or null
-    // Head-mean support (single-block N only): the un-normalised bf16 exponentials E the P V product consumed, exactly as
-    // they sit in TMEM, and 1 / rowsum -- P[b,h,r,:] = einv[b,h,r] * E[b,h,r,:].  head_mean_packed() reduces them over the
-    // heads; [B,H,N,N] fp32 is never written.
+    // Head-mean support ("packed P"): the un-normalised bf16 exponentials E the P V product consumes, stored as they are
+    // produced, 32-key chunk by chunk, together with the running maximum each chunk was taken against (the maximum may rise
+    // later; the copies in TMEM are rescaled then, the stored ones keep their own reference), the final maximum and
+    // 1 / rowsum:  P[b,h,r,k] = einv[b,h,r] * 2^(mtab[b,h,r,k/32] - mfin[b,h,r]) * E[b,h,r,k].
+    // head_mean_packed() reduces that over the heads; [B,H,N,N] fp32 is never written.
     __nv_bfloat16* edump;    // [B,H,N,lde] or null
+    float* mtab;             // [B,H,N,lde/32]
+    float* mfin;             // [B,H,N]
     float* einv;             // [B,H,N]
-    int lde;                 // 32 * number of key chunks
+    int lde;                 // keys per stored row: nb * KB rounded up to 32
     int B, N, H;
     int KB, nb;
     float scale, scale_log2;
@@ -127,7 +131,7 @@ __device__ __forceinline__ void rescale_f16(uint32_t taddr, float f) {
 // One 32-key chunk: cur = raw accumulator values of this thread's row.  t_p = TMEM address of this warp's P area of the
 // block, pc = index of the chunk inside that area (chunks [0, pc) are already stored there).
 __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nvalid, float sc, float& m, uint64_t& sum2, uint32_t t_p,
-                                      float* cls_dst, bool cls_thread) {
+                                      float* cls_dst, bool cls_thread, __nv_bfloat16* edst, float* mdst) {
     float mc = -INFINITY;
     if (nvalid >= 32) {
 #pragma unroll
@@ -185,6 +189,11 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
         }
     }
     tmem_st_32x32b_x16(t_p + pc * 16, pk);
+    if (edst != nullptr) {                            // packed P: 64 contiguous bytes of this row + the chunk's reference maximum
+        st_u8(edst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+        st_u8(edst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+        *mdst = m;
+    }
     if (cls_thread) {                                 // raw logits of the CLS row; normalised once the row is complete
         // eight 16-byte stores (entries past nvalid are never read back)
 #pragma unroll
@@ -390,6 +399,9 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float m = 0.f;
             uint64_t sum2 = pack2(0.f, 0.f);
             float inv = 0.f;
+            const size_t erow_idx = (static_cast<size_t>(b) * H + h) * N + row;
+            __nv_bfloat16* erow = (p.edump != nullptr && row < N) ? p.edump + erow_idx * p.lde : nullptr;
+            float* mrow = erow ? p.mtab + erow_idx * (p.lde >> 5) : nullptr;
             for (int j = 0; j < nb; ++j, ++s) {
                 const int vj = min(KB, N - j * KB);
                 const int nch = (vj + 31) >> 5;
@@ -423,7 +435,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         if (nvalid > 16) tmem_ld_32x32b_x32(t_s + c * 32, cur);
                         else tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
                         tmem_ld_wait();
-                        chunk(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread);
+                        chunk(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
+                              erow ? erow + j * KB + c * 32 : nullptr, mrow ? mrow + ((j * KB) >> 5) + c : nullptr);
                     }
                     stamp(2);
                     // ---- the warps that share these rows agree on the row maximum (and, at the end, on the row sum)
@@ -481,23 +494,9 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 uint32_t o[OCOLS];
                 tmem_ld_cols(t_s + O_COL + part * OCOLS, o);
                 tmem_ld_wait();
-                if (p.edump != nullptr) {
-                    // the bf16 exponentials of my column range are still in TMEM (P V has retired): one 64-byte row segment per
-                    // 32-key chunk, two full 32-byte sectors per lane
-                    const int nch = (N + 31) >> 5;
-                    const int c0 = part_begin(part, nch), c1 = part_begin(part + 1, nch);
-                    const size_t erow_idx = (static_cast<size_t>(b) * H + h) * N + (row < N ? row : 0);
-                    __nv_bfloat16* erow = p.edump + erow_idx * p.lde + c0 * 32;
-                    for (int pc = 0; pc < c1 - c0; ++pc) {
-                        uint32_t q[16];
-                        tmem_ld_32x32b_x16(t_s + c0 * 32 + P_SHIFT + pc * 16, q);
-                        tmem_ld_wait();
-                        if (row < N) {
-                            st_u8(erow + pc * 32, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
-                            st_u8(erow + pc * 32 + 16, q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
-                        }
-                    }
-                    if (part == 0 && row < N) p.einv[erow_idx] = inv;
+                if (erow != nullptr && part == 0) {
+                    p.einv[erow_idx] = inv;
+                    p.mfin[erow_idx] = m;
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -528,22 +527,25 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }  // namespace acs
 
 int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
-                 cudaStream_t stream, int reverse, void* edump, float* einv) {
+                 cudaStream_t stream, int reverse, const PackedP* packed) {
     using namespace acs;
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
     VTC_REQUIRE(n_tokens <= NMAX, VTC_ERR_SHAPE, "attention: %d tokens > %d", n_tokens, NMAX);
-    VTC_REQUIRE(edump == nullptr || (n_tokens <= KBMAX && einv != nullptr), VTC_ERR_SHAPE, "attention: the packed-P output needs n_tokens <= %d", KBMAX);
+    VTC_REQUIRE(packed == nullptr || (packed->e && packed->mtab && packed->mfin && packed->einv), VTC_ERR_ARG, "attention: incomplete packed-P output");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     Params p{};
     p.key_bias = key_bias;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.cls_rows = cls_rows;
-    p.edump = static_cast<__nv_bfloat16*>(edump);
-    p.einv = einv;
-    p.lde = attention_packed_ld(n_tokens);
+    if (packed) {
+        p.edump = static_cast<__nv_bfloat16*>(packed->e);
+        p.mtab = packed->mtab;
+        p.mfin = packed->mfin;
+        p.einv = packed->einv;
+    }
     p.B = batch;
     p.N = n_tokens;
     p.H = heads;
@@ -554,6 +556,8 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
         p.nb = cdiv(n_tokens, KBLONG);
         p.KB = (cdiv(n_tokens, p.nb) + 31) & ~31;
     }
+    p.lde = attention_packed_ld(n_tokens);
+    VTC_REQUIRE(p.lde == (p.nb == 1 ? ((n_tokens + 31) & ~31) : p.nb * p.KB), VTC_ERR_SHAPE, "attention: packed-P row stride out of sync with the key blocking");
     p.scale = scale;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.reverse = reverse;

@@ -49,8 +49,8 @@ static size_t packed_bytes(const vtc_model* m) {
     return seg(D * m->KP, eb) + m->L * (seg(3 * D * D, eb) + seg(D * D, eb) + 2 * seg(HID * D, eb) + fold);
 }
 
-// short sequences, bf16 mode: the head mean of P comes from the packed bf16 P of the fast attention kernel
-// (attention_mean, attention.cu) instead of a [B,H,N,N] fp32 round trip
+// bf16 mode: the head mean of P comes from the packed bf16 P of the fast attention kernel (attention_mean, attention.cu)
+// instead of a [B,H,N,N] fp32 round trip
 static bool fused_mean_ok(const vtc_model* m) {
     static const bool off = []() { const char* e = getenv("VTC_NO_FUSED_MEAN"); return e && e[0] == '1'; }();
     return !off && !m->split && m->N <= kAttentionFusedMeanMaxTokens;

@@ -28,22 +28,35 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* 
                    int split = 0, int reverse = 0);
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
               float scale, cudaStream_t stream, int reverse = 0);
-// Attention + head mean of P (the rollout's input, predict.py:189-190) without a [B,H,N,N] fp32 round trip, n_tokens <=
-// kAttentionFusedMeanMaxTokens: the fast kernel dumps the bf16 exponentials it feeds to P V and 1 / rowsum into `scratch`
+// Attention + head mean of P (the rollout's input, predict.py:189-190) without a [B,H,N,N] fp32 round trip, any n_tokens the
+// fast kernel serves: it stores the bf16 exponentials it feeds to P V ("packed P", see attention_cs.cu) into `scratch`
 // (attention_mean_scratch_bytes), head_mean_packed reduces them over the heads into attn_mean [B,N,N].
-constexpr int kAttentionFusedMeanMaxTokens = 208;
-inline int attention_packed_ld(int n_tokens) { return ((n_tokens + 31) / 32) * 32; }
+struct PackedP {
+    void* e;        // bf16 [B,H,N,ld]
+    float* mtab;    // [B,H,N,ld/32]: reference maximum of every 32-key chunk (log2 domain)
+    float* mfin;    // [B,H,N]: final row maximum
+    float* einv;    // [B,H,N]: 1 / row sum (relative to mfin)
+};
+constexpr int kAttentionFusedMeanMaxTokens = 2048;
+constexpr int kAttentionSingleBlockKeys = 208;     // attention_cs: whole sequence in one key block up to here,
+constexpr int kAttentionLongBlockKeys = 192;       // blocks of at most this many keys beyond
+// keys per stored row of the packed P = the key blocking of attention_cs rounded to whole 32-key chunks
+inline int attention_packed_ld(int n_tokens) {
+    if (n_tokens <= kAttentionSingleBlockKeys) return ((n_tokens + 31) / 32) * 32;
+    const int nb = (n_tokens + kAttentionLongBlockKeys - 1) / kAttentionLongBlockKeys;
+    return nb * ((((n_tokens + nb - 1) / nb) + 31) / 32 * 32);
+}
 size_t attention_mean_scratch_bytes(int batch, int n_tokens, int heads);
 int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
                    int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse = 0);
-int head_mean_packed(const void* e, const float* einv, float* mean, int batch, int heads, int n_tokens, int lde, cudaStream_t stream);
+int head_mean_packed(const PackedP& packed, float* mean, int batch, int heads, int n_tokens, int ld, cudaStream_t stream);
 // KV-blocked kernel (attention_kv.cu): any n_tokens <= 2048; split = (hi, lo) bf16 operands: qkv [B,N,2,3,H,64], out [B*N,2,H*64]
 int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
                  float scale, bool split, cudaStream_t stream, int reverse = 0);
 // column-split pipelined kernel (attention_cs.cu): the fast path when the full P is not requested, any n_tokens <= 2048
-// edump [B,H,N,attention_packed_ld(N)] bf16 + einv [B,H,N] or null: the packed P of attention_mean (n_tokens <= 208 only)
+// packed: optional packed-P output (row stride attention_packed_ld(N)) for attention_mean
 int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
-                 cudaStream_t stream, int reverse = 0, void* edump = nullptr, float* einv = nullptr);
+                 cudaStream_t stream, int reverse = 0, const PackedP* packed = nullptr);
 unsigned long long* attention_trace_buffer();   // debug: device buffer for %globaltimer stamps (vtc_debug_set_attention_trace) or null
 int head_mean(const float* attn, float* mean, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream);
