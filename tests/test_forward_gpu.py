@@ -280,3 +280,31 @@ def test_ln_fused_forward_matches_reference_golden(tmp_path):
     r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600, env={**os.environ, "VTC_LN_FUSION": "1"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "LNFUSED" in r.stdout
+
+
+def test_cuda_graph_replay_equals_eager_and_follows_weight_updates(env):
+    """forward_cam_graphed (the launch-bound batch-1 path of predict.py / validate.py): bit-identical to the eager forward,
+    for new inputs, after a weight update (packed copies refreshed before the replay), for uint8 input, and per signature."""
+    model = load(env, "peaked")
+    dev = env["dev"]
+    for B in (1, 3):
+        for seed in (0, 1, 2):
+            x = env["VF"].make_images(50 + seed, B).to(dev)
+            g = model.forward_cam_graphed(x, attn_mean=True)
+            got = {k: getattr(g, k).clone() for k in ("logits", "hwp_logits", "hwp_tokens", "tokens", "cls_rows", "attn_mean")}
+            e = model.forward_cam(x, attn_mean=True)
+            for k, v in got.items():
+                assert torch.equal(v, getattr(e, k)), (B, seed, k)
+    assert len(model._engine.graphs) == 2
+    # in-place weight update (what an optimiser step or load_state_dict does): same storage, new version
+    x = env["VF"].make_images(60, 1).to(dev)
+    before = model.forward_cam_graphed(x, attn_mean=True).logits.clone()
+    model = load(env, "default")
+    after = model.forward_cam_graphed(x, attn_mean=True).logits.clone()
+    assert not torch.equal(before, after) and torch.equal(after, model.forward_cam(x).logits)
+    assert len(model._engine.graphs) == 2                       # replayed, not re-captured
+    # uint8 ingest through the same mechanism
+    u8 = torch.randint(0, 256, (1, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).to(dev)
+    assert torch.equal(model.forward_cam_graphed(u8).logits, model.forward_cam_u8(u8).logits)
+    with pytest.raises(ValueError):
+        model.forward_cam_graphed(x, forced_topk=torch.zeros((1, 16), dtype=torch.int32))
