@@ -450,11 +450,13 @@ int head_mean(const float* attn_in, float* mean, int batch, int heads, int n_tok
 }
 
 // ---- head mean of the packed P written by attention_cs ---------------------------------------------------------------
-//   mean[b,r,k] = 1/H sum_h einv[b,h,r] * 2^(mtab[b,h,r,k/32] - mfin[b,h,r]) * E[b,h,r,k]
+//   mean[b,r,k] = 1/H sum_h einv[b,h,r] * 2^(mtab[b,h,r,k/32] - mfin[b,h,r]) * E[b,h,r,k]      (MTAB: several key blocks)
+//   mean[b,r,k] = 1/H sum_h einv[b,h,r] * E[b,h,r,k]                                             (one key block)
 // One warp per (image, query row); per 256-key segment a lane owns 8 consecutive keys (one 16-byte load per head).  Heads
 // are added in order, so the result is bit-reproducible.  A segment leaves through a per-warp staging line because
 // [B,N,N] rows (N odd) are not 16-byte aligned: the global stores are 32 consecutive floats per instruction.
 constexpr int HMP_WARPS = 8;
+template <bool MTAB>
 __global__ void __launch_bounds__(HMP_WARPS * 32)
 head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ mtab, const float* __restrict__ mfin,
                         const float* __restrict__ einv, float* __restrict__ mean, int B, int H, int N, int ld) {
@@ -475,19 +477,30 @@ head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ m
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
             if (v < vec_per_row) {
-#pragma unroll 4
-                for (int h = 0; h < H; ++h) {
-                    const size_t row = row0 + static_cast<size_t>(h) * N;
-                    const float w = __ldg(einv + row) * exp2f(__ldg(mtab + row * chunks_per_row + (v >> 2)) - __ldg(mfin + row));
-                    const uint4 q = ld_stream_u4(e + row * vec_per_row + v);
-                    acc[0] = fmaf(w, __uint_as_float(q.x << 16), acc[0]);
-                    acc[1] = fmaf(w, __uint_as_float(q.x & 0xffff0000u), acc[1]);
-                    acc[2] = fmaf(w, __uint_as_float(q.y << 16), acc[2]);
-                    acc[3] = fmaf(w, __uint_as_float(q.y & 0xffff0000u), acc[3]);
-                    acc[4] = fmaf(w, __uint_as_float(q.z << 16), acc[4]);
-                    acc[5] = fmaf(w, __uint_as_float(q.z & 0xffff0000u), acc[5]);
-                    acc[6] = fmaf(w, __uint_as_float(q.w << 16), acc[6]);
-                    acc[7] = fmaf(w, __uint_as_float(q.w & 0xffff0000u), acc[7]);
+                // four heads per batch: all eight loads are issued before the first fused multiply-add consumes one
+                for (int h0 = 0; h0 < H; h0 += 4) {
+                    float w[4];
+                    uint4 q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool ok = h0 + u < H;
+                        const size_t row = row0 + static_cast<size_t>(ok ? h0 + u : H - 1) * N;
+                        w[u] = __ldg(einv + row);
+                        if (MTAB) w[u] *= exp2f(__ldg(mtab + row * chunks_per_row + (v >> 2)) - __ldg(mfin + row));
+                        if (!ok) w[u] = 0.f;
+                        q[u] = ld_stream_u4(e + row * vec_per_row + v);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[0] = fmaf(w[u], __uint_as_float(q[u].x << 16), acc[0]);
+                        acc[1] = fmaf(w[u], __uint_as_float(q[u].x & 0xffff0000u), acc[1]);
+                        acc[2] = fmaf(w[u], __uint_as_float(q[u].y << 16), acc[2]);
+                        acc[3] = fmaf(w[u], __uint_as_float(q[u].y & 0xffff0000u), acc[3]);
+                        acc[4] = fmaf(w[u], __uint_as_float(q[u].z << 16), acc[4]);
+                        acc[5] = fmaf(w[u], __uint_as_float(q[u].z & 0xffff0000u), acc[5]);
+                        acc[6] = fmaf(w[u], __uint_as_float(q[u].w << 16), acc[6]);
+                        acc[7] = fmaf(w[u], __uint_as_float(q[u].w & 0xffff0000u), acc[7]);
+                    }
                 }
             }
             float4* s4 = reinterpret_cast<float4*>(st + lane * 8);
@@ -502,7 +515,7 @@ head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ m
 }
 
 int head_mean_packed(const PackedP& pk, float* mean, int batch, int heads, int n_tokens, int ld, cudaStream_t stream) {
-    VTC_REQUIRE(pk.e && pk.mtab && pk.mfin && pk.einv && mean, VTC_ERR_ARG, "head_mean_packed: null pointer");
+    VTC_REQUIRE(pk.e && pk.einv && mean && ((pk.mtab == nullptr) == (pk.mfin == nullptr)), VTC_ERR_ARG, "head_mean_packed: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0 && ld >= n_tokens && ld % 32 == 0, VTC_ERR_SHAPE, "head_mean_packed: bad shape");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
@@ -510,8 +523,10 @@ int head_mean_packed(const PackedP& pk, float* mean, int batch, int heads, int n
     int blocks = cdiv(nrows, HMP_WARPS);
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    head_mean_packed_kernel<<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(pk.e), pk.mtab, pk.mfin, pk.einv, mean, batch, heads,
-                                                                  n_tokens, ld);
+    if (pk.mtab) head_mean_packed_kernel<true><<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(pk.e), pk.mtab, pk.mfin, pk.einv, mean,
+                                                                                     batch, heads, n_tokens, ld);
+    else head_mean_packed_kernel<false><<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(pk.e), nullptr, nullptr, pk.einv, mean, batch,
+                                                                               heads, n_tokens, ld);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
@@ -523,10 +538,11 @@ static PackedP carve_packed(void* scratch, int batch, int n_tokens, int heads, s
     size_t off = 0;
     auto take = [&](size_t bytes) { uint8_t* q = base ? base + off : nullptr; off += align_up(bytes, 256); return q; };
     PackedP pk;
+    const bool multi = n_tokens > kAttentionSingleBlockKeys;      // several key blocks: per-chunk reference maxima (attention_cs.cu)
     pk.e = take(rows * ld * 2);
-    pk.mtab = reinterpret_cast<float*>(take(rows * (ld / 32) * 4));
-    pk.mfin = reinterpret_cast<float*>(take(rows * 4));
     pk.einv = reinterpret_cast<float*>(take(rows * 4));
+    pk.mtab = multi ? reinterpret_cast<float*>(take(rows * (ld / 32) * 4)) : nullptr;
+    pk.mfin = multi ? reinterpret_cast<float*>(take(rows * 4)) : nullptr;
     *total = off;
     return pk;
 }

@@ -75,11 +75,14 @@ struct Params {
     const float* key_bias;   // [B,N] or null
     __nv_bfloat16* out;      // [B,N,H*64]
     float* cls_rows;         // [B,H,N] or null
-    // Head-mean support ("packed P"): the un-normalised bf16 exponentials E the P V product consumes, stored as they are
-    // produced, 32-key chunk by chunk, together with the running maximum each chunk was taken against (the maximum may rise
-    // later; the copies in TMEM are rescaled then, the stored ones keep their own reference), the final maximum and
-    // 1 / rowsum:  P[b,h,r,k] = einv[b,h,r] * 2^(mtab[b,h,r,k/32] - mfin[b,h,r]) * E[b,h,r,k].
-    // head_mean_packed() reduces that over the heads; [B,H,N,N] fp32 is never written.
+    // Head-mean support ("packed P"): the un-normalised bf16 exponentials E the P V product consumes and 1 / rowsum;
+    // head_mean_packed() reduces them over the heads, [B,H,N,N] fp32 is never written.
+    //  * one key block (N <= 208): E is copied out of TMEM once the row is complete (P V has retired; every chunk is
+    //    relative to the final maximum by then): P[b,h,r,k] = einv[b,h,r] * E[b,h,r,k]; mtab / mfin are not used;
+    //  * several key blocks: a block's P is overwritten by the next block's scores, so every 32-key chunk is stored as it is
+    //    produced, together with the running maximum it was taken against (the maximum may rise later; the copies in TMEM
+    //    are rescaled then, the stored ones keep their own reference), and the final maximum follows per row:
+    //    P[b,h,r,k] = einv[b,h,r] * 2^(mtab[b,h,r,k/32] - mfin[b,h,r]) * E[b,h,r,k].
     __nv_bfloat16* edump;    // [B,H,N,lde] or null
     float* mtab;             // [B,H,N,lde/32]
     float* mfin;             // [B,H,N]
@@ -130,6 +133,7 @@ __device__ __forceinline__ void rescale_f16(uint32_t taddr, float f) {
 
 // One 32-key chunk: cur = raw accumulator values of this thread's row.  t_p = TMEM address of this warp's P area of the
 // block, pc = index of the chunk inside that area (chunks [0, pc) are already stored there).
+template <bool DUMP>      // DUMP: store the chunk of the packed P as it is produced (multi-block sequences)
 __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nvalid, float sc, float& m, uint64_t& sum2, uint32_t t_p,
                                       float* cls_dst, bool cls_thread, __nv_bfloat16* edst, float* mdst) {
     float mc = -INFINITY;
@@ -189,10 +193,12 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
         }
     }
     tmem_st_32x32b_x16(t_p + pc * 16, pk);
-    if (edst != nullptr) {                            // packed P: 64 contiguous bytes of this row + the chunk's reference maximum
-        st_u8(edst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-        st_u8(edst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
-        *mdst = m;
+    if constexpr (DUMP) {
+        if (edst != nullptr) {                        // packed P: 64 contiguous bytes of this row + the chunk's reference maximum
+            st_u8(edst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            st_u8(edst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            *mdst = m;
+        }
     }
     if (cls_thread) {                                 // raw logits of the CLS row; normalised once the row is complete
         // eight 16-byte stores (entries past nvalid are never read back)
@@ -202,6 +208,11 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
     }
 }
 
+// DUMP: the instantiation that also stores the packed P (kept apart: the extra pointers cost the plain kernel, which sits at
+// its register cap, 6 % when they were a run-time option)
+// SINGLE: the whole sequence is one key block (nb == 1, up to 208 tokens): the block loops and the cross-block rescale of O
+// fold away at compile time.
+template <bool DUMP, bool SINGLE>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -224,7 +235,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + GROUPS * BARS_PER_GROUP * 8);
     uint8_t* gsm = smem + g * GROUP_BYTES;
 
-    const int N = p.N, H = p.H, KB = p.KB, nb = p.nb;
+    const int N = p.N, H = p.H, KB = p.KB, nb = SINGLE ? 1 : p.nb;
     const int qtiles = (N + 127) >> 7;
     const int n_items = p.B * H * qtiles;
     // items of this (CTA, group): global index (GROUPS * blockIdx + g) + i * GROUPS * gridDim
@@ -399,9 +410,11 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float m = 0.f;
             uint64_t sum2 = pack2(0.f, 0.f);
             float inv = 0.f;
-            const size_t erow_idx = (static_cast<size_t>(b) * H + h) * N + row;
-            __nv_bfloat16* erow = (p.edump != nullptr && row < N) ? p.edump + erow_idx * p.lde : nullptr;
-            float* mrow = erow ? p.mtab + erow_idx * (p.lde >> 5) : nullptr;
+            constexpr bool DUMP_LOOP = DUMP && !SINGLE;
+            // (the single-block variant forms its row pointer in the epilogue: nothing extra stays live across the softmax loop)
+            const size_t erow_idx = DUMP_LOOP ? (static_cast<size_t>(b) * H + h) * N + row : 0;
+            __nv_bfloat16* erow = (DUMP_LOOP && row < N) ? p.edump + erow_idx * p.lde : nullptr;
+            float* mrow = (DUMP_LOOP && row < N) ? p.mtab + erow_idx * (p.lde >> 5) : nullptr;
             for (int j = 0; j < nb; ++j, ++s) {
                 const int vj = min(KB, N - j * KB);
                 const int nch = (vj + 31) >> 5;
@@ -435,8 +448,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         if (nvalid > 16) tmem_ld_32x32b_x32(t_s + c * 32, cur);
                         else tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
                         tmem_ld_wait();
-                        chunk(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
-                              erow ? erow + j * KB + c * 32 : nullptr, mrow ? mrow + ((j * KB) >> 5) + c : nullptr);
+                        chunk<DUMP_LOOP>(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
+                                         (DUMP_LOOP && erow) ? erow + j * KB + c * 32 : nullptr, (DUMP_LOOP && mrow) ? mrow + ((j * KB) >> 5) + c : nullptr);
                     }
                     stamp(2);
                     // ---- the warps that share these rows agree on the row maximum (and, at the end, on the row sum)
@@ -494,9 +507,29 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 uint32_t o[OCOLS];
                 tmem_ld_cols(t_s + O_COL + part * OCOLS, o);
                 tmem_ld_wait();
-                if (erow != nullptr && part == 0) {
-                    p.einv[erow_idx] = inv;
-                    p.mfin[erow_idx] = m;
+                if constexpr (DUMP && SINGLE) {
+                    // the bf16 exponentials of my column range are still in TMEM (P V has retired): one 64-byte row segment per
+                    // 32-key chunk, two full 32-byte sectors per lane
+                    const int nch = (N + 31) >> 5;
+                    const int c0 = part_begin(part, nch), c1 = part_begin(part + 1, nch);
+                    const size_t ridx = (static_cast<size_t>(b) * H + h) * N + (row < N ? row : 0);
+                    __nv_bfloat16* er = p.edump + ridx * p.lde + c0 * 32;
+                    for (int pc = 0; pc < c1 - c0; ++pc) {
+                        uint32_t q[16];
+                        tmem_ld_32x32b_x16(t_s + c0 * 32 + P_SHIFT + pc * 16, q);
+                        tmem_ld_wait();
+                        if (row < N) {
+                            st_u8(er + pc * 32, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+                            st_u8(er + pc * 32 + 16, q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
+                        }
+                    }
+                    if (part == 0 && row < N) p.einv[ridx] = inv;
+                }
+                if constexpr (DUMP && !SINGLE) {
+                    if (erow != nullptr && part == 0) {
+                        p.einv[erow_idx] = inv;
+                        p.mfin[erow_idx] = m;
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -533,7 +566,8 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
     VTC_REQUIRE(n_tokens <= NMAX, VTC_ERR_SHAPE, "attention: %d tokens > %d", n_tokens, NMAX);
-    VTC_REQUIRE(packed == nullptr || (packed->e && packed->mtab && packed->mfin && packed->einv), VTC_ERR_ARG, "attention: incomplete packed-P output");
+    VTC_REQUIRE(packed == nullptr || (packed->e && packed->einv && (n_tokens <= KBMAX || (packed->mtab && packed->mfin))), VTC_ERR_ARG,
+                "attention: incomplete packed-P output");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     Params p{};
@@ -574,13 +608,20 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     if (rc != VTC_OK) return rc;
     static bool configured = false;
     if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
     const int items = batch * heads * cdiv(n_tokens, 128);
     int grid = cdiv(items, GROUPS);
     if (grid > device_sm_count()) grid = device_sm_count();
-    attention_cs_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+    const bool single = p.nb == 1;
+    if (packed && single) attention_cs_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+    else if (packed) attention_cs_kernel<true, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+    else if (single) attention_cs_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+    else attention_cs_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }

@@ -33,8 +33,8 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
 // (attention_mean_scratch_bytes), head_mean_packed reduces them over the heads into attn_mean [B,N,N].
 struct PackedP {
     void* e;        // bf16 [B,H,N,ld]
-    float* mtab;    // [B,H,N,ld/32]: reference maximum of every 32-key chunk (log2 domain)
-    float* mfin;    // [B,H,N]: final row maximum
+    float* mtab;    // [B,H,N,ld/32]: reference maximum of every 32-key chunk (log2 domain); null for one key block
+    float* mfin;    // [B,H,N]: final row maximum; null for one key block
     float* einv;    // [B,H,N]: 1 / row sum (relative to mfin)
 };
 constexpr int kAttentionFusedMeanMaxTokens = 2048;
