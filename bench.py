@@ -149,7 +149,10 @@ def main():
     config = {"workload": "ViT-B/16 224px, 20-class head, batch 256 per GPU, forward + patch-token CAM (BASELINE configs[1])",
               "img": IMG, "batch_per_gpu": args.batch, "global_batch": args.batch * max(world, 1), "tokens": N,
               "gflop_per_image": round(FLOP_IMAGE / 1e9, 3), "mask_norm": "batch",
-              "l2": "inputs larger than L2: 154 MB of images + ~1 GB of activations per step vs 126 MB L2"}
+              "l2": "inputs larger than L2: 154 MB of images + ~1 GB of activations per step vs 126 MB L2",
+              "collectives": ("none (1 GPU)" if world <= 1 else
+                              "CAM maps all-gathered (NCCL) once per 8 steps on a side stream + at the end, int64 counters all-reduced at "
+                              "the end; all inside the timed region, none inside the forward")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -185,7 +188,8 @@ def main():
     model = V.vit_base_patch16_224_in21k(num_classes=C, has_logits=False).to(dev).eval()
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_dev = torch.randn((B, 3, IMG, IMG), generator=g, device=dev)
-    gathered = torch.empty((world * B, C, 14, 14), device=dev) if world > 1 else None
+    GATHER_EVERY = 8       # steps per collective (dist.SideStreamGather): every CAM is gathered inside the timed region
+    gathered = torch.empty((world, GATHER_EVERY, B, C, 14, 14), device=dev) if world > 1 else None
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
 
     def local_step(x):
@@ -194,12 +198,12 @@ def main():
         return o, cam
 
     from vision_transformer_cam_b200 import dist as VD
-    gatherer = VD.SideStreamGather(dev) if world > 1 else None
+    gatherer = VD.SideStreamGather(dev, every=GATHER_EVERY) if world > 1 else None
 
     def step(x):
         o, cam = local_step(x)
         if world > 1:       # gather of the CAM maps + reduction of the counters: the only collectives (never inside the forward);
-            gatherer.gather(gathered, cam)      # on a side stream: the gather of step i overlaps the forward of step i+1
+            gatherer.gather(gathered, cam)      # staged; one all-gather per GATHER_EVERY steps on a side stream, under the following forwards
         return o, cam
 
     def barrier():

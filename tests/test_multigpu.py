@@ -43,6 +43,25 @@ g.wait()
 for k in range(4):
     want = torch.cat([torch.full((3, 5), float(10 * k + r)) for r in range(world)])
     assert torch.equal(outs[k].cpu(), want)
+# batched variant: 3 steps per collective, 7 steps => two full collectives + a flush of one step
+g3 = D.SideStreamGather(dev, every=3)
+out3 = torch.empty((world, 3, 3, 5), device=dev)
+seen = []
+for k in range(7):
+    local = torch.full((3, 5), float(100 * k + rank), device=dev)
+    g3.gather(out3, local)
+    del local
+    if k % 3 == 2:
+        g3.wait()
+        seen.append(out3.clone().cpu())
+g3.wait()
+for blk in range(2):
+    for r in range(world):
+        for j in range(3):
+            assert torch.equal(seen[blk][r, j], torch.full((3, 5), float(100 * (3 * blk + j) + r)))
+tail = out3.view(-1)[: world * 15].view(world, 1, 3, 5).cpu()
+for r in range(world):
+    assert torch.equal(tail[r, 0], torch.full((3, 5), float(600 + r)))
 c = torch.tensor([rank + 1], dtype=torch.int64, device=dev)
 D.reduce_counters(c)
 assert int(c) == world * (world + 1) // 2

@@ -83,26 +83,77 @@ def gather_shards(local: torch.Tensor, n_items: int) -> torch.Tensor:
 
 
 class SideStreamGather:
-    """All-gather of per-step results on a side stream, so the collective of step i overlaps the forward of step i+1
-    (collectives outside the forward, on a side stream).  `gather(local)` enqueues
-    all_gather_into_tensor(out, local) behind everything already enqueued on the caller's stream; `wait()` makes the
-    caller's stream wait for all gathers issued so far (call it before reading `out`)."""
+    """All-gather of per-step results on a side stream, so the collective overlaps the forward of the following steps
+    (collectives outside the forward, on a side stream, once per k batches).
 
-    def __init__(self, device):
+    every == 1: `gather(out, local)` enqueues all_gather_into_tensor(out, local) behind everything already enqueued on the
+    caller's stream; out is [world * B, ...].
+    every == k > 1: the results of k consecutive steps are staged in a device buffer (one 4 MB device-to-device copy per
+    step at the bench shape) and leave in ONE collective: out, with room for world * k * B rows, then holds
+    [world, k, B, ...].  The NCCL kernel needs SMs, which the persistent kernels of the forward occupy completely, and it
+    spins while its peers catch up -- so every collective both waits for a gap between two kernels and holds SMs the next
+    kernel's CTAs want; issuing it every k-th step divides that cost by k (measured at 2 GPUs: 12.06 -> see DESIGN.md).
+    `wait()` flushes what is staged (a shorter [world, n, B, ...] in the leading elements of the last `out`) and makes the
+    caller's stream wait for all collectives issued so far (call it before reading `out`)."""
+
+    def __init__(self, device, every: int = 1):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.every = max(int(every), 1)
+        self._stage = [None, None]          # two staging buffers: one fills while the other is being sent
+        self._sent = [None, None]           # event: the collective reading staging buffer i has finished
+        self._flip = 0
+        self._k = 0
+        self._out = None
 
     def gather(self, out: torch.Tensor, local: torch.Tensor) -> None:
-        if rank_world()[1] == 1:
-            out.copy_(local)
+        world = rank_world()[1]
+        if self.every == 1:
+            if world == 1:
+                out.copy_(local)
+                return
+            cur = torch.cuda.current_stream(self.device)
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(out, local)
+            local.record_stream(self.stream)       # `local` may be freed by the caller while the collective still reads it
             return
+        assert out.numel() >= world * self.every * local.numel() and out.is_contiguous(), "out must hold world * every * local elements"
         cur = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(out, local)
-        local.record_stream(self.stream)       # `local` may be freed by the caller while the collective still reads it
+        st = self._stage[self._flip]
+        if st is None or st.shape[1:] != local.shape or st.dtype != local.dtype:
+            st = self._stage[self._flip] = torch.empty((self.every,) + tuple(local.shape), dtype=local.dtype, device=self.device)
+        if self._k == 0 and self._sent[self._flip] is not None:
+            cur.wait_event(self._sent[self._flip])          # the previous collective out of this staging buffer has read it
+        st[self._k].copy_(local)
+        self._k += 1
+        self._out = out
+        if self._k == self.every:
+            self._flush()
+
+    def _flush(self) -> None:
+        n = self._k
+        if n == 0:
+            return
+        world = rank_world()[1]
+        st = self._stage[self._flip][:n]
+        dst = self._out.view(-1)[: world * st.numel()].view((world,) + tuple(st.shape))
+        cur = torch.cuda.current_stream(self.device)
+        if world == 1:
+            dst[0].copy_(st)
+        else:
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(dst, st)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self._sent[self._flip] = ev
+        self._flip ^= 1
+        self._k = 0
 
     def wait(self) -> None:
+        if self.every > 1:
+            self._flush()
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
 
 
