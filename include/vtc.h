@@ -246,6 +246,10 @@ VTC_API int vtc_attention(const void* qkv, const float* key_bias, void* out, flo
 VTC_API size_t vtc_attention_mean_scratch_bytes(int32_t batch, int32_t n_tokens, int32_t heads);
 VTC_API int vtc_attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch,
                        size_t scratch_bytes, int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream);
+/* vtc_attention for head dimensions other than 64 (ViT-H/14: 1280 / 16 = 80): qkv [B,N,3,H,head_dim], head_dim a multiple
+ * of 16 up to 128, n_tokens <= 320; fp32 arithmetic on bf16 operands, same outputs and mask semantics (vit_model.py:113-137). */
+VTC_API int vtc_attention_generic(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch,
+                          int32_t n_tokens, int32_t heads, int32_t head_dim, float scale, void* stream);
 /* The KV-blocked kernel behind vtc_attention for n_tokens > 256 (ViT-B/16-448: 785 tokens, ViT-L/16-384: 577 tokens),
  * callable directly for any n_tokens <= 2048.  Same arguments and outputs as vtc_attention.
  *   split != 0 ("fp32 mode"): operands are (hi, lo) bf16 pairs, x ~= hi + lo: qkv is [B,N,2,3,H,64] (all hi parts of a

@@ -132,3 +132,49 @@ def test_patch32_factory_with_pre_logits(lib_built):
     assert e <= LOGIT_TOL and c_cam >= 0.999 and c_roll >= 0.999
     out = model(x.to("cuda:0"))
     assert out[1][0].shape == (3, 12, 50, 50) and out[5].shape == (3, 16, 768)
+
+
+def test_vit_h14_224_factory_runs_through_the_general_shape_path(lib_built):
+    """vit_huge_patch14_224_in21k: patch 14 (K = 588 padded to 640), 257 tokens, head_dim 80 (attention_generic.cu), 32 layers.
+    The reference cannot execute this factory (197 tokens / 12 heads hard-coded); truth = the generalised CPU oracle.  A small
+    head-dim-48 model exercises the same path on the cheap side (depth 2), the real factory runs once at batch 1."""
+    import vision_transformer_cam_b200 as V
+    from vision_transformer_cam_b200 import cam as CAM
+    from oracle import vit_forward as VF, postproc as PP
+    # (a) ViT-H/14 itself
+    cfg = VF.VitConfig(patch_size=14, embed_dim=1280, depth=32, num_heads=16)
+    torch.manual_seed(0)
+    model = V.vit_huge_patch14_224_in21k(num_classes=20, has_logits=False)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert sd["pos_embed"].shape == (1, 257, 1280) and sd["patch_embed.proj.weight"].shape == (1280, 3, 14, 14)
+    model = model.to("cuda:0").eval()
+    x = VF.make_images(0, 1)
+    ref = VF.forward(sd, x, cfg, keep_P=False)
+    o = model.forward_cam(x.to("cuda:0"), attn_mean=True)
+    e = relerr(o.logits, ref["logits"])
+    c_cam = cosine(CAM.classic_cam(o.tokens_last, model.head1.weight.data), PP.classic_cam(ref["X"][-1], sd["head1.weight"]))
+    print(f"H/14-224: logits relerr {e:.2e} CAM cos {c_cam:.6f}")
+    assert o.cls_rows.shape == (32, 1, 16, 257) and o.attn_mean.shape == (32, 1, 257, 257)
+    assert e <= LOGIT_TOL and c_cam >= 0.999
+    assert float((o.cls_rows.cpu() - ref["cls_rows"]).abs().max()) <= 0.02 * float(ref["cls_rows"].max())
+    assert float((o.attn_mean.sum(-1) - 1).abs().max()) < 1e-4
+    out = model(x.to("cuda:0"))                       # reference-compatible 6-tuple: last 12 layers (vit_model.py:322)
+    assert len(out[1]) == 12 and out[1][0].shape == (1, 16, 257, 257) and out[5].shape == (1, 16, 1280)
+    with pytest.raises(Exception):                    # uint8 ingest needs a patch size that is a multiple of 8
+        model.forward_cam_u8(torch.zeros((1, 224, 224, 3), dtype=torch.uint8, device="cuda:0"))
+    del model
+    torch.cuda.empty_cache()
+    # (b) head_dim 48, patch 16, with the mask active (peaked weights), teacher-forced decisions
+    cfg = VF.VitConfig(embed_dim=768, depth=6, num_heads=16)
+    torch.manual_seed(1)
+    m2 = V.VisionTransformer(img_size=224, patch_size=16, embed_dim=768, depth=6, num_heads=16, num_classes=20)
+    sd2 = VF.peaked({k: v.clone() for k, v in m2.state_dict().items()})
+    m2.load_state_dict(sd2)
+    m2 = m2.to("cuda:0").eval()
+    x = VF.make_images(3, 2)
+    ref = VF.forward(sd2, x, cfg, keep_P=False)
+    forced = {l: b for l, b in enumerate(ref["bg"]) if b is not None}
+    o2 = m2.forward_cam(x.to("cuda:0"), forced_bg=forced, forced_topk=ref["topk_idx"])
+    e2 = relerr(o2.logits, ref["logits"])
+    print(f"head_dim 48, 6 layers, peaked teacher-forced: logits relerr {e2:.2e}")
+    assert e2 <= PEAKED_TOL

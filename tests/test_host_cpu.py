@@ -61,9 +61,16 @@ def test_model_create_rejects_unsupported_shapes(lib_built):
     assert lib.vtc_model_packed_bytes(h) == 2 * (768 * 768 + 12 * (3 * 768 * 768 + 768 * 768 + 2 * 3072 * 768))
     assert lib.vtc_workspace_bytes(h, 256, None) > 0
     assert lib.vtc_model_destroy(h) == 0
-    bad = _lib.Config(224, 14, 3, 20, 1280, 32, 16, 5120, 0, 4, 0.25, 16, 1e-6)    # ViT-H/14: patch 14, head_dim 80
-    assert lib.vtc_model_create(ctypes.byref(bad), ctypes.byref(h)) == -2
-    assert b"patch_size" in lib.vtc_last_error() or b"head_dim" in lib.vtc_last_error()
+    vith = _lib.Config(224, 14, 3, 20, 1280, 32, 16, 5120, 0, 4, 0.25, 16, 1e-6)   # ViT-H/14: patch 14 (K 588 -> 640), head_dim 80
+    assert lib.vtc_model_create(ctypes.byref(vith), ctypes.byref(h)) == 0
+    assert lib.vtc_model_packed_bytes(h) == 2 * (1280 * 640 + 32 * (3 * 1280 * 1280 + 1280 * 1280 + 2 * 5120 * 1280))
+    assert lib.vtc_model_destroy(h) == 0
+    bad = _lib.Config(224, 16, 3, 20, 768, 12, 16, 3072, 0, 4, 0.25, 16, 1e-6)      # head_dim 48 runs; 768 / 32 = 24 does not
+    assert lib.vtc_model_create(ctypes.byref(bad), ctypes.byref(h)) == 0 and lib.vtc_model_destroy(h) == 0
+    bad = _lib.Config(224, 16, 3, 20, 768, 12, 32, 3072, 0, 4, 0.25, 16, 1e-6)
+    assert lib.vtc_model_create(ctypes.byref(bad), ctypes.byref(h)) == -2 and b"head_dim" in lib.vtc_last_error()
+    bad = _lib.Config(448, 16, 3, 20, 1280, 12, 16, 5120, 0, 4, 0.25, 16, 1e-6)     # head_dim 80 with 785 tokens: general-shape kernel limit
+    assert lib.vtc_model_create(ctypes.byref(bad), ctypes.byref(h)) == -2 and b"tokens" in lib.vtc_last_error()
 
 
 def test_dropin_module_surface_and_state_dict():

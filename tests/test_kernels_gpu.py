@@ -550,3 +550,42 @@ def test_attention_fused_head_mean_large_dynamic_range(dev, N, amp):
         assert float((mean - ref_m).abs().max()) <= 1e-2 * float(ref_m.max()), float((mean - ref_m).abs().max())
         assert float((mean.sum(-1) - 1).abs().max()) < 5e-3
         assert relerr(out.float(), ref_o) < 1.5e-2
+
+
+def _attn_ref_hd(qkv, H, scale, kb):
+    """_attn_ref for any head dimension."""
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    q, k, v = qkv.float().view(B, N, 3, H, D // H).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) * scale
+    if kb is not None:
+        v_ = (kb != 0).float()
+        s = s - 100.0 * torch.clamp(v_[:, :, None] + v_[:, None, :], max=1.0)[:, None]
+    p = s.softmax(-1)
+    return (p @ v).transpose(1, 2).reshape(B, N, D), p
+
+
+@pytest.mark.parametrize("B,N,H,hd,masked", [(2, 257, 3, 80, True), (1, 257, 16, 80, False), (3, 100, 2, 96, True), (2, 33, 2, 16, False),
+                                             (1, 320, 1, 128, True), (2, 197, 2, 64, True)])
+def test_attention_generic_head_dims(dev, B, N, H, hd, masked):
+    """The general-shape attention path (ViT-H/14: head_dim 80, 257 tokens) against the fp32 softmax attention of the same
+    bf16 operands: P (fp32, not rounded before P V here) to 2e-6, O to the bf16 rounding of the output."""
+    from vision_transformer_cam_b200 import ops
+    qkv = _rand((B, N, 3 * H * hd), 130, dev, 1.2).bfloat16()
+    kb = None
+    if masked:
+        g = torch.Generator().manual_seed(131)
+        kb = torch.where(torch.rand((B, N), generator=g) < 0.3, -100.0, 0.0)
+        kb[:, 0] = 0
+        kb = kb.to(dev)
+    scale = hd ** -0.5
+    out, cls, attn = ops.attention_generic(qkv, H, scale, key_bias=kb, want_cls=True, want_attn=True)
+    ref_o, ref_p = _attn_ref_hd(qkv, H, scale, kb)
+    assert float((attn - ref_p).abs().max()) < 5e-6, float((attn - ref_p).abs().max())
+    assert torch.equal(cls, attn[:, :, 0, :])
+    assert relerr(out.float(), ref_o) < 5e-3, relerr(out.float(), ref_o)
+    out2, cls2, none = ops.attention_generic(qkv, H, scale, key_bias=kb, want_cls=True, want_attn=False)
+    assert none is None and torch.equal(out, out2) and torch.equal(cls, cls2)
+    if hd == 64:      # same operator as the tensor-core kernels
+        o64, c64, _ = ops.attention(qkv, H, scale, key_bias=kb)
+        assert relerr(o64.float(), out.float()) < 1e-2 and float((c64 - cls).abs().max()) < 5e-6

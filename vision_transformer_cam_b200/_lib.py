@@ -91,6 +91,7 @@ SIGNATURES = {
     "vtc_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "vtc_attention_mean_scratch_bytes": (_Z, [_I, _I, _I]),
     "vtc_attention_mean": (C.c_int, [_P, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _F, _P]),
+    "vtc_attention_generic": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "vtc_attention_kv": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
     "vtc_head_mean": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "vtc_cls_stat": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libvtc.so")
-SOURCES = ["runtime.cu", "gemm.cu", "elementwise.cu", "attention.cu", "attention_kv.cu", "attention_cs.cu", "cls_ops.cu", "postproc.cu", "model.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "elementwise.cu", "attention.cu", "attention_kv.cu", "attention_cs.cu", "attention_generic.cu", "cls_ops.cu", "postproc.cu", "model.cu"]
 HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "ops.h", "tma_host.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "vtc.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

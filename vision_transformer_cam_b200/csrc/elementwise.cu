@@ -34,6 +34,31 @@ int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream) {
     return VTC_OK;
 }
 
+// fp32 [rows, cols] -> bf16 [rows, ld] with the columns cols .. ld-1 zeroed (weights of a GEMM whose K is padded, e.g. the
+// 3*14*14 = 588 -> 640 patch-embedding contraction of ViT-H/14)
+__global__ void cast_bf16_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t rows, int cols, int ld) {
+    const size_t total = rows * ld;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t r = i / ld;
+        const int c = static_cast<int>(i - r * ld);
+        dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+    }
+}
+
+int cast_bf16_pad(const float* src, void* dst, size_t rows, int cols, int ld, cudaStream_t stream) {
+    VTC_REQUIRE(src && dst, VTC_ERR_ARG, "cast_pad: null pointer");
+    VTC_REQUIRE(rows > 0 && cols > 0 && ld >= cols, VTC_ERR_SHAPE, "cast_pad: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    size_t blocks = (rows * ld + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    cast_bf16_pad_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols, ld);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 // ---- split (fp32 mode) ------------------------------------------------------------------------------
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits.  Rows keep their halves side by side, [rows, 2*cols].
 __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
@@ -117,6 +142,40 @@ int patchify(const float* x, void* patches, int batch, int in_c, int img, int pa
     if (blocks > cap) blocks = cap;
     if (split) patchify_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, total8);
     else patchify_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, total8);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// Any patch size (ViT-H/14: 14 is not a multiple of the 8-pixel vectors above), K padded to `kp` columns with zeros: one
+// thread per element of the patch matrix.  Reads are 4-byte gathers along image rows (p consecutive pixels per run).
+__global__ void patchify_generic_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int in_c, int S, int p, int kp, size_t total) {
+    const int g = S / p;
+    const int kdim = in_c * p * p;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t row = i / kp;
+        const int k = static_cast<int>(i - row * kp);
+        float v = 0.f;
+        if (k < kdim) {
+            const int c = k / (p * p), rem = k - c * p * p, kh = rem / p, kw = rem - kh * p;
+            const size_t b = row / (static_cast<size_t>(g) * g);
+            const int pr = static_cast<int>(row - b * g * g), py = pr / g, px = pr - py * g;
+            v = x[((b * in_c + c) * S + (py * p + kh)) * S + px * p + kw];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+int patchify_generic(const float* x, void* patches, int batch, int in_c, int img, int patch, int kp, cudaStream_t stream) {
+    VTC_REQUIRE(x && patches, VTC_ERR_ARG, "patchify: null pointer");
+    VTC_REQUIRE(batch > 0 && in_c > 0 && img > 0 && patch > 0 && img % patch == 0 && kp >= in_c * patch * patch, VTC_ERR_SHAPE, "patchify: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const size_t total = static_cast<size_t>(batch) * (img / patch) * (img / patch) * kp;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    patchify_generic_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), in_c, img, patch, kp, total);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }

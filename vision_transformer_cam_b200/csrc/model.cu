@@ -10,6 +10,8 @@
 struct vtc_model {
     vtc_config cfg;
     int N, P, D, H, L, C, HID, KP, R;
+    int HD = 64;                 // head dimension; != 64 routes attention through the general-shape kernel (attention_generic.cu)
+    bool generic_patch = false;  // patch size not a multiple of 8: element-wise patch matrix, K padded to a multiple of 64
     vtc_weights w;
     std::vector<vtc_layer_weights> lw;
     // packed bf16 GEMM weights (inside the caller's packed buffer)
@@ -40,7 +42,7 @@ static size_t seg(size_t elems, size_t elem_bytes) { return align_up(elems * ele
 // LayerNorm, whose bf16 rounding is also independent of the row mean.
 static bool ln_fusion_enabled(const vtc_model* m) {
     static const bool on = []() { const char* e = getenv("VTC_LN_FUSION"); return e && e[0] == '1'; }();
-    return !m->split && on;
+    return !m->split && m->HD == 64 && on;
 }
 
 static size_t packed_bytes(const vtc_model* m) {
@@ -53,7 +55,7 @@ static size_t packed_bytes(const vtc_model* m) {
 // instead of a [B,H,N,N] fp32 round trip
 static bool fused_mean_ok(const vtc_model* m) {
     static const bool off = []() { const char* e = getenv("VTC_NO_FUSED_MEAN"); return e && e[0] == '1'; }();
-    return !off && !m->split && m->N <= kAttentionFusedMeanMaxTokens;
+    return !off && !m->split && m->HD == 64 && m->N <= kAttentionFusedMeanMaxTokens;
 }
 
 struct Workspace {
@@ -131,6 +133,9 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
                    uint32_t flags, cudaStream_t st) {
     VTC_REQUIRE(m && (in.f32 || (in.u8 && in.mean && in.std)) && o && workspace, VTC_ERR_ARG, "forward: null pointer");
     VTC_REQUIRE(!in.u8 || m->cfg.in_c == 3, VTC_ERR_SHAPE, "forward: uint8 HWC input needs in_c == 3");
+    VTC_REQUIRE(!in.u8 || !m->generic_patch, VTC_ERR_SHAPE, "forward: uint8 input needs a patch size that is a multiple of 8");
+    VTC_REQUIRE(!m->split || (m->HD == 64 && !m->generic_patch), VTC_ERR_SHAPE,
+                "forward: the fp32 (split) mode needs head_dim 64 and a patch size that is a multiple of 8");
     VTC_REQUIRE(m->packed, VTC_ERR_ARG, "forward: vtc_model_pack_weights has not been called");
     VTC_REQUIRE(B > 0, VTC_ERR_SHAPE, "forward: batch %d", B);
     VTC_REQUIRE(o->logits && o->hwp_logits && o->hwp_tokens, VTC_ERR_ARG, "forward: logits / hwp_logits / hwp_tokens are required outputs");
@@ -157,6 +162,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     // ---- patch embedding + token assembly (vit_model.py:306-314)
     float* t_cur = ws.tok;
     if (in.u8) VTC_STEP(VTC_PROF_PATCHIFY, patchify_u8(in.u8, in.mean, in.std, ws.patches, B, m->cfg.img_size, m->cfg.patch_size, st, sp));
+    else if (m->generic_patch) VTC_STEP(VTC_PROF_PATCHIFY, patchify_generic(in.f32, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, m->KP, st));
     else VTC_STEP(VTC_PROF_PATCHIFY, patchify(in.f32, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st, sp));
     VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));
     VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st, sp));
@@ -207,7 +213,8 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_in, w.norm1_w, w.norm1_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
             VTC_STEP(VTC_PROF_GEMM_QKV, gemm_bf16(ws.y, pw.qkv, w.qkv_b, nullptr, nullptr, ws.qkv, M, 3 * D, D, VTC_EPI_BIAS, 0, st, sp, next_dir()));
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
-            if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
+            if (m->HD != 64) VTC_STEP(VTC_PROF_ATTENTION, attention_generic(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, m->HD, scale, st));
+            else if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
             else if (mean_l) VTC_STEP(VTC_PROF_ATTENTION, attention_mean(ws.qkv, kb, ws.ao, cls_l, mean_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
             else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
             VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
@@ -245,17 +252,22 @@ int vtc_model_create(const vtc_config* cfg, vtc_model** out) {
     VTC_REQUIRE(cfg && out, VTC_ERR_ARG, "model_create: null pointer");
     VTC_REQUIRE(cfg->img_size > 0 && cfg->patch_size > 0 && cfg->img_size % cfg->patch_size == 0, VTC_ERR_SHAPE,
                 "model_create: img_size %d / patch_size %d", cfg->img_size, cfg->patch_size);
-    VTC_REQUIRE(cfg->patch_size % 8 == 0, VTC_ERR_SHAPE, "model_create: patch_size %d must be a multiple of 8", cfg->patch_size);
-    VTC_REQUIRE(cfg->embed_dim > 0 && cfg->num_heads > 0 && cfg->embed_dim == cfg->num_heads * 64, VTC_ERR_SHAPE,
-                "model_create: head_dim must be 64 (embed_dim %d, heads %d)", cfg->embed_dim, cfg->num_heads);
+    VTC_REQUIRE(cfg->embed_dim > 0 && cfg->num_heads > 0 && cfg->embed_dim % cfg->num_heads == 0, VTC_ERR_SHAPE,
+                "model_create: embed_dim %d is not a multiple of num_heads %d", cfg->embed_dim, cfg->num_heads);
+    const int hd = cfg->embed_dim / cfg->num_heads;
+    // head_dim 64 runs on the tcgen05 attention kernels; other multiples of 16 up to 128 (ViT-H/14: 80) on the general-shape one
+    VTC_REQUIRE(hd == 64 || (hd % 16 == 0 && hd >= 16 && hd <= 128), VTC_ERR_SHAPE, "model_create: head_dim %d (64, or a multiple of 16 up to 128)", hd);
     VTC_REQUIRE(cfg->embed_dim % 256 == 0 && cfg->mlp_hidden % 256 == 0, VTC_ERR_SHAPE,
                 "model_create: embed_dim %d and mlp_hidden %d must be multiples of 256", cfg->embed_dim, cfg->mlp_hidden);
-    VTC_REQUIRE((cfg->in_c * cfg->patch_size * cfg->patch_size) % 64 == 0, VTC_ERR_SHAPE, "model_create: in_c*patch^2 must be a multiple of 64");
+    VTC_REQUIRE(cfg->patch_size % 8 != 0 || (cfg->in_c * cfg->patch_size * cfg->patch_size) % 64 == 0, VTC_ERR_SHAPE,
+                "model_create: in_c*patch^2 must be a multiple of 64");
     VTC_REQUIRE(cfg->depth > 0 && cfg->depth <= 32 && cfg->num_classes > 0, VTC_ERR_SHAPE, "model_create: depth %d classes %d", cfg->depth, cfg->num_classes);
     VTC_REQUIRE(cfg->representation_size == 0 || cfg->representation_size == cfg->embed_dim, VTC_ERR_SHAPE,
                 "model_create: representation_size must be 0 or embed_dim (head1 consumes embed_dim features, vit_model.py:295,393)");
     const int g = cfg->img_size / cfg->patch_size;
     VTC_REQUIRE(cfg->topk > 0 && cfg->topk <= 64 && cfg->topk <= g * g, VTC_ERR_SHAPE, "model_create: topk %d", cfg->topk);
+    VTC_REQUIRE(hd == 64 || g * g + 1 <= kAttentionGenericMaxTokens, VTC_ERR_SHAPE, "model_create: head_dim %d supports at most %d tokens (%d given)", hd,
+                kAttentionGenericMaxTokens, g * g + 1);
     vtc_model* m = new (std::nothrow) vtc_model();
     VTC_REQUIRE(m != nullptr, VTC_ERR_ARG, "model_create: out of host memory");
     m->cfg = *cfg;
@@ -266,7 +278,10 @@ int vtc_model_create(const vtc_config* cfg, vtc_model** out) {
     m->L = cfg->depth;
     m->C = cfg->num_classes;
     m->HID = cfg->mlp_hidden;
-    m->KP = cfg->in_c * cfg->patch_size * cfg->patch_size;
+    m->HD = hd;
+    m->generic_patch = cfg->patch_size % 8 != 0;
+    m->KP = (cfg->in_c * cfg->patch_size * cfg->patch_size + 63) / 64 * 64;      // == in_c*patch^2 unless generic_patch
+
     m->R = cfg->representation_size;
     *out = m;
     return VTC_OK;
@@ -328,7 +343,13 @@ int vtc_model_pack_weights(vtc_model* m, const vtc_weights* w, void* packed, siz
         *dst = d;
         return split ? split_bf16(src, d, rows, cols, st) : cast_bf16(src, d, rows * cols, st);
     };
-    if ((rc = pack(w->patch_w, D, m->KP, &m->patch_w)) != VTC_OK) return rc;
+    if (m->generic_patch) {        // K = in_c * patch^2 padded with zero columns to KP
+        VTC_REQUIRE(!split, VTC_ERR_SHAPE, "pack_weights: the fp32 (split) mode needs a patch size that is a multiple of 8");
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(base + off);
+        off += seg(D * m->KP, 2);
+        m->patch_w = d;
+        if ((rc = cast_bf16_pad(w->patch_w, d, D, m->cfg.in_c * m->cfg.patch_size * m->cfg.patch_size, m->KP, st)) != VTC_OK) return rc;
+    } else if ((rc = pack(w->patch_w, D, m->KP, &m->patch_w)) != VTC_OK) return rc;
     for (int l = 0; l < m->L; ++l) {
         const vtc_layer_weights& lw = m->lw[l];
         VTC_REQUIRE(lw.norm1_w && lw.norm1_b && lw.norm2_w && lw.norm2_b && lw.qkv_b && lw.proj_b && lw.fc1_b && lw.fc2_b, VTC_ERR_ARG,

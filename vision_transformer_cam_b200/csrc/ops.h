@@ -21,6 +21,9 @@ int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
 int split_bf16(const float* src, void* dst, size_t rows, size_t cols, cudaStream_t stream);
 int patchify(const float* x, void* patches, int batch, int in_c, int img, int patch, cudaStream_t stream, int split = 0);
 // decoded u8 HWC images [B,S,S,3] -> normalised bf16 patch matrix; mean / std are HOST arrays of 3 floats
+// any patch size, K padded with zeros to kp columns (bf16 mode, fp32 input)
+int patchify_generic(const float* x, void* patches, int batch, int in_c, int img, int patch, int kp, cudaStream_t stream);
+int cast_bf16_pad(const float* src, void* dst, size_t rows, int cols, int ld, cudaStream_t stream);
 int patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, cudaStream_t stream,
                 int split = 0);
 int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int batch, int n_tokens, int dim, cudaStream_t stream);
@@ -57,6 +60,10 @@ int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_r
 // packed: optional packed-P output (row stride attention_packed_ld(N)) for attention_mean
 int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
                  cudaStream_t stream, int reverse = 0, const PackedP* packed = nullptr);
+// general-shape path (attention_generic.cu): head_dim a multiple of 16 up to 128, n_tokens <= 320; same outputs as `attention`
+int attention_generic(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
+                      int head_dim, float scale, cudaStream_t stream);
+constexpr int kAttentionGenericMaxTokens = 320;
 unsigned long long* attention_trace_buffer();   // debug: device buffer for %globaltimer stamps (vtc_debug_set_attention_trace) or null
 int head_mean(const float* attn, float* mean, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream);

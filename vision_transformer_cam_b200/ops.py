@@ -137,6 +137,19 @@ def attention_mean(qkv: torch.Tensor, heads: int, scale: float, key_bias: Option
     return out, cls, mean
 
 
+def attention_generic(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, want_cls: bool = True,
+                      want_attn: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """The general-shape attention path (any head_dim that is a multiple of 16 up to 128, N <= 320): (out, cls_rows, attn)."""
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if want_cls else None
+    attn = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv.device) if want_attn else None
+    _lib.call("vtc_attention_generic", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), _ptr(attn),
+              B, N, heads, D // heads, scale, _stream())
+    return out, cls, attn
+
+
 def attention_kv(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, want_cls: bool = True,
                  want_attn: bool = False, split: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     """The KV-blocked kernel called directly (any N <= 2048).  split: qkv [B,N,2*3*H*64] and out [B,N,2*H*64] hold

@@ -580,5 +580,6 @@ def vit_large_patch32_224_in21k(num_classes: int = 21843, has_logits: bool = Tru
 
 
 def vit_huge_patch14_224_in21k(num_classes: int = 21843, has_logits: bool = True):
-    """ViT-H/14: constructible (state_dict parity) but the fused path rejects patch 14 / head_dim 80 at the first forward."""
+    """ViT-H/14 (257 tokens, head_dim 80): patch matrix with K padded 588 -> 640, attention through the general-shape kernel
+    (csrc/attention_generic.cu); bf16 mode, fp32 image input."""
     return _vit(14, 1280, 32, 16, num_classes, 1280 if has_logits else None)
