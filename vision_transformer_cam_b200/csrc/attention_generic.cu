@@ -1,27 +1,27 @@
 // Attention for head dimensions other than 64 (vit_model.py:113-137 with head_dim = embed_dim / num_heads: ViT-H/14 has
 // 1280 / 16 = 80).  The tcgen05 kernels (attention_cs / attention_kv / attention.cu) are built around one 128-byte swizzle
-// atom per Q / K / V row, i.e. exactly 64 bf16; this kernel is the general-shape path of the same operator: bf16 operands,
-// fp32 products / softmax / P (P is NOT rounded to bf16 before P V here), every output of vtc_attention -- O, the CLS query
-// row and, on request, the full P.  It runs on the FMA pipe out of shared memory; ViT-H is not a benchmark configuration
-// of the reference (whose forward cannot run it at all: 197 tokens and 12 heads are hard-coded), so the
-// point here is the complete factory surface, not speed.
+// atom per Q / K / V row, i.e. exactly 64 bf16; this kernel is the general-shape path of the same operator, with every
+// output of vtc_attention: O, the CLS query row and, on request, the full P.  ViT-H is not a benchmark configuration of the
+// reference (whose forward cannot run it at all: 197 tokens and 12 heads are hard-coded); the point is the
+// complete factory surface at a reasonable speed, so it uses the warp-level tensor-core path (mma.sync m16n8k16, bf16
+// operands, fp32 accumulation) that works for any multiple of 16, not a second tcgen05 pipeline.
 //
-// One CTA = 32 query rows of one (image, head); 8 warps x 4 rows.  K ([N][hd+2] bf16: odd word pitch, conflict-free for
-// lane = key), V ([N][hd] bf16: lane = feature) and the 32 Q rows ([warp][hd][4] fp32: one broadcast 16-byte read gives a
-// feature of all four rows) sit in shared memory.
-//   phase 1: lane owns keys lane + 32 t: s[4][T] = q . k (8 FMAs per key pair of features), + mask, softmax across the warp;
-//   phase 2: P goes through a per-warp staging area ([key][4] fp32), lane owns features lane + 32 u: o[4][U] += p * v.
+// One CTA = one (image, head): K and V of the whole sequence are staged once ([Npad][hd+8] bf16 each; the +8 makes every
+// fragment load bank-conflict free; two CTAs fit an SM at ViT-H's shape) with the key bias [Npad]; its 8 warps take the
+// 16-row query groups round robin, Q fragments straight from global memory.  V stays row-major: the B fragments of P V come
+// out of ldmatrix.trans.  Per query group two sweeps over 64-key blocks, both recomputing S = Q K^T on the tensor cores:
+//   sweep 1: running row maximum and row sum (online, fp32);
+//   sweep 2: P = exp(S - m) / sum -> optional outputs (full P, CLS row) -> bf16 A fragments straight from the accumulator
+//            registers -> O += P V.
 #include "common.cuh"
 #include "ops.h"
 
 namespace vtc {
 
 namespace ag {
-constexpr int QT = 32;            // query rows per CTA
 constexpr int WARPS = 8;
-constexpr int ROWS = QT / WARPS;  // 4 rows per warp
-constexpr int TMAX = 10;          // keys per lane: n_tokens <= 320
-constexpr int UMAX = 4;           // features per lane: head_dim <= 128
+constexpr int KBLK = 64;          // keys per block
+constexpr int MAXKS = 8;          // head_dim / 16 <= 8
 
 struct Params {
     const __nv_bfloat16* qkv;   // [B,N,3,H,hd]
@@ -30,153 +30,208 @@ struct Params {
     float* cls_rows;            // [B,H,N] or null
     float* attn;                // [B,H,N,N] or null
     int B, N, H, hd;
-    int npad;                   // N rounded up to 32
+    int npad;                   // N rounded up to KBLK
     float scale;
 };
 
-__host__ __device__ inline size_t smem_bytes(int npad, int hd) {
-    return static_cast<size_t>(npad) * (hd + 2) * 2 + static_cast<size_t>(npad) * hd * 2 + static_cast<size_t>(QT) * hd * 4 +
-           static_cast<size_t>(WARPS) * npad * ROWS * 4;
+__host__ __device__ inline size_t smem_bytes(int npad, int hd) { return static_cast<size_t>(2) * npad * (hd + 8) * 2 + static_cast<size_t>(npad) * 4; }
+
+// four 8x8 b16 matrices, transposed on the way to the registers (B fragments of P V from row-major V)
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
 }
 
-__global__ void __launch_bounds__(WARPS * 32) attention_generic_kernel(const Params p) {
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// S block (16 rows x 64 keys) of this warp: 8 key tiles x 4 accumulators; scaled, masked, padding keys at -inf.
+template <int KS>
+__device__ __forceinline__ void score_block(float (&s)[8][4], const uint32_t (&qa)[MAXKS][4], const __nv_bfloat16* Ks, int kp, int key0, int N,
+                                            float scale, const float* kbs, bool fg0, bool fg1, int g, int t) {
+#pragma unroll
+    for (int jt = 0; jt < 8; ++jt) {
+        s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
+        const __nv_bfloat16* krow = Ks + static_cast<size_t>(key0 + jt * 8 + g) * kp + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+            mma_bf16_16816(s[jt], qa[ks], b0, b1);
+        }
+        const int j = key0 + jt * 8 + 2 * t;
+        const float kb0 = kbs ? kbs[j] : 0.f, kb1 = kbs ? kbs[j + 1] : 0.f;
+        s[jt][0] = j < N ? fmaf(s[jt][0], scale, fg0 ? kb0 : 0.f) : -INFINITY;
+        s[jt][1] = j + 1 < N ? fmaf(s[jt][1], scale, fg0 ? kb1 : 0.f) : -INFINITY;
+        s[jt][2] = j < N ? fmaf(s[jt][2], scale, fg1 ? kb0 : 0.f) : -INFINITY;
+        s[jt][3] = j + 1 < N ? fmaf(s[jt][3], scale, fg1 ? kb1 : 0.f) : -INFINITY;
+    }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+template <int KS>      // head_dim = 16 * KS
+__global__ void __launch_bounds__(WARPS * 32, 2) attention_generic_kernel(const Params p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int N = p.N, H = p.H, hd = p.hd, npad = p.npad;
-    const int kp = hd + 2;                                       // K row pitch in bf16
+    constexpr int HD = 16 * KS;
+    constexpr int NT = HD / 8;                                   // output tiles of 8 features (even)
+    constexpr int kp = HD + 8;                                   // K / V row pitch (bf16)
+    const int N = p.N, H = p.H, npad = p.npad;
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
     __nv_bfloat16* Vs = Ks + static_cast<size_t>(npad) * kp;
-    float* Qs = reinterpret_cast<float*>(Vs + static_cast<size_t>(npad) * hd);      // [WARPS][hd][ROWS]
-    float* Ps = Qs + QT * hd;                                                       // [WARPS][npad][ROWS]
+    float* kbs = reinterpret_cast<float*>(Vs + static_cast<size_t>(npad) * kp);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-    const size_t tok_stride = static_cast<size_t>(3) * H * hd;                      // elements per token in qkv
-    const __nv_bfloat16* base = p.qkv + static_cast<size_t>(b) * N * tok_stride + static_cast<size_t>(h) * hd;
+    const int g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.y, h = blockIdx.x;
+    const size_t tok_stride = static_cast<size_t>(3) * H * HD;
+    const __nv_bfloat16* base = p.qkv + static_cast<size_t>(b) * N * tok_stride + static_cast<size_t>(h) * HD;
 
-    // ---- stage K, V (all keys of this head) and the 32 query rows
-    const int pairs = hd >> 1;
-    for (int i = threadIdx.x; i < npad * pairs; i += blockDim.x) {
-        const int n = i / pairs, d2 = i - n * pairs;
-        uint32_t kv = 0u, vv = 0u;
+    // ---- stage K, V (all keys of this head) and the key bias
+    constexpr int V8 = HD / 8;                                   // 16-byte vectors per row
+    for (int i = threadIdx.x; i < npad * V8; i += blockDim.x) {
+        const int n = i / V8, c = i - n * V8;
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
         if (n < N) {
             const __nv_bfloat16* tok = base + static_cast<size_t>(n) * tok_stride;
-            kv = *reinterpret_cast<const uint32_t*>(tok + static_cast<size_t>(H) * hd + 2 * d2);
-            vv = *reinterpret_cast<const uint32_t*>(tok + static_cast<size_t>(2) * H * hd + 2 * d2);
+            kv = *reinterpret_cast<const uint4*>(tok + static_cast<size_t>(H) * HD + c * 8);
+            vv = *reinterpret_cast<const uint4*>(tok + static_cast<size_t>(2) * H * HD + c * 8);
         }
-        *reinterpret_cast<uint32_t*>(Ks + static_cast<size_t>(n) * kp + 2 * d2) = kv;
-        *reinterpret_cast<uint32_t*>(Vs + static_cast<size_t>(n) * hd + 2 * d2) = vv;
+        *reinterpret_cast<uint4*>(Ks + static_cast<size_t>(n) * kp + c * 8) = kv;
+        *reinterpret_cast<uint4*>(Vs + static_cast<size_t>(n) * kp + c * 8) = vv;
     }
-    for (int i = threadIdx.x; i < QT * hd; i += blockDim.x) {
-        const int r = i / hd, d = i - r * hd;                    // r: row inside the tile
-        const int row = q0 + r;
-        const float v = row < N ? __bfloat162float(base[static_cast<size_t>(row) * tok_stride + d]) : 0.f;
-        Qs[(static_cast<size_t>(r / ROWS) * hd + d) * ROWS + (r % ROWS)] = v;
-    }
+    const bool has_bias = p.key_bias != nullptr;
+    if (has_bias)
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) kbs[i] = i < N ? p.key_bias[static_cast<size_t>(b) * N + i] : 0.f;
     __syncthreads();
+    const float* kbp = has_bias ? kbs : nullptr;
+    const int nblk = npad / KBLK;
+    // ldmatrix source of this lane: matrices 0..3 = (keys +0 / +8) x (features +0 / +8)
+    const int lm_key = (lane & 7) + ((lane & 8) ? 8 : 0), lm_feat = (lane & 16) ? 8 : 0;
 
-    const int row0 = q0 + warp * ROWS;                           // first of this warp's four rows
-    if (row0 >= N) return;
-    const int T = npad >> 5;
-    const float* kb = p.key_bias ? p.key_bias + static_cast<size_t>(b) * N : nullptr;
-
-    // ---- phase 1: scores of my keys for the four rows
-    float s[ROWS][TMAX];
+    for (int rg = warp; rg * 16 < N; rg += WARPS) {
+        const int row0 = rg * 16 + g, row1 = row0 + 8;            // this thread's two query rows
+        const bool ok0 = row0 < N, ok1 = row1 < N;
+        // foreground rows take the key bias; a background row's uniform -100 is softmax-invariant (vit_model.py:348-361)
+        const bool fg0 = has_bias && (!ok0 || kbs[row0] == 0.f), fg1 = has_bias && (!ok1 || kbs[row1] == 0.f);
+        // Q fragments of the group's 16 rows (rows past the sequence: zeros)
+        uint32_t qa[MAXKS][4];
+        {
+            const __nv_bfloat16* qr0 = base + static_cast<size_t>(row0) * tok_stride + 2 * t;
+            const __nv_bfloat16* qr1 = base + static_cast<size_t>(row1) * tok_stride + 2 * t;
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-        for (int t = 0; t < TMAX; ++t) s[r][t] = 0.f;
-    const float4* q4 = reinterpret_cast<const float4*>(Qs + static_cast<size_t>(warp) * hd * ROWS);
-    for (int d2 = 0; d2 < pairs; ++d2) {
-        const float4 qa = q4[2 * d2], qb = q4[2 * d2 + 1];
-#pragma unroll
-        for (int t = 0; t < TMAX; ++t) {
-            if (t < T) {
-                const uint32_t kk = *reinterpret_cast<const uint32_t*>(Ks + static_cast<size_t>(lane + 32 * t) * kp + 2 * d2);
-                const float k0 = __uint_as_float(kk << 16), k1 = __uint_as_float(kk & 0xffff0000u);
-                s[0][t] = fmaf(qa.x, k0, fmaf(qb.x, k1, s[0][t]));
-                s[1][t] = fmaf(qa.y, k0, fmaf(qb.y, k1, s[1][t]));
-                s[2][t] = fmaf(qa.z, k0, fmaf(qb.z, k1, s[2][t]));
-                s[3][t] = fmaf(qa.w, k0, fmaf(qb.w, k1, s[3][t]));
+            for (int ks = 0; ks < KS; ++ks) {
+                qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(qr0 + ks * 16) : 0u;
+                qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(qr1 + ks * 16) : 0u;
+                qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(qr0 + ks * 16 + 8) : 0u;
+                qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(qr1 + ks * 16 + 8) : 0u;
             }
         }
-    }
-    // ---- scale, mask (-100 on background keys for foreground query rows, vit_model.py:348-361; a background row's uniform
-    //      -100 is softmax-invariant), softmax
-    float* Pw = Ps + static_cast<size_t>(warp) * npad * ROWS;
+        float s[8][4];
+
+        // ---- sweep 1: row maximum and row sum
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        for (int kb = 0; kb < nblk; ++kb) {
+            score_block<KS>(s, qa, Ks, kp, kb * KBLK, N, p.scale, kbp, fg0, fg1, g, t);
+            float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int row = row0 + r;
-        const bool row_ok = row < N;
-        const bool row_fg = kb == nullptr || !row_ok || kb[row] == 0.f;
-        float mx = -INFINITY;
+            for (int jt = 0; jt < 8; ++jt) {
+                bm0 = fmaxf(bm0, fmaxf(s[jt][0], s[jt][1]));
+                bm1 = fmaxf(bm1, fmaxf(s[jt][2], s[jt][3]));
+            }
+            const float n0 = fmaxf(m0, quad_max(bm0)), n1 = fmaxf(m1, quad_max(bm1));      // key 0 is never masked: finite from block 0 on
+            l0 *= __expf(m0 - n0);
+            l1 *= __expf(m1 - n1);
+            m0 = n0;
+            m1 = n1;
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t) {
-            const int j = lane + 32 * t;
-            if (t < T && j < N) {
-                float x = s[r][t] * p.scale;
-                if (kb != nullptr && row_fg) x += kb[j];
-                s[r][t] = x;
-                mx = fmaxf(mx, x);
-            } else {
-                s[r][t] = -INFINITY;
+            for (int jt = 0; jt < 8; ++jt) {
+                l0 += __expf(s[jt][0] - m0) + __expf(s[jt][1] - m0);
+                l1 += __expf(s[jt][2] - m1) + __expf(s[jt][3] - m1);
             }
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
+        const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
+
+        // ---- sweep 2: P, outputs, O += P V
+        float o[NT][4];
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t) {
-            const float e = (t < T && s[r][t] > -INFINITY) ? __expf(s[r][t] - mx) : 0.f;
-            s[r][t] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
+        for (int nt = 0; nt < NT; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+        float* attn0 = (p.attn && ok0) ? p.attn + ((static_cast<size_t>(b) * H + h) * N + row0) * N : nullptr;
+        float* attn1 = (p.attn && ok1) ? p.attn + ((static_cast<size_t>(b) * H + h) * N + row1) * N : nullptr;
+        float* cls = (p.cls_rows && row0 == 0) ? p.cls_rows + (static_cast<size_t>(b) * H + h) * N : nullptr;
+        for (int kb = 0; kb < nblk; ++kb) {
+            score_block<KS>(s, qa, Ks, kp, kb * KBLK, N, p.scale, kbp, fg0, fg1, g, t);
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t) {
-            if (t < T) {
-                const int j = lane + 32 * t;
-                const float pv = s[r][t] * inv;
-                Pw[static_cast<size_t>(j) * ROWS + r] = pv;
-                if (row_ok && j < N) {
-                    if (p.attn != nullptr) p.attn[((static_cast<size_t>(b) * H + h) * N + row) * N + j] = pv;
-                    if (row == 0 && p.cls_rows != nullptr) p.cls_rows[(static_cast<size_t>(b) * H + h) * N + j] = pv;
+            for (int jt = 0; jt < 8; ++jt) {
+                s[jt][0] = __expf(s[jt][0] - m0) * inv0;
+                s[jt][1] = __expf(s[jt][1] - m0) * inv0;
+                s[jt][2] = __expf(s[jt][2] - m1) * inv1;
+                s[jt][3] = __expf(s[jt][3] - m1) * inv1;
+                const int j = kb * KBLK + jt * 8 + 2 * t;
+                if (attn0) {
+                    if (j < N) attn0[j] = s[jt][0];
+                    if (j + 1 < N) attn0[j + 1] = s[jt][1];
+                }
+                if (attn1) {
+                    if (j < N) attn1[j] = s[jt][2];
+                    if (j + 1 < N) attn1[j + 1] = s[jt][3];
+                }
+                if (cls) {
+                    if (j < N) cls[j] = s[jt][0];
+                    if (j + 1 < N) cls[j + 1] = s[jt][1];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < KBLK / 16; ++kk) {             // 16 keys per k-step = two score tiles
+                uint32_t pa[4];
+                pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+                pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+                pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+                pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+                const __nv_bfloat16* vrow = Vs + static_cast<size_t>(kb * KBLK + kk * 16 + lm_key) * kp + lm_feat;
+#pragma unroll
+                for (int nt = 0; nt < NT; nt += 2) {
+                    uint32_t vb[4];                               // (b0, b1) of feature tile nt, (b0, b1) of tile nt + 1
+                    ldsm_x4_trans(vb, vrow + nt * 8);
+                    mma_bf16_16816(o[nt], pa, vb[0], vb[1]);
+                    mma_bf16_16816(o[nt + 1], pa, vb[2], vb[3]);
                 }
             }
         }
+        if (ok0) {
+            __nv_bfloat16* out0 = p.out + (static_cast<size_t>(b) * N + row0) * H * HD + static_cast<size_t>(h) * HD + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<uint32_t*>(out0 + nt * 8) = pack_bf16x2(o[nt][0], o[nt][1]);
+        }
+        if (ok1) {
+            __nv_bfloat16* out1 = p.out + (static_cast<size_t>(b) * N + row1) * H * HD + static_cast<size_t>(h) * HD + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<uint32_t*>(out1 + nt * 8) = pack_bf16x2(o[nt][2], o[nt][3]);
+        }
     }
-    __syncwarp();
+}
 
-    // ---- phase 2: O = P V, lane owns features lane + 32 u
-    float o[ROWS][UMAX];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-        for (int u = 0; u < UMAX; ++u) o[r][u] = 0.f;
-    const float4* p4 = reinterpret_cast<const float4*>(Pw);
-    for (int j = 0; j < N; ++j) {
-        const float4 pj = p4[j];
-#pragma unroll
-        for (int u = 0; u < UMAX; ++u) {
-            const int d = lane + 32 * u;
-            if (d < hd) {
-                const float v = __bfloat162float(Vs[static_cast<size_t>(j) * hd + d]);
-                o[0][u] = fmaf(pj.x, v, o[0][u]);
-                o[1][u] = fmaf(pj.y, v, o[1][u]);
-                o[2][u] = fmaf(pj.z, v, o[2][u]);
-                o[3][u] = fmaf(pj.w, v, o[3][u]);
-            }
-        }
+template <int KS>
+static int launch(const Params& p, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        VTC_CUDA(cudaFuncSetAttribute(attention_generic_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
     }
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int row = row0 + r;
-        if (row >= N) break;
-        __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * H * hd + static_cast<size_t>(h) * hd;
-#pragma unroll
-        for (int u = 0; u < UMAX; ++u) {
-            const int d = lane + 32 * u;
-            if (d < hd) dst[d] = __float2bfloat16_rn(o[r][u]);
-        }
-    }
+    dim3 grid(p.H, p.B);
+    attention_generic_kernel<KS><<<grid, WARPS * 32, smem, stream>>>(p);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
 }
 }  // namespace ag
 
@@ -185,9 +240,9 @@ int attention_generic(const void* qkv, const float* key_bias, void* out, float* 
     using namespace ag;
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention_generic: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention_generic: bad shape");
-    VTC_REQUIRE(head_dim >= 16 && head_dim % 16 == 0 && head_dim <= 32 * UMAX, VTC_ERR_SHAPE, "attention_generic: head_dim %d (multiple of 16 up to %d)",
-                head_dim, 32 * UMAX);
-    VTC_REQUIRE(n_tokens <= 32 * TMAX, VTC_ERR_SHAPE, "attention_generic: %d tokens > %d", n_tokens, 32 * TMAX);
+    VTC_REQUIRE(head_dim >= 16 && head_dim % 16 == 0 && head_dim <= 16 * MAXKS, VTC_ERR_SHAPE, "attention_generic: head_dim %d (multiple of 16 up to %d)",
+                head_dim, 16 * MAXKS);
+    VTC_REQUIRE(n_tokens <= kAttentionGenericMaxTokens, VTC_ERR_SHAPE, "attention_generic: %d tokens > %d", n_tokens, kAttentionGenericMaxTokens);
     VTC_REQUIRE(heads <= 65535 && batch <= 65535, VTC_ERR_SHAPE, "attention_generic: grid limits");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention_generic: scale must be positive");
     int rc = check_arch();
@@ -202,19 +257,20 @@ int attention_generic(const void* qkv, const float* key_bias, void* out, float* 
     p.N = n_tokens;
     p.H = heads;
     p.hd = head_dim;
-    p.npad = (n_tokens + 31) & ~31;
+    p.npad = cdiv(n_tokens, KBLK) * KBLK;
     p.scale = scale;
     const size_t smem = smem_bytes(p.npad, head_dim);
     VTC_REQUIRE(smem <= 232448, VTC_ERR_SHAPE, "attention_generic: %zu bytes of shared memory needed", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        VTC_CUDA(cudaFuncSetAttribute(attention_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
+    switch (head_dim / 16) {
+        case 1: return launch<1>(p, smem, stream);
+        case 2: return launch<2>(p, smem, stream);
+        case 3: return launch<3>(p, smem, stream);
+        case 4: return launch<4>(p, smem, stream);
+        case 5: return launch<5>(p, smem, stream);
+        case 6: return launch<6>(p, smem, stream);
+        case 7: return launch<7>(p, smem, stream);
+        default: return launch<8>(p, smem, stream);
     }
-    dim3 grid(cdiv(n_tokens, QT), heads, batch);
-    attention_generic_kernel<<<grid, WARPS * 32, smem, stream>>>(p);
-    VTC_CHECK_LAUNCH();
-    return VTC_OK;
 }
 
 }  // namespace vtc
