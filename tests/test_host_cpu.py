@@ -41,7 +41,7 @@ def test_library_is_sm100a_only_and_has_tcgen05(lib_built):
     for line in sass.splitlines():
         if "Function :" in line:
             func = line
-        elif "HMMA." in line:
+        elif " HMMA." in line:                      # (UTCHMMA is the tcgen05 mnemonic)
             assert "attention_generic" in func, func
 
 
