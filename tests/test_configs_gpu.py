@@ -160,8 +160,14 @@ def test_vit_h14_224_factory_runs_through_the_general_shape_path(lib_built):
     assert float((o.attn_mean.sum(-1) - 1).abs().max()) < 1e-4
     out = model(x.to("cuda:0"))                       # reference-compatible 6-tuple: last 12 layers (vit_model.py:322)
     assert len(out[1]) == 12 and out[1][0].shape == (1, 16, 257, 257) and out[5].shape == (1, 16, 1280)
-    with pytest.raises(Exception):                    # uint8 ingest needs a patch size that is a multiple of 8
-        model.forward_cam_u8(torch.zeros((1, 224, 224, 3), dtype=torch.uint8, device="cuda:0"))
+    # uint8 ingest through the general-shape patch kernel: bit-identical to the fp32 path on Normalize(ToTensor(u8))
+    u8 = torch.randint(0, 256, (1, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    mean, std = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
+    xf = ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(model.forward_cam_u8(u8.to("cuda:0")).logits, model.forward_cam(xf.to("cuda:0")).logits)
+    with pytest.raises(Exception):                    # the fp32 (split) mode stays on head_dim 64
+        model.set_precision("fp32").forward_cam(x.to("cuda:0"))
+    model.set_precision("bf16")
     del model
     torch.cuda.empty_cache()
     # (b) head_dim 48, patch 16, with the mask active (peaked weights), teacher-forced decisions

@@ -227,6 +227,44 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16*
     }
 }
 
+// uint8 HWC input, any patch size, K padded to kp (the general-shape counterpart of patchify_u8: same two fp32 operations)
+__global__ void patchify_generic_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int S, int p, int kp, size_t total,
+                                           NormParams nm) {
+    const int g = S / p;
+    const int kdim = 3 * p * p;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t row = i / kp;
+        const int k = static_cast<int>(i - row * kp);
+        float v = 0.f;
+        if (k < kdim) {
+            const int c = k / (p * p), rem = k - c * p * p, kh = rem / p, kw = rem - kh * p;
+            const size_t b = row / (static_cast<size_t>(g) * g);
+            const int pr = static_cast<int>(row - b * g * g), py = pr / g, px = pr - py * g;
+            const float u = static_cast<float>(x[((b * S + (py * p + kh)) * S + px * p + kw) * 3 + c]);
+            v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nm.mean[c]), nm.std[c]);
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+int patchify_generic_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, int kp,
+                        cudaStream_t stream) {
+    VTC_REQUIRE(x && mean && std && patches, VTC_ERR_ARG, "patchify_u8: null pointer");
+    VTC_REQUIRE(batch > 0 && img > 0 && patch > 0 && img % patch == 0 && kp >= 3 * patch * patch, VTC_ERR_SHAPE, "patchify_u8: bad shape");
+    for (int c = 0; c < 3; ++c) VTC_REQUIRE(std[c] != 0.f, VTC_ERR_ARG, "patchify_u8: std[%d] is zero", c);
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    NormParams nm{{mean[0], mean[1], mean[2]}, {std[0], std[1], std[2]}};
+    const size_t total = static_cast<size_t>(batch) * (img / patch) * (img / patch) * kp;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    patchify_generic_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(patches), img, patch, kp, total, nm);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 int patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, cudaStream_t stream, int split) {
     VTC_REQUIRE(x && mean && std && patches, VTC_ERR_ARG, "patchify_u8: null pointer");
     VTC_REQUIRE(batch > 0 && img > 0 && patch > 0, VTC_ERR_SHAPE, "patchify_u8: bad shape");

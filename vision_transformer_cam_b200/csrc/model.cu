@@ -133,7 +133,6 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
                    uint32_t flags, cudaStream_t st) {
     VTC_REQUIRE(m && (in.f32 || (in.u8 && in.mean && in.std)) && o && workspace, VTC_ERR_ARG, "forward: null pointer");
     VTC_REQUIRE(!in.u8 || m->cfg.in_c == 3, VTC_ERR_SHAPE, "forward: uint8 HWC input needs in_c == 3");
-    VTC_REQUIRE(!in.u8 || !m->generic_patch, VTC_ERR_SHAPE, "forward: uint8 input needs a patch size that is a multiple of 8");
     VTC_REQUIRE(!m->split || (m->HD == 64 && !m->generic_patch), VTC_ERR_SHAPE,
                 "forward: the fp32 (split) mode needs head_dim 64 and a patch size that is a multiple of 8");
     VTC_REQUIRE(m->packed, VTC_ERR_ARG, "forward: vtc_model_pack_weights has not been called");
@@ -161,7 +160,9 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
 
     // ---- patch embedding + token assembly (vit_model.py:306-314)
     float* t_cur = ws.tok;
-    if (in.u8) VTC_STEP(VTC_PROF_PATCHIFY, patchify_u8(in.u8, in.mean, in.std, ws.patches, B, m->cfg.img_size, m->cfg.patch_size, st, sp));
+    if (in.u8 && m->generic_patch)
+        VTC_STEP(VTC_PROF_PATCHIFY, patchify_generic_u8(in.u8, in.mean, in.std, ws.patches, B, m->cfg.img_size, m->cfg.patch_size, m->KP, st));
+    else if (in.u8) VTC_STEP(VTC_PROF_PATCHIFY, patchify_u8(in.u8, in.mean, in.std, ws.patches, B, m->cfg.img_size, m->cfg.patch_size, st, sp));
     else if (m->generic_patch) VTC_STEP(VTC_PROF_PATCHIFY, patchify_generic(in.f32, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, m->KP, st));
     else VTC_STEP(VTC_PROF_PATCHIFY, patchify(in.f32, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st, sp));
     VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));

@@ -23,6 +23,8 @@ int patchify(const float* x, void* patches, int batch, int in_c, int img, int pa
 // decoded u8 HWC images [B,S,S,3] -> normalised bf16 patch matrix; mean / std are HOST arrays of 3 floats
 // any patch size, K padded with zeros to kp columns (bf16 mode, fp32 input)
 int patchify_generic(const float* x, void* patches, int batch, int in_c, int img, int patch, int kp, cudaStream_t stream);
+int patchify_generic_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, int kp,
+                        cudaStream_t stream);
 int cast_bf16_pad(const float* src, void* dst, size_t rows, int cols, int ld, cudaStream_t stream);
 int patchify_u8(const uint8_t* x, const float* mean, const float* std, void* patches, int batch, int img, int patch, cudaStream_t stream,
                 int split = 0);
