@@ -116,67 +116,79 @@ int cls_layer_map(const float* cls_rows, float* map, int layers, int first, int 
 
 // ---- classic CAM ---------------------------------------------------------------------------------------------------
 // cam[b,c,p] = <W[c,:], F[b,p,:]> on the block-L patch tokens, ReLU, per-map min-max (t.py:66-70, utils.py:84-85).
-// One CTA per image: W staged once in shared memory, each warp streams patch rows with float4 loads, C running dot
-// products per lane, shuffle reduction, raw maps kept in shared memory for the normalisation pass.
-constexpr int CAM_MAXC = 32;     // classes per pass (more classes: several passes over the tokens)
-constexpr int CAM_PB = 4;        // patches per warp iteration: each W float4 read from smem feeds 4 patches
-template <int CB>
-__device__ __forceinline__ void cam_rows(const float* __restrict__ F, const float* __restrict__ ws, float* __restrict__ raw, int P, int D,
-                                         int c0, int cn, int relu, int warp, int lane) {
-    const int nv = D / 128;
-    for (int p0 = warp * CAM_PB; p0 < P; p0 += 8 * CAM_PB) {
-        float acc[CAM_PB][CB];
+// A [P x D] x [D x C] product per image with C = 20: HBM-bound (602 KB of fp32 tokens per image, read once).  One CTA per
+// image, one warp per 16-patch tile; the product runs on the warp-level tensor cores with fp32-equivalent operands: tokens
+// and weights are split into (hi, lo) bf16 pairs on the fly (x ~= hi + lo, 16 mantissa bits) and every product is
+// hi.hi + lo.hi + hi.lo with fp32 accumulation -- three mma.sync per k-step instead of 40 running dot products and 40
+// shuffle reductions per lane, which made the first (FMA-pipe) version of this kernel latency-bound at 13 % of the HBM rate.
+// W sits in shared memory as [C8][D+8] hi / lo (bank-conflict-free B fragments), the raw maps as [C][P] for the min-max pass.
+__device__ __forceinline__ void mma_bf16_16816_acc(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pair(float2 v, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(v.x, v.y);
+    lo = pack_bf16x2(v.x - __uint_as_float(hi << 16), v.y - __uint_as_float(hi & 0xffff0000u));
+}
+
+template <int NT>      // class tiles of 8: C <= 8 * NT
+__global__ void __launch_bounds__(512) cam_project_kernel(const float* __restrict__ tokens, const float* __restrict__ w, float* __restrict__ cam,
+                                                          int N, int D, int C, int relu, float eps) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int P = N - 1;
+    const int wp = D + 8;                                                   // W row pitch (bf16)
+    __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(sm_raw);          // [8 NT][wp]
+    __nv_bfloat16* wlo = whi + static_cast<size_t>(8 * NT) * wp;
+    float* raw = reinterpret_cast<float*>(wlo + static_cast<size_t>(8 * NT) * wp);      // [C][P]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < 8 * NT * (D / 2); i += blockDim.x) {
+        const int c = i / (D / 2), d2 = i - c * (D / 2);
+        uint32_t hi = 0u, lo = 0u;
+        if (c < C) split_pair(__ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(c) * D) + d2), hi, lo);
+        *reinterpret_cast<uint32_t*>(whi + static_cast<size_t>(c) * wp + 2 * d2) = hi;
+        *reinterpret_cast<uint32_t*>(wlo + static_cast<size_t>(c) * wp + 2 * d2) = lo;
+    }
+    __syncthreads();
+    const float* F = tokens + (static_cast<size_t>(b) * N + 1) * D;
+    for (int tile = warp; tile * 16 < P; tile += nwarps) {
+        const int p0 = tile * 16 + g, p1 = p0 + 8;
+        const float* f0 = F + static_cast<size_t>(p0 < P ? p0 : P - 1) * D + 2 * t;
+        const float* f1 = F + static_cast<size_t>(p1 < P ? p1 : P - 1) * D + 2 * t;
+        float acc[NT][4];
 #pragma unroll
-        for (int q = 0; q < CAM_PB; ++q)
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 4
+        for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t ah[4], al[4];
+            split_pair(*reinterpret_cast<const float2*>(f0 + ks * 16), ah[0], al[0]);
+            split_pair(*reinterpret_cast<const float2*>(f1 + ks * 16), ah[1], al[1]);
+            split_pair(*reinterpret_cast<const float2*>(f0 + ks * 16 + 8), ah[2], al[2]);
+            split_pair(*reinterpret_cast<const float2*>(f1 + ks * 16 + 8), ah[3], al[3]);
 #pragma unroll
-            for (int c = 0; c < CB; ++c) acc[q][c] = 0.f;
-        for (int i = 0; i < nv; ++i) {
-            const int d = (lane + 32 * i) * 4;
-            float4 f[CAM_PB];
-#pragma unroll
-            for (int q = 0; q < CAM_PB; ++q) {
-                const int pp = (p0 + q < P) ? p0 + q : P - 1;
-                f[q] = ld_stream_f4(F + static_cast<size_t>(pp) * D + d);
-            }
-#pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                if (c < cn) {
-                    const float4 wv = *reinterpret_cast<const float4*>(ws + (c0 + c) * D + d);
-#pragma unroll
-                    for (int q = 0; q < CAM_PB; ++q)
-                        acc[q][c] = fmaf(f[q].x, wv.x, fmaf(f[q].y, wv.y, fmaf(f[q].z, wv.z, fmaf(f[q].w, wv.w, acc[q][c]))));
-                }
+            for (int nt = 0; nt < NT; ++nt) {
+                const size_t off = static_cast<size_t>(nt * 8 + g) * wp + ks * 16 + 2 * t;
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(whi + off), bh1 = *reinterpret_cast<const uint32_t*>(whi + off + 8);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wlo + off), bl1 = *reinterpret_cast<const uint32_t*>(wlo + off + 8);
+                mma_bf16_16816_acc(acc[nt], ah, bh0, bh1);
+                mma_bf16_16816_acc(acc[nt], al, bh0, bh1);
+                mma_bf16_16816_acc(acc[nt], ah, bl0, bl1);
             }
         }
 #pragma unroll
-        for (int q = 0; q < CAM_PB; ++q)
+        for (int nt = 0; nt < NT; ++nt) {
+            const int c = nt * 8 + 2 * t;
 #pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                if (c < cn) {
-                    const float s = warp_sum(acc[q][c]);
-                    if (lane == 0 && p0 + q < P) raw[(c0 + c) * P + p0 + q] = relu ? fmaxf(s, 0.f) : s;
-                }
+            for (int e = 0; e < 4; ++e) {
+                const int cc = c + (e & 1), pp = (e & 2) ? p1 : p0;
+                if (cc < C && pp < P) raw[cc * P + pp] = relu ? fmaxf(acc[nt][e], 0.f) : acc[nt][e];
             }
-    }
-}
-
-__global__ void __launch_bounds__(256) cam_project_kernel(const float* __restrict__ tokens, const float* __restrict__ w, float* __restrict__ cam,
-                                                          int N, int D, int C, int relu, float eps) {
-    extern __shared__ float sm[];
-    float* ws = sm;                 // [C][D]
-    float* raw = sm + C * D;        // [C][P]
-    const int P = N - 1;
-    const int b = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < C * D / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = ldg_f4(w + 4 * i);
-    __syncthreads();
-    const float* F = tokens + (static_cast<size_t>(b) * N + 1) * D;
-    for (int c0 = 0; c0 < C; c0 += 10) {          // 10 classes x 4 patches = 40 accumulators per lane
-        const int cn = (C - c0 < 10) ? C - c0 : 10;
-        cam_rows<10>(F, ws, raw, P, D, c0, cn, relu, warp, lane);
+        }
     }
     __syncthreads();
-    for (int c = warp; c < C; c += 8) {
+    for (int c = warp; c < C; c += nwarps) {
         float mn = INFINITY, mx = -INFINITY;
         for (int p = lane; p < P; p += 32) { const float v = raw[c * P + p]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
         mn = warp_min(mn);
@@ -187,22 +199,41 @@ __global__ void __launch_bounds__(256) cam_project_kernel(const float* __restric
     }
 }
 
+template <int NT>
+static int launch_cam_project(const float* tokens, const float* w, float* cam, int batch, int n_tokens, int dim, int classes, int relu, float eps,
+                              cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(2) * 8 * NT * (dim + 8) * 2 + sizeof(float) * static_cast<size_t>(classes) * (n_tokens - 1);
+    VTC_REQUIRE(smem <= 220 * 1024, VTC_ERR_SHAPE, "cam_project: %zu bytes of smem", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        VTC_CUDA(cudaFuncSetAttribute(cam_project_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    int warps = cdiv(n_tokens - 1, 16);
+    if (warps > 16) warps = 16;
+    if (warps < 1) warps = 1;
+    cam_project_kernel<NT><<<batch, warps * 32, smem, stream>>>(tokens, w, cam, n_tokens, dim, classes, relu, eps);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 int cam_project(const float* tokens, const float* w, float* cam, int batch, int n_tokens, int dim, int classes, int relu, float eps, cudaStream_t stream) {
     VTC_REQUIRE(tokens && w && cam, VTC_ERR_ARG, "cam_project: null pointer");
     VTC_REQUIRE(batch > 0 && n_tokens > 1 && dim % 128 == 0 && classes > 0 && classes <= 64, VTC_ERR_SHAPE,
                 "cam_project: dim %d (multiple of 128) classes %d (<= 64)", dim, classes);
+    VTC_REQUIRE(((reinterpret_cast<uintptr_t>(tokens) | reinterpret_cast<uintptr_t>(w)) & 7) == 0, VTC_ERR_ARG, "cam_project: pointers must be 8-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(classes) * dim + static_cast<size_t>(classes) * (n_tokens - 1));
-    VTC_REQUIRE(smem <= 200 * 1024, VTC_ERR_SHAPE, "cam_project: %zu bytes of smem", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        VTC_CUDA(cudaFuncSetAttribute(cam_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
+    switch (cdiv(classes, 8)) {
+        case 1: return launch_cam_project<1>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 2: return launch_cam_project<2>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 3: return launch_cam_project<3>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 4: return launch_cam_project<4>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 5: return launch_cam_project<5>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 6: return launch_cam_project<6>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 7: return launch_cam_project<7>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        default: return launch_cam_project<8>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
     }
-    cam_project_kernel<<<batch, 256, smem, stream>>>(tokens, w, cam, n_tokens, dim, classes, relu, eps);
-    VTC_CHECK_LAUNCH();
-    return VTC_OK;
 }
 
 // ---- row-wise / max -------------------------------------------------------------------------------------------------
