@@ -241,6 +241,13 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int OUT_BUF_BYTES = 128 * 128;       // 128 rows x 128 B staging tile
 constexpr int EPI_RESID_LN = 4;                // internal epilogue id (see below); the public ids are VTC_EPI_*
+// Patch embedding (vit_model.py:64-83, 308-314): out[b, 1 + p, :] = acc + bias + pos_embed[1 + p, :] in fp32.  The row remap
+// (196 patch rows per image land behind that image's CLS row) is done by the TMA: both the patch matrix (A) and the output are
+// 3-D maps [cols, patches, B] (the output's base one row into the token buffer), and a 256-row pair tile never leaves its
+// image -- tile (b, q) covers patches q*256 .. of image b, the rows past the image's last patch are zero-filled on the load
+// and clipped on the store (196 patches: one tile per image, 23 % of its MMA rows idle; a TMA store does not take the
+// negative start coordinate that a tile crossing into the next image would need).
+constexpr int EPI_PATCH = 5;
 __host__ __device__ constexpr int stages_of(int) { return 5; }
 __host__ __device__ constexpr int out_bufs_of(int) { return 4; }       // [2 halves][2 buffers]
 __host__ __device__ constexpr int off_out_of(int epi) { return stages_of(epi) * STAGE_BYTES; }
@@ -260,6 +267,9 @@ struct Params {
     int nslices;
     float eps;
     __nv_bfloat16* out_bf16;   // residual epilogue: bf16 copy of the new residual stream [M,N]
+    const float* pos;          // EPI_PATCH: pos_embed [1 + patches, N]
+    int patches;               // EPI_PATCH: patch rows per image
+    int tiles_per_img;         // EPI_PATCH: 256-row pair tiles per image
 };
 }  // namespace gemm2
 
@@ -319,7 +329,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+    const int num_m = (EPI == EPI_PATCH) ? (p.M / p.patches) * p.tiles_per_img : (p.M + 2 * BM - 1) / (2 * BM);
     const int num_n = p.N / BN;
     const int num_tiles = num_m * num_n;
     const int nk1 = p.K / BK;
@@ -335,12 +345,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tile = p.reverse ? num_tiles - 1 - t_ : t_;
                 const int m0 = (tile / num_n) * (2 * BM) + rank * BM;
                 const int n0 = (tile % num_n) * BN + rank * (BN / 2);
+                const int pimg = (EPI == EPI_PATCH) ? (tile / num_n) / p.tiles_per_img : 0;                       // EPI_PATCH: image,
+                const int prow = (EPI == EPI_PATCH) ? ((tile / num_n) % p.tiles_per_img) * (2 * BM) + rank * BM : 0;   // first patch of this CTA
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int seg = kb / nk1, kr = (kb - seg * nk1) * BK;      // split: A = hi, lo, hi ; W = hi, hi, lo
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);     // both CTAs' bytes land on this barrier
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
-                    tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kr + (seg == 1 ? p.K : 0), m0);
+                    if (EPI == EPI_PATCH) tma_load_3d_2sm(a_dst, &tmA, &full_bar[s], kr + (seg == 1 ? p.K : 0), prow, pimg);
+                    else tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kr + (seg == 1 ? p.K : 0), m0);
                     tma_load_2d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], kr + (seg == 2 ? p.K : 0), n0);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -383,7 +396,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool issuer = (quarter == 0) && (lane == 0);
         const uint32_t bar_id = 1 + half;
         uint8_t* stage_out = smem + OFF_OUT + half * (out_bufs_of(EPI) / 2) * OUT_BUF_BYTES;
-        constexpr int CHUNK_COLS = (EPI == VTC_EPI_BIAS_RESIDUAL || EPI == EPI_RESID_LN) ? 32 : 64;     // 128-byte rows
+        constexpr int CHUNK_COLS = (EPI == VTC_EPI_BIAS_RESIDUAL || EPI == EPI_RESID_LN || EPI == EPI_PATCH) ? 32 : 64;     // 128-byte rows
         constexpr int NCHUNK = 128 / CHUNK_COLS;
         int as = 0;
         uint32_t aph = 0;
@@ -506,13 +519,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int col0 = half * 128 + c * CHUNK_COLS;
                 const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0);
                 uint32_t pk[32];
-                uint32_t pl[(EPI == VTC_EPI_BIAS_RESIDUAL || !SPLIT) ? 1 : 32];      // split mode: low halves
-                if (EPI == VTC_EPI_BIAS_RESIDUAL) {
+                uint32_t pl[(EPI == VTC_EPI_BIAS_RESIDUAL || EPI == EPI_PATCH || !SPLIT) ? 1 : 32];      // split mode: low halves
+                if (EPI == VTC_EPI_BIAS_RESIDUAL || EPI == EPI_PATCH) {
                     tmem_ld_32x32b_x32(t_row + c * 32, pk);
                     tmem_ld_wait();
+                    // EPI_PATCH: + pos_embed[1 + patch index of my row] (what the reference adds after the concat, vit_model.py:313)
+                    const int prow = (EPI == EPI_PATCH) ? ((tile / num_n) % p.tiles_per_img) * (2 * BM) + rank * BM + r_local : 0;
+                    const float4* pos4 = (EPI == EPI_PATCH)
+                        ? reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + (prow < p.patches ? prow : p.patches - 1)) * p.N + n0 + col0) : nullptr;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = __ldg(bias4 + j);
+                        float4 b4 = __ldg(bias4 + j);
+                        if (EPI == EPI_PATCH) {
+                            const float4 q4 = __ldg(pos4 + j);
+                            b4.x += q4.x; b4.y += q4.y; b4.z += q4.z; b4.w += q4.w;
+                        }
                         pk[4 * j + 0] = __float_as_uint(__uint_as_float(pk[4 * j + 0]) + b4.x);
                         pk[4 * j + 1] = __float_as_uint(__uint_as_float(pk[4 * j + 1]) + b4.y);
                         pk[4 * j + 2] = __float_as_uint(__uint_as_float(pk[4 * j + 2]) + b4.z);
@@ -558,7 +579,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         pk[2 * j + 1] = pack_bf16x2(v2, v3);
                         pk[16 + 2 * j] = pack_bf16x2(w0, w1);
                         pk[16 + 2 * j + 1] = pack_bf16x2(w2, w3);
-                        if (EPI != VTC_EPI_BIAS_RESIDUAL) {
+                        if (EPI != VTC_EPI_BIAS_RESIDUAL && EPI != EPI_PATCH) {
                             if (SPLIT) {
                                 pl[2 * j] = pack_bf16x2(v0 - __uint_as_float(pk[2 * j] << 16), v1 - __uint_as_float(pk[2 * j] & 0xffff0000u));
                                 pl[2 * j + 1] = pack_bf16x2(v2 - __uint_as_float(pk[2 * j + 1] << 16), v3 - __uint_as_float(pk[2 * j + 1] & 0xffff0000u));
@@ -580,14 +601,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
                     if (issuer) {
-                        if (EPI == VTC_EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, m0);
-                        else tma_store_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, m0);
+                        if (EPI == VTC_EPI_BIAS_RESIDUAL) {
+                            tma_reduce_add_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, m0);
+                        } else if (EPI == EPI_PATCH) {
+                            const int b0 = (tile / num_n) / p.tiles_per_img, p0 = ((tile / num_n) % p.tiles_per_img) * (2 * BM) + rank * BM;
+                            tma_store_3d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, p0, b0);
+                        } else {
+                            tma_store_2d(&tmO, stage_out + buf * OUT_BUF_BYTES, col, m0);
+                        }
                         tma_store_commit();
                     }
                     buf ^= 1;
                 };
                 stage_and_store(pk, n0 + col0);
-                if (EPI != VTC_EPI_BIAS_RESIDUAL) {
+                if (EPI != VTC_EPI_BIAS_RESIDUAL && EPI != EPI_PATCH) {
                     if (SPLIT) stage_and_store(pl, p.N + n0 + col0);
                 }
             }
@@ -613,7 +640,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
         VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI, SPLIT, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::smem_bytes_of(EPI)));
         configured = true;
     }
-    const int tiles = cdiv(p.M, 2 * gemm2::BM) * (p.N / gemm2::BN);
+    const int tiles = (EPI == gemm2::EPI_PATCH ? (p.M / p.patches) * p.tiles_per_img : cdiv(p.M, 2 * gemm2::BM)) * (p.N / gemm2::BN);
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = tiles;
     cudaLaunchConfig_t cfg{};
@@ -654,8 +681,10 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
                 "gemm: patch-embed epilogue needs pos_embed and M %% (tokens-1) == 0");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    // the single-CTA kernel has no split bf16 epilogue: in split mode it only serves the fp32-output patch embedding
-    const bool v1 = (use_v1() && !split) || epilogue == VTC_EPI_PATCH_EMBED;
+    // patch embedding through the CTA-pair kernel (3-D TMA store does the row remap) unless the patch count per image is
+    // smaller than a 128-row staging tile (a tile would then span three images: ViT-B/32 has 49) -> single-CTA kernel
+    const bool patch_pair = epilogue == VTC_EPI_PATCH_EMBED && tokens - 1 >= gemm2::BM && !use_v1();
+    const bool v1 = (use_v1() && !split) || (epilogue == VTC_EPI_PATCH_EMBED && !patch_pair);
     const uint64_t kcols = static_cast<uint64_t>(split ? 2 : 1) * K;       // (hi | lo) halves side by side
     CUtensorMap tmA, tmB;
     {
@@ -682,7 +711,26 @@ int gemm_bf16(const void* A, const void* W, const float* bias, const float* resi
         }
     }
     CUtensorMap tmO;
-    gemm2::Params p2{bias, M, N, K, split, reverse, nullptr, nullptr, 0, 0.f, nullptr};
+    gemm2::Params p2{bias, M, N, K, split, reverse, nullptr, nullptr, 0, 0.f, nullptr, nullptr, 0, 0};
+    if (patch_pair) {
+        const int patches = tokens - 1;
+        p2.pos = pos;
+        p2.patches = patches;
+        p2.tiles_per_img = cdiv(patches, 2 * gemm2::BM);
+        {   // A as [K, patches, B]: rows past an image's last patch come back as zeros
+            uint64_t adims[3] = {kcols, (uint64_t)patches, (uint64_t)(M / patches)};
+            uint64_t astrides[2] = {kcols * 2, (uint64_t)patches * kcols * 2};
+            uint32_t abox[3] = {gemm::BK, 128, 1};
+            rc = make_tmap_bf16(&tmA, A, 3, adims, astrides, abox);
+            if (rc != VTC_OK) return rc;
+        }
+        uint64_t dims[3] = {(uint64_t)N, (uint64_t)patches, (uint64_t)(M / patches)};
+        uint64_t strides[2] = {(uint64_t)N * 4, (uint64_t)tokens * N * 4};
+        uint32_t box[3] = {32, 128, 1};
+        rc = make_tmap_f32(&tmO, static_cast<float*>(out) + N, 3, dims, strides, box);       // base: row 1 of image 0 (behind its CLS row)
+        if (rc != VTC_OK) return rc;
+        return split ? launch_gemm2<gemm2::EPI_PATCH, true>(tmA, tmB, tmO, p2, stream) : launch_gemm2<gemm2::EPI_PATCH, false>(tmA, tmB, tmO, p2, stream);
+    }
     if (epilogue == VTC_EPI_BIAS_RESIDUAL) {
         // out = residual + A.W^T + bias, with the add done by the TMA reduction into `out`
         if (out != static_cast<const void*>(residual))
