@@ -266,8 +266,10 @@ VTC_API int vtc_cls_stat(const float* cls_rows, float* cls_map, float* gmax, int
  * per_image); key_bias[b,0] = 0, key_bias[b,1+p] = -100*bg.  forced_bg [B,P] overrides the decision when non-NULL. */
 VTC_API int vtc_cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image,
                  uint8_t* bg, float* key_bias, int32_t batch, int32_t n_tokens, void* stream);
-/* high-weight-patch head + final norm + head (vit_model.py:374-422). tokens [B,N,D] fp32 (block-L output). */
-VTC_API int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const int32_t* forced_topk,
+/* high-weight-patch head + final norm + head (vit_model.py:374-422). tokens [B,N,D] fp32 (block-L output).  The top-16
+ * runs on cls_map / max exactly like vit_model.py:372,377 (max = gmax[0], the batch-global one, or the image's own when
+ * gmax is NULL): descending, ties to the smaller index, NaN ranked first (torch.topk). */
+VTC_API int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const float* gmax, const int32_t* forced_topk,
                    float* logits, float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int32_t batch, void* stream);
 
 /* ---- CAM / rollout / pseudo-label post-processing ----------------------------------------------

@@ -144,6 +144,29 @@ def peaked(sd: Dict[str, torch.Tensor], qkv_scale: float = 5.0, head1_scale: flo
     return out
 
 
+def masked(sd: Dict[str, torch.Tensor], qk_scale: float = 3.5, first_layer: int = 3, head1_scale: float = 30.0,
+           head1_bias: float = 1.0) -> Dict[str, torch.Tensor]:
+    """The 'masked' parity regime: the q and k rows of `attn.qkv.weight` (v untouched) of blocks >= `first_layer`
+    are scaled by 3.5, head1 as in `peaked`.  The attention logits stay at a natural scale (|S| of a few units, the
+    residual stream is not swamped by the attention output as in `peaked`), yet the CLS row varies enough for the
+    layer>4 background mask of vit_model.py:325-361 to fire on 0.5-0.6 of the patches (layers 5..11; asserted to lie
+    in (0.1, 0.9) where it is used).  A CPU emulation of bf16-operand arithmetic (tools/emulate_bf16.py) sits at
+    6.5e-3 of the fp32 logits here, i.e. the north-star 1e-2 bar is meaningful in this regime."""
+    out = {k: v.clone() for k, v in sd.items()}
+    for k in out:
+        if k.endswith("attn.qkv.weight") and int(k.split(".")[1]) >= first_layer:
+            two_d = 2 * out[k].shape[1]
+            out[k][:two_d] *= qk_scale
+    out["head1.weight"] *= head1_scale
+    out["head1.bias"] += head1_bias
+    return out
+
+
+# the batch-global max of vit_model.py:335 grows with the batch (one outlier patch among 256 x 196), so a background
+# fraction inside (0.1, 0.9) (0.36-0.40 on layers 5..11) needs a slightly smaller q/k scale at B = 256 than at B = 3
+MASKED_B256_QK_SCALE = 3.0
+
+
 def make_images(first_index: int, count: int, size: int = 224, device="cpu") -> torch.Tensor:
     """Synthetic ImageNet-normalised images: N(0,1), seed 1000+global index."""
     imgs = []

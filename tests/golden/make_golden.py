@@ -26,6 +26,7 @@ from oracle import ref_shim  # noqa: E402
 from oracle import vit_forward as VF  # noqa: E402
 from oracle import postproc as PP  # noqa: E402
 
+MASKED_B256_QK_SCALE = VF.MASKED_B256_QK_SCALE
 OUT_HW = (375, 500)   # typical VOC image size
 
 
@@ -89,6 +90,36 @@ def pack_forward(out, prefix, store):
     store[prefix + "p_l6_img0_h3"] = attn_w[6][0, 3].numpy()
 
 
+def big_batch(ref, ora_sd, report, B=256):
+    """BASELINE config 2 shape: the reference itself on 256 images (batch-global max of vit_model.py:335 over the whole
+    batch), default-init weights and the mask-firing 'masked' regime.  Only the small outputs are stored; the GPU tests run
+    the oracle live at this shape for the CAM / label comparison, and this file pins the oracle there."""
+    cls_labels = np.load(os.path.join(ref_shim.REFERENCE_DIR, "voc12", "cls_labels.npy"), allow_pickle=True).item()
+    names = sorted(cls_labels.keys())[:B]
+    labels = np.stack([cls_labels[k] for k in names]).astype(np.uint8)                # [B,20] image-level labels (utils.py:100)
+    x = VF.make_images(0, B)
+    for name, sd in (("default_b256", ora_sd), ("masked_b256", VF.masked(ora_sd, qk_scale=MASKED_B256_QK_SCALE))):
+        out = run_reference(ref, sd, x)
+        ora = VF.forward(sd, x, VF.VIT_B16_224, keep_P=False)
+        rep = {"logits": maxdiff(out[0], ora["logits"]), "hwp": maxdiff(out[3], ora["hwp"]), "ori": maxdiff(out[5], ora["ori"]),
+               "X_last": maxdiff(out[2][-1], ora["X"][-1]),
+               "cls_rows_last": maxdiff(out[1][-1][:, :, 0, :], ora["cls_rows"][-1]),
+               "bg_fraction": [None if b is None else float(b.mean()) for b in ora["bg"]],
+               "labels_per_image_mean": float(labels.sum(1).mean())}
+        report[name] = rep
+        print(name, rep)
+        assert rep["logits"] <= 1e-6 and rep["X_last"] <= 1e-5, rep
+        store = {"x_sig": np.array([float(x.double().sum()), float(x.double().abs().sum())]),
+                 "logits": out[0].numpy(), "hwp": out[3].numpy(), "topk_idx": ora["topk_idx"].numpy().astype(np.int16),
+                 "c_last": ora["c_last"].numpy(), "x_cls_last": out[2][-1][:, 0, :].numpy(), "labels": labels,
+                 "bg_packed": np.packbits(np.stack([b.numpy().astype(np.uint8) for b in ora["bg"] if b is not None]), axis=-1)}
+        cam = PP.classic_cam(out[2][-1], out[4])
+        store["cam_img0"] = cam[0].numpy()
+        store["cam_abs_mean"] = cam.abs().mean(dim=(1, 2, 3)).numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+        del out, ora
+
+
 def main():
     assert ref_shim.available(), "run in the build container (needs /root/reference)"
     ref = ref_shim.import_reference()
@@ -110,7 +141,8 @@ def main():
         json.dump({"keys": keys, "shapes": {k: list(ref_sd[k].shape) for k in keys}, "sig": sd_sig}, f)
 
     cfg = VF.VIT_B16_224
-    cases = {"default_b2": (ora_sd, 0, 2), "peaked_b3": (VF.peaked(ora_sd), 0, 3), "peaked_b1": (VF.peaked(ora_sd), 0, 1)}
+    cases = {"default_b2": (ora_sd, 0, 2), "peaked_b3": (VF.peaked(ora_sd), 0, 3), "peaked_b1": (VF.peaked(ora_sd), 0, 1),
+             "masked_b3": (VF.masked(ora_sd), 0, 3), "masked_b1": (VF.masked(ora_sd), 0, 1)}
     for name, (sd, first, count) in cases.items():
         x = VF.make_images(first, count)
         out = run_reference(ref, sd, x)
@@ -130,7 +162,7 @@ def main():
         store["topk_idx"] = ora["topk_idx"].numpy()
         store["bg"] = np.stack([b.numpy().astype(np.uint8) for b in ora["bg"] if b is not None])   # layers 4..L-1
         store["c_last"] = ora["c_last"].numpy()
-        if name == "peaked_b1":
+        if name.endswith("_b1"):
             h, w = OUT_HW
             seg, p2c, bgm = exec_validate(out, h, w)
             seg_o = PP.hwp_pseudo_seg(ora["hwp"], sd["head1.weight"], ora["ori"], ora["X"][-1], ora["cls_rows"], (h, w))
@@ -170,6 +202,7 @@ def main():
             store["cam_label_sig"] = PP.cam_pseudo_label(cam, labels_sig, (h, w)).numpy()
             store["cam_labels_sig_in"] = labels_sig.numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+    big_batch(ref, ora_sd, report)
     with open(os.path.join(HERE, "REPORT.json"), "w") as f:
         json.dump(report, f, indent=1)
     print(json.dumps(report, indent=1))

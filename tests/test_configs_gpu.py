@@ -97,6 +97,9 @@ def test_vit_l16_384_forward_cam(lib_built):
     assert e <= LOGIT_TOL and c_cam >= 0.999
     assert relerr(o.tokens[0], ref["X"][12]) <= LOGIT_TOL and relerr(o.tokens[-1], ref["X"][-1]) <= LOGIT_TOL
     assert float((o.cls_rows.cpu() - ref["cls_rows"]).abs().max()) <= 0.02 * float(ref["cls_rows"].max())
+    # validate.py:225-237 / predict.py:261-269 index into the forward's LAST-12 list (vit_model.py:322): blocks 17..23 / 12..23
+    assert cosine(CAM.bg_map(o.cls_rows), PP.bg_map(ref["cls_rows"][-12:])) >= 0.999
+    assert CAM.layer_maps(o.cls_rows).shape[0] == 12
     # peaked: masks fire on layers 5..23
     sdp = VF.peaked(sd)
     model.load_state_dict(sdp)

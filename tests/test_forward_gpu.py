@@ -15,12 +15,18 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 1e-2          # BASELINE.json: bf16 logits max relative error, on the reference's own (default-init) weights
-# "peaked" regime (qkv weights x5, used only to make the background mask fire): attention logits are 25x larger, so the
-# softmax is 25x more sensitive to bf16 operand rounding.  A CPU emulation of bf16-operand / fp32-accumulate arithmetic
-# (tools/emulate_bf16.py) deviates from the fp32 reference by 0.9-1.2e-2 there -- that is the arithmetic's floor, so the
-# bound for this stress regime is 2e-2.
-PEAKED_TOL = 2e-2
+# BASELINE.json north_star, bf16 mode: logits max relative error <= 1e-2, CAM cosine >= 0.999, pseudo-label agreement >= 99.5 %.
+# These bars are asserted (a) on the reference's own default-init weights (BASELINE config 2; the layer>4 mask never fires
+# there) and (b) in the "masked" regime (oracle.vit_forward.masked: q/k rows x3.5 from block 3), where the background mask
+# of vit_model.py:325-361 fires on 0.5-0.6 of the patches at a natural logit scale.
+LOGIT_TOL = 1e-2
+CAM_COS = 0.999
+LABEL_AGREE = 0.995
+# STRESS regime, reported separately and not a north-star claim: "peaked" = every qkv weight x5 (attention logits x25 AND the
+# attention output x5 against the residual stream).  A CPU emulation of bf16-operand arithmetic (tools/emulate_bf16.py) sits
+# at 0.9-1.2e-2 of the fp32 logits there, i.e. no bf16 implementation meets 1e-2 in it; the stress bound is 2e-2.
+PEAKED_STRESS_TOL = 2e-2
+PEAKED_TOL = PEAKED_STRESS_TOL
 
 
 def relerr(a, b):
@@ -43,11 +49,12 @@ def env(lib_built):
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev).eval()
     model.is_train = False
-    return dict(V=V, VF=VF, dev=dev, model=model, sd0=sd0, sd_peaked=VF.peaked(sd0))
+    return dict(V=V, VF=VF, dev=dev, model=model, sd0=sd0, sd_peaked=VF.peaked(sd0), sd_masked=VF.masked(sd0))
 
 
 def load(env, which):
-    env["model"].load_state_dict(env["sd0"] if which == "default" else env["sd_peaked"])
+    env["model"].load_state_dict({"default": env["sd0"], "peaked": env["sd_peaked"], "masked": env["sd_masked"]}[which]
+                                 if isinstance(which, str) else which)
     return env["model"]
 
 
@@ -85,6 +92,114 @@ def test_reference_6tuple_surface(env):
         model(torch.zeros(1, 3, 200, 200, device=env["dev"]))
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 3, 224, 224))                                # CPU input: loud failure, no fallback
+
+
+def test_masked_regime_meets_the_north_star_bar(env):
+    """The reference's distinguishing feature -- the layer>4 background mask -- firing (bg fraction 0.52-0.58 on layers
+    5..11), at the north-star tolerance: logits / hwp / tokens <= 1e-2 with the discrete decisions teacher-forced (so the
+    continuous arithmetic is graded on identical masks), then the decisions themselves free-running."""
+    gold = np.load(os.path.join(GOLDEN, "masked_b3.npz"))
+    model = load(env, "masked")
+    x = env["VF"].make_images(0, 3).to(env["dev"])
+    frac = gold["bg"][1:].mean(axis=(1, 2))                               # masks consumed by layers 6..11 (+ the unused last)
+    assert (frac > 0.1).all() and (frac < 0.9).all(), frac               # the mask path is really exercised
+    forced = {4 + i: torch.from_numpy(gold["bg"][i]) for i in range(gold["bg"].shape[0])}
+    o = model.forward_cam(x, tokens_layers=12, bg=True, cls_map=True, forced_bg=forced, forced_topk=torch.from_numpy(gold["topk_idx"]))
+    e = dict(logits=relerr(o.logits, gold["logits"]), hwp=relerr(o.hwp_logits, gold["hwp"]), ori=relerr(o.hwp_tokens, gold["ori"]),
+             x_cls=relerr(o.tokens[:, :, 0, :], gold["x_cls"]))
+    print("masked teacher-forced:", {k: f"{v:.2e}" for k, v in e.items()})
+    assert max(e.values()) <= LOGIT_TOL, e
+    assert float((o.cls_rows.cpu() - torch.from_numpy(gold["cls_rows"])).abs().max()) <= 0.02 * float(gold["cls_rows"].max())
+    assert torch.equal(o.bg[4:].cpu(), torch.from_numpy(gold["bg"]))
+    assert cosine(o.cls_map[-1], gold["c_last"]) >= 0.9999
+    # free running: the same forward making its own decisions
+    f = model.forward_cam(x, bg=True, cls_map=True)
+    agree = float((f.bg[4:].cpu() == torch.from_numpy(gold["bg"])).float().mean())
+    overlap = np.mean([len(set(f.topk_idx[b].cpu().tolist()) & set(gold["topk_idx"][b].tolist())) / 16.0 for b in range(3)])
+    ef = relerr(f.logits, gold["logits"])
+    print(f"masked free-running: bg agreement {agree:.4f}, top-16 overlap {overlap:.3f}, logits relerr {ef:.2e}")
+    assert agree >= 0.99 and overlap >= 0.9
+    assert ef <= 3e-2                                                      # a flipped threshold-adjacent patch changes a whole key column
+
+
+def test_masked_regime_cam_rollout_pseudo_labels(env):
+    """CAM agreement (BASELINE metric) in the mask-firing regime against the reference's outputs + exec'd reference lines."""
+    from vision_transformer_cam_b200 import cam as CAM
+    gold = np.load(os.path.join(GOLDEN, "masked_b1.npz"))
+    model = load(env, "masked")
+    x = env["VF"].make_images(0, 1).to(env["dev"])
+    forced = {4 + i: torch.from_numpy(gold["bg"][i]) for i in range(gold["bg"].shape[0])}
+    o = model.forward_cam(x, attn_mean=True, forced_bg=forced, forced_topk=torch.from_numpy(gold["topk_idx"]))
+    hw = (375, 500)
+    cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)
+    assert cosine(cam, gold["classic_cam"]) >= CAM_COS, cosine(cam, gold["classic_cam"])
+    for key_in, key_out in (("cam_labels_in", "cam_label"), ("cam_labels_sig_in", "cam_label_sig")):
+        lab = CAM.cam_pseudo_label(cam, torch.from_numpy(gold[key_in]).to(env["dev"]), hw)
+        agree = float((lab.cpu() == torch.from_numpy(gold[key_out])).float().mean())
+        print(f"masked regime {key_out}: {int(gold[key_in].sum())} labels, agreement {agree:.5f}")
+        assert agree >= LABEL_AGREE, (key_out, agree)
+    assert cosine(CAM.rollout_row(o.attn_mean), gold["rollout_row"]) >= CAM_COS
+    assert cosine(CAM.rollout_map(o.attn_mean, hw), gold["rollout_up"].astype(np.float32)) >= CAM_COS
+    assert cosine(CAM.layer_maps(o.cls_rows)[:, 0], gold["layer_maps14"]) >= CAM_COS
+    seg, p2c, bgm = CAM.hwp_pseudo_seg(o, model.head1.weight.data, hw, return_parts=True)
+    assert cosine(bgm, gold["val_bg_map"]) >= CAM_COS
+    ref_seg = torch.from_numpy(gold["val_seg"]).to(torch.uint8)
+    ref_seg = torch.where(ref_seg > 21, torch.zeros_like(ref_seg), ref_seg)
+    free = float((seg[0].cpu() == ref_seg).float().mean())
+    print(f"masked regime validate pseudo-seg agreement {free:.5f}")
+    assert free >= 0.98, free
+
+
+@pytest.mark.parametrize("regime", ["default", "masked"])
+def test_batch_256_against_the_oracle(env, regime):
+    """BASELINE config 2 shape (B = 256, mask_norm='batch': the global max of vit_model.py:335 spans all 256 images) against
+    the CPU oracle run live on the same inputs, itself pinned to the reference's own B = 256 outputs (golden).  Bars over ALL
+    256 images: logits <= 1e-2, CAM cosine >= 0.999 (every image), CAM pseudo-label agreement >= 99.5 % with the image-level
+    label rows of the reference's voc12/cls_labels.npy."""
+    from vision_transformer_cam_b200 import cam as CAM
+    from oracle import postproc as PP
+    VF = env["VF"]
+    gold = np.load(os.path.join(GOLDEN, regime + "_b256.npz"))
+    sd = env["sd0"] if regime == "default" else VF.masked(env["sd0"], qk_scale=VF.MASKED_B256_QK_SCALE)
+    x = VF.make_images(0, 256)
+    assert abs(float(x.double().sum()) - float(gold["x_sig"][0])) < 1e-2
+    ref = VF.forward(sd, x, VF.VIT_B16_224, keep_P=False)
+    assert float((ref["logits"] - torch.from_numpy(gold["logits"])).abs().max()) <= 1e-6          # the oracle IS the reference here
+    assert torch.equal(ref["topk_idx"], torch.from_numpy(gold["topk_idx"].astype(np.int64)))
+    bg_ref = torch.stack([b for b in ref["bg"] if b is not None]).to(torch.uint8)                     # [8,256,196]
+    assert np.array_equal(np.packbits(bg_ref.numpy(), axis=-1), gold["bg_packed"])
+    model = load(env, sd)
+    xd = x.to(env["dev"])
+    free = model.forward_cam(xd, bg=True, mask_norm="batch")
+    if regime == "default":
+        assert int(bg_ref.sum()) == 0 and int(free.bg.sum()) == 0
+        o = free
+    else:
+        frac = bg_ref[1:].float().mean(dim=(1, 2))
+        assert bool((frac > 0.1).all()) and bool((frac < 0.9).all()), frac
+        agree = float((free.bg[4:].cpu() == bg_ref).float().mean())
+        print(f"B=256 masked free-running: bg agreement {agree:.5f}, logits relerr {relerr(free.logits, ref['logits']):.2e}")
+        assert agree >= 0.99
+        o = model.forward_cam(xd, bg=True, mask_norm="batch", forced_bg={4 + i: bg_ref[i] for i in range(8)}, forced_topk=ref["topk_idx"])
+    e, eh = relerr(o.logits, ref["logits"]), relerr(o.hwp_logits, ref["hwp"])
+    cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)
+    cam_ref = PP.classic_cam(ref["X"][-1], sd["head1.weight"])
+    cos = torch.nn.functional.cosine_similarity(cam.cpu().double().flatten(1), cam_ref.double().flatten(1), dim=1)
+    labels = torch.from_numpy(gold["labels"]).float()
+    hw = (375, 500)
+    lab = CAM.cam_pseudo_label(cam, labels.to(env["dev"]), hw).cpu()
+    per_image = []
+    for i in range(0, 256, 32):
+        r = PP.cam_pseudo_label(cam_ref[i:i + 32], labels[i:i + 32], hw)
+        per_image.append((lab[i:i + 32] == r).float().mean(dim=(1, 2)))
+    per_image = torch.cat(per_image)
+    print(f"B=256 {regime}: logits {e:.2e} hwp {eh:.2e}  CAM cosine min {float(cos.min()):.6f} mean {float(cos.mean()):.6f}  "
+          f"label agreement mean {float(per_image.mean()):.5f} min {float(per_image.min()):.5f} ({float(labels.sum(1).mean()):.2f} labels / image)")
+    assert e <= LOGIT_TOL, e
+    if regime == "masked":
+        assert eh <= LOGIT_TOL, eh                       # top-16 teacher-forced; default regime: near-uniform map, index flips
+    assert float(cos.min()) >= CAM_COS
+    assert float(per_image.mean()) >= LABEL_AGREE
 
 
 def test_peaked_regime_teacher_forced_continuous_parity(env):
@@ -260,8 +375,16 @@ from oracle import vit_forward as VF
 gold = np.load(os.path.join(sys.argv[1], "tests", "golden", "default_b2.npz"))
 torch.manual_seed(0)
 model = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).to("cuda:0").eval()
-o = model.forward_cam(VF.make_images(0, 2).to("cuda:0"), tokens_layers=12)
+o = model.forward_cam(VF.make_images(0, 2).to("cuda:0"), tokens_layers=12, attn_mean=True, attn_layers=12)
 ref = torch.from_numpy(gold["logits"]).double()
+# the head mean requested next to the LayerNorm-fused GEMMs comes from the packed-P attention variant: it must equal the
+# mean of the full P the same forward returns (it used to be left unwritten on this path)
+for l in range(12):
+    d = float((o.attn_mean[l] - o.attn[l].mean(dim=1)).abs().max())
+    assert d <= 2e-3 * float(o.attn[l].max()), (l, d)
+o2 = model.forward_cam(VF.make_images(0, 2).to("cuda:0"), attn_mean=True)
+pb = torch.from_numpy(gold["pbar_last_img0"])
+assert float((o2.attn_mean[-1][0].cpu() - pb).abs().max()) <= 0.02 * float(pb.max())
 e = float((o.logits.double().cpu() - ref).abs().max() / ref.abs().max())
 et = float((o.tokens[:, :, 0, :].double().cpu() - torch.from_numpy(gold["x_cls"]).double()).abs().max() / np.abs(gold["x_cls"]).max())
 print("LNFUSED logits %.3e tokens %.3e" % (e, et))
@@ -308,3 +431,16 @@ def test_cuda_graph_replay_equals_eager_and_follows_weight_updates(env):
     assert torch.equal(model.forward_cam_graphed(u8).logits, model.forward_cam_u8(u8).logits)
     with pytest.raises(ValueError):
         model.forward_cam_graphed(x, forced_topk=torch.zeros((1, 16), dtype=torch.int32))
+    # precision round trip: fp32 mode needs a larger packed-weight buffer, the bf16 graph captured above pointed into the
+    # old one -- it must be re-captured, not replayed against freed memory
+    want = model.forward_cam(x).logits.clone()
+    assert torch.equal(model.forward_cam_graphed(x).logits, want)
+    model.set_precision("fp32")
+    try:
+        f32 = model.forward_cam_graphed(x).logits.clone()
+        assert torch.equal(f32, model.forward_cam(x).logits)
+    finally:
+        model.set_precision("bf16")
+    junk = [torch.full((1 << 26,), 7, dtype=torch.uint8, device=dev) for _ in range(8)]      # recycle freed blocks
+    assert torch.equal(model.forward_cam_graphed(x).logits, want)
+    del junk

@@ -271,6 +271,74 @@ def test_cls_stat_and_mask(dev):
     assert torch.equal(bg_f, forced)
 
 
+def test_topk_heads_bit_exact(dev):
+    """vit_model.py:372-393 is index work: on the reference's own CLS maps (golden c_last of the B = 256 runs, where the
+    batch-global max of :372 spans 256 images) `vtc_topk_heads` must return torch.topk's indices IN ORDER, gather the
+    block-L tokens exactly, and reproduce head1(mean) / head(LN(cls)) to fp32 rounding."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    import vision_transformer_cam_b200 as V
+    torch.manual_seed(0)
+    model = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).to(dev).eval()
+    for name in ("default_b256", "masked_b256"):
+        gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+        c = torch.from_numpy(gold["c_last"])                                   # [256,196] fp32, the reference's values
+        B = c.shape[0]
+        tokens = _rand((B, 197, 768), 77, dev)
+        for per_image in (False, True):
+            mx = c.max(dim=1, keepdim=True).values if per_image else c.max()
+            m14 = c / mx                                                       # vit_model.py:372
+            ref_idx = torch.stack([torch.topk(m14[j], 16, dim=0).indices for j in range(B)])       # :377
+            if not per_image:
+                assert torch.equal(ref_idx, torch.from_numpy(gold["topk_idx"].astype(np.int64)))   # == what the reference chose
+            gmax = None if per_image else c.max().reshape(1).to(dev)
+            logits, hwp, ori, idx = model.topk_heads(tokens, c.to(dev), gmax)
+            assert torch.equal(idx.cpu().long(), ref_idx), (name, per_image)
+            ref_ori = torch.stack([tokens[j][ref_idx[j].to(dev) + 1] for j in range(B)])           # :381-389
+            assert torch.equal(ori, ref_ori)
+            ref_hwp = F.linear(ref_ori.mean(dim=1), model.head1.weight, model.head1.bias)          # :392-393
+            assert relerr(hwp, ref_hwp) <= 1e-6, relerr(hwp, ref_hwp)
+            ref_logits = model.head(F.layer_norm(tokens[:, 0], (768,), model.norm.weight, model.norm.bias, 1e-6))
+            assert relerr(logits, ref_logits) <= 1e-5, relerr(logits, ref_logits)
+    # forced indices are used as given (and clamped into range instead of reading out of bounds)
+    forced = torch.tensor([[0, 195, 7, 7] + list(range(12))] * B, dtype=torch.int32)
+    _, _, ori_f, idx_f = model.topk_heads(tokens, c.to(dev), None, forced_topk=forced)
+    assert torch.equal(idx_f.cpu(), forced) and torch.equal(ori_f[:, 1], tokens[:, 196])
+    bad = forced.clone()
+    bad[:, 0], bad[:, 1] = -5, 9999
+    _, _, _, idx_b = model.topk_heads(tokens, c.to(dev), None, forced_topk=bad)
+    assert int(idx_b.min()) == 0 and int(idx_b.max()) == 195
+
+
+def test_topk_heads_ties_nan_and_inf(dev):
+    """Edge cases of the selection: exact ties go to the smaller index, NaN ranks above every number (torch.topk), -inf
+    entries stay selectable, and no index is returned twice (a NaN map used to index out of bounds)."""
+    import vision_transformer_cam_b200 as V
+    torch.manual_seed(0)
+    model = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).to(dev).eval()
+    P = 196
+    maps = torch.zeros((6, P))
+    maps[0] = torch.arange(P).float() % 7                       # many exact ties
+    maps[1] = float("nan")                                      # all NaN
+    maps[2] = torch.rand(P, generator=torch.Generator().manual_seed(1)); maps[2, [3, 50]] = float("nan")
+    maps[3] = float("-inf"); maps[3, 10:20] = 1.0               # fewer than 16 finite entries
+    maps[4] = torch.rand(P, generator=torch.Generator().manual_seed(2)); maps[4, 100] = float("inf")
+    maps[5] = 0.5                                               # constant map
+    tokens = _rand((6, 197, 768), 78, dev)
+    one = torch.ones(1, device=dev)
+    _, _, ori, idx = model.topk_heads(tokens, maps.to(dev), one)
+    idx = idx.cpu().long()
+    for b in range(6):
+        assert len(set(idx[b].tolist())) == 16 and int(idx[b].min()) >= 0 and int(idx[b].max()) < P
+        key = torch.where(torch.isnan(maps[b]), torch.full_like(maps[b], float("inf")), maps[b])
+        order = sorted(range(P), key=lambda j: (-key[j].item(), j))[:16]          # descending value, ascending index
+        assert idx[b].tolist() == order, (b, idx[b].tolist(), order)
+        tv = torch.topk(maps[b], 16).values                                        # torch agrees on the VALUES (its tie order is unspecified)
+        assert torch.equal(torch.nan_to_num(maps[b][idx[b]], nan=9e9), torch.nan_to_num(tv, nan=9e9))
+    assert torch.equal(ori[0], tokens[0][idx[0].to(dev) + 1])
+
+
 # ------------------------------------------------------------------------------------------- postproc
 def test_rollout_and_layer_maps(dev):
     from vision_transformer_cam_b200 import ops

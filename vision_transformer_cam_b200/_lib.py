@@ -96,7 +96,7 @@ SIGNATURES = {
     "vtc_head_mean": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "vtc_cls_stat": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "vtc_cls_mask": (C.c_int, [_P, _P, _P, _F, _I, _P, _P, _I, _I, _P]),
-    "vtc_topk_heads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "vtc_topk_heads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "vtc_rollout": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "vtc_cls_layer_map": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vtc_cam_project": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),

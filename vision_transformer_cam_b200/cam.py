@@ -14,6 +14,16 @@ from . import ops
 from .vit_model import CamForward
 
 
+REF_KEPT_LAYERS = 12
+
+
+def last_kept(per_layer: torch.Tensor) -> torch.Tensor:
+    """The reference's forward only returns the last 12 layers' attention / tokens (vit_model.py:322, `len(blocks) - i <=
+    12`), and predict.py / validate.py index into THAT list: for depth 24 'layers[5:]' are blocks 17..23 and the rollout
+    runs over blocks 12..23.  [L,...] -> [min(L,12),...] (a contiguous view)."""
+    return per_layer[-REF_KEPT_LAYERS:] if per_layer.shape[0] > REF_KEPT_LAYERS else per_layer
+
+
 def patch_similarity(tokens: torch.Tensor) -> torch.Tensor:
     """predict.py:191-199 (viz): `F.normalize(x).squeeze(0) @ ....t()` for block outputs x [B,N,D]; F.normalize's default
     dim=1 normalises every feature column across the tokens (reproduced as is).  -> [B,N,N]."""
@@ -28,7 +38,7 @@ def head_mean(attn_weights: Sequence[torch.Tensor]) -> torch.Tensor:
 
 def rollout_row(attn_mean: torch.Tensor) -> torch.Tensor:
     """predict.py:215-232: CLS row of prod_l (mean_l + I)/rowsum, patch columns, un-normalised.  [L,B,N,N] -> [B,P]."""
-    return ops.rollout(attn_mean.contiguous())
+    return ops.rollout(last_kept(attn_mean).contiguous())
 
 
 def rollout_map(attn_mean: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
@@ -41,7 +51,8 @@ def rollout_map(attn_mean: torch.Tensor, out_hw: Optional[Tuple[int, int]] = Non
 
 
 def layer_maps(cls_rows: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None, as_u8: bool = False) -> torch.Tensor:
-    """predict.py:261-269: per layer (mean_h P + I)/rowsum, CLS row, / max -> [L,B,g,g] (or resized, optionally *255 u8)."""
+    """predict.py:261-269: per layer (mean_h P + I)/rowsum, CLS row, / max -> [min(L,12),B,g,g] (or resized, optionally *255 u8)."""
+    cls_rows = last_kept(cls_rows).contiguous()
     L, B, H, N = cls_rows.shape
     g = int(round((N - 1) ** 0.5))
     m = torch.stack([ops.cls_layer_map(cls_rows, l, l + 1) for l in range(L)]).view(L, B, g, g)
@@ -69,7 +80,9 @@ def cam_upsampled(cam: torch.Tensor, out_hw: Tuple[int, int], as_u8: bool = Fals
 
 # ---- validate.py:132-258 pseudo segmentation ---------------------------------------------------------------------
 def bg_map(cls_rows: torch.Tensor, first_layer: int = 5) -> torch.Tensor:
-    """validate.py:225-237: mean CLS attention over layers[first_layer:] and heads, + identity, renormalised, / max."""
+    """validate.py:225-237: mean CLS attention over layers[first_layer:] of the kept (last 12) layers and heads, + identity,
+    renormalised, / max."""
+    cls_rows = last_kept(cls_rows).contiguous()
     return ops.cls_layer_map(cls_rows, first_layer, cls_rows.shape[0])
 
 

@@ -407,12 +407,8 @@ int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows
     if (rc != VTC_OK) return rc;
     rc = make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq);
     if (rc != VTC_OK) return rc;
-    static bool configured2 = false;
-    if (!configured2) {
-        VTC_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn2::SMEM_BYTES));
-        VTC_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured2 = true;
-    }
+    static SmemOptIn optin;
+    if ((rc = optin.ensure(reinterpret_cast<const void*>(attention2_kernel), attn2::SMEM_BYTES, true)) != VTC_OK) return rc;
     Attn2Params p{key_bias, static_cast<__nv_bfloat16*>(out), cls_rows, attn_out, batch, n_tokens, heads, scale, scale * 1.4426950408889634f,
                   g_attn_trace, 0};
     const int ntiles = (n_tokens + 127) / 128;

@@ -606,14 +606,11 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     if (rc != VTC_OK) return rc;
     rc = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxkv);
     if (rc != VTC_OK) return rc;
-    static bool configured = false;
-    if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        VTC_CUDA(cudaFuncSetAttribute(attention_cs_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
+    static SmemOptIn optin[4];
+    if ((rc = optin[0].ensure(reinterpret_cast<const void*>(attention_cs_kernel<false, false>), SMEM_BYTES)) != VTC_OK) return rc;
+    if ((rc = optin[1].ensure(reinterpret_cast<const void*>(attention_cs_kernel<false, true>), SMEM_BYTES)) != VTC_OK) return rc;
+    if ((rc = optin[2].ensure(reinterpret_cast<const void*>(attention_cs_kernel<true, false>), SMEM_BYTES)) != VTC_OK) return rc;
+    if ((rc = optin[3].ensure(reinterpret_cast<const void*>(attention_cs_kernel<true, true>), SMEM_BYTES)) != VTC_OK) return rc;
     const int items = batch * heads * cdiv(n_tokens, 128);
     int grid = cdiv(items, GROUPS);
     if (grid > device_sm_count()) grid = device_sm_count();

@@ -223,11 +223,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) attention_generic_kernel(const 
 
 template <int KS>
 static int launch(const Params& p, size_t smem, cudaStream_t stream) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        VTC_CUDA(cudaFuncSetAttribute(attention_generic_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    int rc_ = optin.ensure(reinterpret_cast<const void*>(attention_generic_kernel<KS>), smem);
+    if (rc_ != VTC_OK) return rc_;
     dim3 grid(p.H, p.B);
     attention_generic_kernel<KS><<<grid, WARPS * 32, smem, stream>>>(p);
     VTC_CHECK_LAUNCH();

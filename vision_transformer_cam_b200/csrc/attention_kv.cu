@@ -538,11 +538,8 @@ static int launch(const void* qkv, const Params& p, cudaStream_t stream) {
     if (rc != VTC_OK) return rc;
     rc = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxkv);
     if (rc != VTC_OK) return rc;
-    static bool configured = false;
-    if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(attention_kv_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    if ((rc = optin.ensure(reinterpret_cast<const void*>(attention_kv_kernel<SPLIT>), C::SMEM_BYTES)) != VTC_OK) return rc;
     const int items = p.B * p.H * cdiv(p.N, 128);
     int grid = cdiv(items, 2);
     if (grid > device_sm_count()) grid = device_sm_count();

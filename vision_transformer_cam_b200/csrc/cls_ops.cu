@@ -99,9 +99,11 @@ int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, 
 }
 
 // grid = B, block = 256.  Dynamic smem: [P] map copy + [D] mean token + [D] normalised CLS row + [R] pre-logits.
+// The map is divided by its maximum first (batch-global `*gmax`, or the image's own when gmax == nullptr) exactly as
+// vit_model.py:372 does before torch.topk (:377): the fp32 quotients, not the raw values, decide order and ties.
 __global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__ tokens, const float* __restrict__ cls_map,
-                                  const int32_t* __restrict__ forced_topk, float* __restrict__ logits, float* __restrict__ hwp_logits,
-                                  float* __restrict__ hwp_tokens, int32_t* __restrict__ topk_idx) {
+                                  const float* __restrict__ gmax, const int32_t* __restrict__ forced_topk, float* __restrict__ logits,
+                                  float* __restrict__ hwp_logits, float* __restrict__ hwp_tokens, int32_t* __restrict__ topk_idx) {
     extern __shared__ float sm[];
     __shared__ float red[32];
     __shared__ int idx_s[64];
@@ -113,27 +115,41 @@ __global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__
     float* xn = meanv + D;       // [D]
     float* feat = xn + D;        // [R] (only with pre_logits)
 
-    for (int j = threadIdx.x; j < P; j += blockDim.x) mapv[j] = cls_map[static_cast<size_t>(b) * P + j];
-    __syncthreads();
     if (forced_topk != nullptr) {
-        if (threadIdx.x < K) idx_s[threadIdx.x] = forced_topk[b * K + threadIdx.x];
-    } else if (warp == 0) {
-        // K rounds of warp arg-max, descending, ties to the smaller index (torch.topk, vit_model.py:377)
-        for (int k = 0; k < K; ++k) {
-            float best = -INFINITY;
-            int bi = 0x7fffffff;
-            for (int j = lane; j < P; j += 32) {
-                const float v = mapv[j];
-                if (v > best) { best = v; bi = j; }
-            }
+        if (threadIdx.x < K) idx_s[threadIdx.x] = min(max(forced_topk[b * K + threadIdx.x], 0), P - 1);
+    } else {
+        float mx;
+        if (gmax != nullptr) {
+            mx = *gmax;
+        } else {
+            float v = 0.f;
+            for (int j = threadIdx.x; j < P; j += blockDim.x) v = fmaxf(v, cls_map[static_cast<size_t>(b) * P + j]);
+            mx = block_max(v, red);
+        }
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            const float v = cls_map[static_cast<size_t>(b) * P + j] / mx;
+            mapv[j] = (v != v) ? INFINITY : v;            // torch.topk ranks NaN above every number
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // K rounds of warp arg-max, descending, ties to the smaller index (torch.topk, vit_model.py:377); taken entries are
+            // marked with a NaN so that -inf values remain selectable and an index is never returned twice
+            for (int k = 0; k < K; ++k) {
+                float best = 0.f;
+                int bi = 0x7fffffff;
+                for (int j = lane; j < P; j += 32) {
+                    const float v = mapv[j];
+                    if (v == v && (bi == 0x7fffffff || v > best)) { best = v; bi = j; }
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+                }
+                if (lane == 0) { idx_s[k] = bi; mapv[bi] = __int_as_float(0x7fc00000); }      // K <= P: a candidate always exists
+                __syncwarp();
             }
-            if (lane == 0) { idx_s[k] = bi; mapv[bi] = -INFINITY; }
-            __syncwarp();
         }
     }
     __syncthreads();
@@ -187,7 +203,7 @@ __global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__
     }
 }
 
-int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,
+int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, const float* gmax, const int32_t* forced_topk, float* logits,
                float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int batch, cudaStream_t stream) {
     VTC_REQUIRE(tokens && cls_map && logits && hwp_logits && hwp_tokens, VTC_ERR_ARG, "topk_heads: null pointer");
     VTC_REQUIRE(hp.norm_w && hp.norm_b && hp.head_w && hp.head_b && hp.head1_w && hp.head1_b, VTC_ERR_ARG, "topk_heads: missing weights");
@@ -196,7 +212,7 @@ int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, 
     if (rc != VTC_OK) return rc;
     const size_t smem = sizeof(float) * (static_cast<size_t>(hp.n_tokens - 1) + 2 * hp.dim + (hp.pre_w ? hp.rep : 0));
     VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "topk_heads: %zu bytes of smem", smem);
-    topk_heads_kernel<<<batch, 256, smem, stream>>>(hp, tokens, cls_map, forced_topk, logits, hwp_logits, hwp_tokens, topk_idx);
+    topk_heads_kernel<<<batch, 256, smem, stream>>>(hp, tokens, cls_map, gmax, forced_topk, logits, hwp_logits, hwp_tokens, topk_idx);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }

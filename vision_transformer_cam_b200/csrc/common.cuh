@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/vtc.h"
 
 namespace vtc {
@@ -38,6 +40,12 @@ void note_launch();   // global kernel-launch counter (vtc_launch_count)
     } while (0)
 
 int device_sm_count();
+// Per-device, thread-safe opt-in to more than 48 KB of dynamic shared memory: cudaFuncSetAttribute acts on the CURRENT device
+// only, so the "already done" state is one slot per device (a process may drive several GPUs).  One static instance per kernel.
+struct SmemOptIn {
+    std::atomic<size_t> cur[64];
+    int ensure(const void* func, size_t bytes, bool max_carveout = false);
+};
 int check_arch();   // VTC_OK iff the current device is compute capability 10.x
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

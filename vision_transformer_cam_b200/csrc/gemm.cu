@@ -210,11 +210,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const gemm::Params& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    int rc_ = optin.ensure(reinterpret_cast<const void*>(gemm_bf16_kernel<EPI>), gemm::SMEM_BYTES);
+    if (rc_ != VTC_OK) return rc_;
     const int tiles = cdiv(p.M, gemm::BM) * (p.N / gemm::BN);
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
     gemm_bf16_kernel<EPI><<<grid, gemm::THREADS, gemm::SMEM_BYTES, stream>>>(tmA, tmB, p);
@@ -635,11 +633,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <int EPI, bool SPLIT, bool FOLD = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const gemm2::Params& p, cudaStream_t stream,
                         const CUtensorMap* tmR = nullptr, const CUtensorMap* tmH = nullptr) {
-    static bool configured = false;
-    if (!configured) {
-        VTC_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<EPI, SPLIT, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::smem_bytes_of(EPI)));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    int rc_ = optin.ensure(reinterpret_cast<const void*>(gemm2_bf16_kernel<EPI, SPLIT, FOLD>), gemm2::smem_bytes_of(EPI));
+    if (rc_ != VTC_OK) return rc_;
     const int tiles = (EPI == gemm2::EPI_PATCH ? (p.M / p.patches) * p.tiles_per_img : cdiv(p.M, 2 * gemm2::BM)) * (p.N / gemm2::BN);
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = tiles;

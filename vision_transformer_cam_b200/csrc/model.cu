@@ -201,7 +201,8 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             // LayerNorm lives inside the GEMMs: ws.y = bf16(residual stream), ws.stats = its row statistics (gemm.cu)
             VTC_STEP(VTC_PROF_GEMM_QKV, gemm_lnfold(ws.y, pw.qkv, pw.qkv_c, pw.qkv_g, ws.stats, m->cfg.ln_eps, ws.qkv, M, 3 * D, D, 0, st, next_dir()));
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                   // vit_model.py:118
-            VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
+            if (mean_l) VTC_STEP(VTC_PROF_ATTENTION, attention_mean(ws.qkv, kb, ws.ao, cls_l, mean_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
+            else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
             if (fuse_proj) {
                 VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_resid_ln(ws.ao, pw.proj, w.proj_b, t_in, t_out, ws.y, ws.stats, M, D, D, st, next_dir()));
             } else {      // A/B: proj through the L2 reduction + a row pass that produces bf16(t) and its statistics
@@ -240,7 +241,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     }
     HeadParams hp{m->w.norm_w, m->w.norm_b, m->w.pre_w, m->w.pre_b, m->w.head_w, m->w.head_b, m->w.head1_w, m->w.head1_b,
                   D, m->R, m->C, m->cfg.topk, N, m->cfg.ln_eps};
-    VTC_STEP(VTC_PROF_HEADS, topk_heads(hp, t_cur, last_map, f ? f->topk_idx : nullptr, o->logits, o->hwp_logits, o->hwp_tokens, o->topk_idx, B, st));
+    VTC_STEP(VTC_PROF_HEADS, topk_heads(hp, t_cur, last_map, per_image ? nullptr : ws.gmax + (L - 1), f ? f->topk_idx : nullptr, o->logits, o->hwp_logits, o->hwp_tokens, o->topk_idx, B, st));
     return VTC_OK;
 }
 
@@ -414,13 +415,13 @@ int vtc_forward_u8(vtc_model* m, const uint8_t* x, const float* mean, const floa
     return vtc::forward(m, in, batch, outs, forcing, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
 }
 
-int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,
+int vtc_topk_heads(const vtc_model* m, const float* tokens, const float* cls_map, const float* gmax, const int32_t* forced_topk, float* logits,
                    float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int32_t batch, void* stream) {
     using namespace vtc;
     VTC_REQUIRE(m && m->packed, VTC_ERR_ARG, "topk_heads: model without weights");
     HeadParams hp{m->w.norm_w, m->w.norm_b, m->w.pre_w, m->w.pre_b, m->w.head_w, m->w.head_b, m->w.head1_w, m->w.head1_b,
                   m->D, m->R, m->C, m->cfg.topk, m->N, m->cfg.ln_eps};
-    return topk_heads(hp, tokens, cls_map, forced_topk, logits, hwp_logits, hwp_tokens, topk_idx, batch, static_cast<cudaStream_t>(stream));
+    return topk_heads(hp, tokens, cls_map, gmax, forced_topk, logits, hwp_logits, hwp_tokens, topk_idx, batch, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -80,7 +80,7 @@ struct HeadParams {
     int dim, rep, classes, topk, n_tokens;
     float eps;
 };
-int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, const int32_t* forced_topk, float* logits,
+int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, const float* gmax, const int32_t* forced_topk, float* logits,
                float* hwp_logits, float* hwp_tokens, int32_t* topk_idx, int batch, cudaStream_t stream);
 
 }  // namespace vtc

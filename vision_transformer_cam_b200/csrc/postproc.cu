@@ -204,11 +204,9 @@ static int launch_cam_project(const float* tokens, const float* w, float* cam, i
                               cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(2) * 8 * NT * (dim + 8) * 2 + sizeof(float) * static_cast<size_t>(classes) * (n_tokens - 1);
     VTC_REQUIRE(smem <= 220 * 1024, VTC_ERR_SHAPE, "cam_project: %zu bytes of smem", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        VTC_CUDA(cudaFuncSetAttribute(cam_project_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    int rc_ = optin.ensure(reinterpret_cast<const void*>(cam_project_kernel<NT>), smem);
+    if (rc_ != VTC_OK) return rc_;
     int warps = cdiv(n_tokens - 1, 16);
     if (warps > 16) warps = 16;
     if (warps < 1) warps = 1;
@@ -435,11 +433,8 @@ int hwp_cos_vote(const float* hwp_logits, const float* head1_w, const float* hwp
     if (rc != VTC_OK) return rc;
     const size_t smem = sizeof(float) * (static_cast<size_t>(k) * dim + HWP_MAXK) + sizeof(int) * k * classes;
     VTC_REQUIRE(smem <= 200 * 1024, VTC_ERR_SHAPE, "hwp_cos_vote: %zu bytes of smem", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        VTC_CUDA(cudaFuncSetAttribute(hwp_cos_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    if ((rc = optin.ensure(reinterpret_cast<const void*>(hwp_cos_vote_kernel), smem)) != VTC_OK) return rc;
     hwp_cos_vote_kernel<<<batch, 256, smem, stream>>>(hwp_logits, head1_w, hwp_tokens, tokens, sig_thresh, patch_to_cls, cosm, n_tokens, dim, classes, k);
     VTC_CHECK_LAUNCH();
     return VTC_OK;

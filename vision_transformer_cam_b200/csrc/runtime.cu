@@ -39,6 +39,17 @@ int device_sm_count() {
     return cached[dev];
 }
 
+int SmemOptIn::ensure(const void* func, size_t bytes, bool max_carveout) {
+    int dev = -1;
+    VTC_CUDA(cudaGetDevice(&dev));
+    const bool slot = dev >= 0 && dev < 64;
+    if (slot && cur[dev].load(std::memory_order_acquire) >= bytes) return VTC_OK;
+    VTC_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    if (max_carveout) VTC_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (slot) cur[dev].store(bytes, std::memory_order_release);      // racing threads set the same value twice: harmless
+    return VTC_OK;
+}
+
 int check_arch() {
     static int cached[64] = {0};   // 0 unknown, 1 ok, -1 bad
     int dev = 0;

@@ -11,8 +11,9 @@ import torch
 from . import _lib
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+class _DevPtr(int):
+    """A device pointer that remembers the device it lives on (ctypes takes it as a plain integer)."""
+    dev: torch.device
 
 
 def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
@@ -24,12 +25,30 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optiona
         raise RuntimeError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
-    return t.data_ptr()
+    p = _DevPtr(t.data_ptr())
+    p.dev = t.device
+    return p
+
+
+def _call(name: str, *args) -> None:
+    """Enqueue `vtc_<name>(*args, stream)` on the current stream of the device the tensors live on (not torch's current
+    device: a model on cuda:1 must launch on cuda:1), with that device made current for the launch."""
+    dev = None
+    for a in args:
+        if isinstance(a, _DevPtr):
+            if dev is None:
+                dev = a.dev
+            elif a.dev != dev:
+                raise RuntimeError(f"{name}: tensors on different devices ({dev} and {a.dev})")
+    if dev is None:
+        raise RuntimeError(f"{name}: no device tensor among the arguments")
+    with torch.cuda.device(dev):
+        _lib.call(name, *args, torch.cuda.current_stream(dev).cuda_stream)
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    _lib.call("vtc_cast_bf16", _ptr(src, torch.float32, "src"), _ptr(out), src.numel(), _stream())
+    _call("vtc_cast_bf16", _ptr(src, torch.float32, "src"), _ptr(out), src.numel())
     return out
 
 
@@ -47,8 +66,8 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: in
             out = torch.empty((M, N), dtype=torch.float32, device=a.device)
         else:
             raise RuntimeError("patch-embed epilogue needs an explicit token buffer `out`")
-    _lib.call("vtc_gemm_bf16", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32, "bias"),
-              _ptr(residual, torch.float32, "residual"), _ptr(pos, torch.float32, "pos"), _ptr(out), M, N, K, epilogue, tokens, _stream())
+    _call("vtc_gemm_bf16", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32, "bias"),
+              _ptr(residual, torch.float32, "residual"), _ptr(pos, torch.float32, "pos"), _ptr(out), M, N, K, epilogue, tokens)
     return out
 
 
@@ -57,7 +76,7 @@ def split_bf16(src: torch.Tensor) -> torch.Tensor:
     K = src.shape[-1]
     rows = src.numel() // K
     out = torch.empty(src.shape[:-1] + (2 * K,), dtype=torch.bfloat16, device=src.device)
-    _lib.call("vtc_split_bf16", _ptr(src, torch.float32, "src"), _ptr(out), rows, K, _stream())
+    _call("vtc_split_bf16", _ptr(src, torch.float32, "src"), _ptr(out), rows, K)
     return out
 
 
@@ -82,8 +101,8 @@ def gemm_split(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: i
             out = torch.empty((M, N), dtype=torch.float32, device=a.device)
         else:
             raise RuntimeError("patch-embed epilogue needs an explicit token buffer `out`")
-    _lib.call("vtc_gemm_split", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32, "bias"),
-              _ptr(residual, torch.float32, "residual"), _ptr(pos, torch.float32, "pos"), _ptr(out), M, N, K, epilogue, tokens, _stream())
+    _call("vtc_gemm_split", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32, "bias"),
+              _ptr(residual, torch.float32, "residual"), _ptr(pos, torch.float32, "pos"), _ptr(out), M, N, K, epilogue, tokens)
     return out
 
 
@@ -92,22 +111,22 @@ def patchify(x: torch.Tensor, patch: int, split: bool = False) -> torch.Tensor:
     assert S == S2
     g = S // patch
     out = torch.empty((B * g * g, Cin * patch * patch * (2 if split else 1)), dtype=torch.bfloat16, device=x.device)
-    _lib.call("vtc_patchify_split" if split else "vtc_patchify", _ptr(x, torch.float32, "x"), _ptr(out), B, Cin, S, patch, _stream())
+    _call("vtc_patchify_split" if split else "vtc_patchify", _ptr(x, torch.float32, "x"), _ptr(out), B, Cin, S, patch)
     return out
 
 
 def cls_token_rows(cls_token: torch.Tensor, pos_embed: torch.Tensor, tokens: torch.Tensor) -> None:
     B, N, D = tokens.shape
-    _lib.call("vtc_cls_token_rows", _ptr(cls_token, torch.float32), _ptr(pos_embed, torch.float32), _ptr(tokens, torch.float32),
-              B, N, D, _stream())
+    _call("vtc_cls_token_rows", _ptr(cls_token, torch.float32), _ptr(pos_embed, torch.float32), _ptr(tokens, torch.float32),
+              B, N, D)
 
 
 def layernorm_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, split: bool = False) -> torch.Tensor:
     D = x.shape[-1]
     rows = x.numel() // D
     out = torch.empty(x.shape[:-1] + (D * (2 if split else 1),), dtype=torch.bfloat16, device=x.device)
-    _lib.call("vtc_layernorm_split" if split else "vtc_layernorm_bf16", _ptr(x, torch.float32, "x"), _ptr(weight, torch.float32),
-              _ptr(bias, torch.float32), _ptr(out), rows, D, eps, _stream())
+    _call("vtc_layernorm_split" if split else "vtc_layernorm_bf16", _ptr(x, torch.float32, "x"), _ptr(weight, torch.float32),
+              _ptr(bias, torch.float32), _ptr(out), rows, D, eps)
     return out
 
 
@@ -119,8 +138,8 @@ def attention(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[to
     out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
     cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if want_cls else None
     attn = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv.device) if want_attn else None
-    _lib.call("vtc_attention", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls),
-              _ptr(attn), B, N, heads, scale, _stream())
+    _call("vtc_attention", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls),
+              _ptr(attn), B, N, heads, scale)
     return out, cls, attn
 
 
@@ -132,8 +151,8 @@ def attention_mean(qkv: torch.Tensor, heads: int, scale: float, key_bias: Option
     mean = torch.empty((B, N, N), dtype=torch.float32, device=qkv.device)
     nbytes = int(_lib.load().vtc_attention_mean_scratch_bytes(B, N, heads))
     scratch = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
-    _lib.call("vtc_attention_mean", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), _ptr(mean),
-              _ptr(scratch), nbytes, B, N, heads, scale, _stream())
+    _call("vtc_attention_mean", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), _ptr(mean),
+              _ptr(scratch), nbytes, B, N, heads, scale)
     return out, cls, mean
 
 
@@ -145,8 +164,8 @@ def attention_generic(qkv: torch.Tensor, heads: int, scale: float, key_bias: Opt
     out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
     cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if want_cls else None
     attn = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv.device) if want_attn else None
-    _lib.call("vtc_attention_generic", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), _ptr(attn),
-              B, N, heads, D // heads, scale, _stream())
+    _call("vtc_attention_generic", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), _ptr(attn),
+              B, N, heads, D // heads, scale)
     return out, cls, attn
 
 
@@ -159,15 +178,15 @@ def attention_kv(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional
     out = torch.empty((B, N, D * (2 if split else 1)), dtype=torch.bfloat16, device=qkv.device)
     cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if want_cls else None
     attn = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv.device) if want_attn else None
-    _lib.call("vtc_attention_kv", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls),
-              _ptr(attn), B, N, heads, scale, int(split), _stream())
+    _call("vtc_attention_kv", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls),
+              _ptr(attn), B, N, heads, scale, int(split))
     return out, cls, attn
 
 
 def head_mean(attn: torch.Tensor) -> torch.Tensor:
     B, H, N, _ = attn.shape
     out = torch.empty((B, N, N), dtype=torch.float32, device=attn.device)
-    _lib.call("vtc_head_mean", _ptr(attn, torch.float32), _ptr(out), B, H, N, _stream())
+    _call("vtc_head_mean", _ptr(attn, torch.float32), _ptr(out), B, H, N)
     return out
 
 
@@ -175,7 +194,7 @@ def cls_stat(cls_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     B, H, N = cls_rows.shape
     cmap = torch.empty((B, N - 1), dtype=torch.float32, device=cls_rows.device)
     gmax = torch.zeros((1,), dtype=torch.float32, device=cls_rows.device)
-    _lib.call("vtc_cls_stat", _ptr(cls_rows, torch.float32), _ptr(cmap), _ptr(gmax), B, H, N, _stream())
+    _call("vtc_cls_stat", _ptr(cls_rows, torch.float32), _ptr(cmap), _ptr(gmax), B, H, N)
     return cmap, gmax
 
 
@@ -184,8 +203,8 @@ def cls_mask(cls_map: torch.Tensor, gmax: torch.Tensor, thresh: float = 0.25, pe
     B, P = cls_map.shape
     bg = torch.empty((B, P), dtype=torch.uint8, device=cls_map.device)
     kb = torch.empty((B, P + 1), dtype=torch.float32, device=cls_map.device)
-    _lib.call("vtc_cls_mask", _ptr(cls_map, torch.float32), _ptr(gmax, torch.float32), _ptr(forced_bg, torch.uint8), thresh,
-              int(per_image), _ptr(bg), _ptr(kb), B, P + 1, _stream())
+    _call("vtc_cls_mask", _ptr(cls_map, torch.float32), _ptr(gmax, torch.float32), _ptr(forced_bg, torch.uint8), thresh,
+              int(per_image), _ptr(bg), _ptr(kb), B, P + 1)
     return bg, kb
 
 
@@ -193,14 +212,14 @@ def rollout(attn_mean: torch.Tensor) -> torch.Tensor:
     """attn_mean [L,B,N,N] fp32 -> un-normalised rollout row [B,N-1] (predict.py:215-232)."""
     L, B, N, _ = attn_mean.shape
     out = torch.empty((B, N - 1), dtype=torch.float32, device=attn_mean.device)
-    _lib.call("vtc_rollout", _ptr(attn_mean, torch.float32), _ptr(out), L, B, N, _stream())
+    _call("vtc_rollout", _ptr(attn_mean, torch.float32), _ptr(out), L, B, N)
     return out
 
 
 def cls_layer_map(cls_rows: torch.Tensor, first: int, last: int) -> torch.Tensor:
     L, B, H, N = cls_rows.shape
     out = torch.empty((B, N - 1), dtype=torch.float32, device=cls_rows.device)
-    _lib.call("vtc_cls_layer_map", _ptr(cls_rows, torch.float32), _ptr(out), L, first, last, B, H, N, _stream())
+    _call("vtc_cls_layer_map", _ptr(cls_rows, torch.float32), _ptr(out), L, first, last, B, H, N)
     return out
 
 
@@ -209,14 +228,14 @@ def cam_project(tokens: torch.Tensor, w: torch.Tensor, relu: bool = True, eps: f
     Ccls = w.shape[0]
     g = int(round((N - 1) ** 0.5))
     out = torch.empty((B, Ccls, g, g), dtype=torch.float32, device=tokens.device)
-    _lib.call("vtc_cam_project", _ptr(tokens, torch.float32, "tokens"), _ptr(w, torch.float32, "w"), _ptr(out), B, N, D, Ccls,
-              int(relu), eps, _stream())
+    _call("vtc_cam_project", _ptr(tokens, torch.float32, "tokens"), _ptr(w, torch.float32, "w"), _ptr(out), B, N, D, Ccls,
+              int(relu), eps)
     return out
 
 
 def normalize_max_(maps: torch.Tensor) -> torch.Tensor:
     P = maps.shape[-1]
-    _lib.call("vtc_normalize_max", _ptr(maps, torch.float32), maps.numel() // P, P, _stream())
+    _call("vtc_normalize_max", _ptr(maps, torch.float32), maps.numel() // P, P)
     return maps
 
 
@@ -226,7 +245,7 @@ def upsample_bilinear(maps: torch.Tensor, out_hw: Tuple[int, int], as_u8: bool =
     n = maps.numel() // (g * g)
     H, W = out_hw
     out = torch.empty((*maps.shape[:-2], H, W), dtype=torch.uint8 if as_u8 else torch.float32, device=maps.device)
-    _lib.call("vtc_upsample_bilinear_u8" if as_u8 else "vtc_upsample_bilinear", _ptr(maps, torch.float32), _ptr(out), n, g, H, W, _stream())
+    _call("vtc_upsample_bilinear_u8" if as_u8 else "vtc_upsample_bilinear", _ptr(maps, torch.float32), _ptr(out), n, g, H, W)
     return out
 
 
@@ -235,7 +254,7 @@ def cam_label(cam: torch.Tensor, labels: torch.Tensor, out_hw: Tuple[int, int], 
     H, W = out_hw
     lab = labels.to(torch.uint8).contiguous()
     out = torch.empty((B, H, W), dtype=torch.uint8, device=cam.device)
-    _lib.call("vtc_cam_label", _ptr(cam, torch.float32), _ptr(lab, torch.uint8), bg_thresh, _ptr(out), B, Ccls, g, H, W, _stream())
+    _call("vtc_cam_label", _ptr(cam, torch.float32), _ptr(lab, torch.uint8), bg_thresh, _ptr(out), B, Ccls, g, H, W)
     return out
 
 
@@ -247,8 +266,8 @@ def hwp_cos_vote(hwp_logits: torch.Tensor, head1_w: torch.Tensor, hwp_tokens: to
     g = int(round((N - 1) ** 0.5))
     p2c = torch.empty((B, K), dtype=torch.int32, device=tokens.device)
     cos = torch.empty((B, K, g, g), dtype=torch.float32, device=tokens.device)
-    _lib.call("vtc_hwp_cos_vote", _ptr(hwp_logits, torch.float32), _ptr(head1_w, torch.float32), _ptr(hwp_tokens, torch.float32),
-              _ptr(tokens, torch.float32), sig_thresh, _ptr(p2c), _ptr(cos), B, N, D, Ccls, K, _stream())
+    _call("vtc_hwp_cos_vote", _ptr(hwp_logits, torch.float32), _ptr(head1_w, torch.float32), _ptr(hwp_tokens, torch.float32),
+              _ptr(tokens, torch.float32), sig_thresh, _ptr(p2c), _ptr(cos), B, N, D, Ccls, K)
     return p2c, cos
 
 
@@ -257,15 +276,15 @@ def hwp_seg(cos: torch.Tensor, p2c: torch.Tensor, bg_map: torch.Tensor, out_hw: 
     B, K, g, _ = cos.shape
     H, W = out_hw
     out = torch.empty((B, H, W), dtype=torch.uint8, device=cos.device)
-    _lib.call("vtc_hwp_seg", _ptr(cos, torch.float32), _ptr(p2c, torch.int32), _ptr(bg_map, torch.float32), cos_thresh, bg_thresh,
-              _ptr(out), B, K, g, H, W, _stream())
+    _call("vtc_hwp_seg", _ptr(cos, torch.float32), _ptr(p2c, torch.int32), _ptr(bg_map, torch.float32), cos_thresh, bg_thresh,
+              _ptr(out), B, K, g, H, W)
     return out
 
 
 def confmat_update(mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
     n = mat.shape[0]
-    _lib.call("vtc_confmat_update", _ptr(gt, torch.uint8, "gt"), _ptr(pred, torch.uint8, "pred"), gt.numel(), n,
-              _ptr(mat, torch.int64, "mat"), _stream())
+    _call("vtc_confmat_update", _ptr(gt, torch.uint8, "gt"), _ptr(pred, torch.uint8, "pred"), gt.numel(), n,
+              _ptr(mat, torch.int64, "mat"))
     return mat
 
 
@@ -274,8 +293,8 @@ def average_precision(labels: torch.Tensor, scores: torch.Tensor, acc: Optional[
     `acc` (fp64 [2], optional) accumulates (sum of APs, number of scored images)."""
     B, C = scores.shape
     ap = torch.empty((B,), dtype=torch.float64, device=scores.device)
-    _lib.call("vtc_average_precision", _ptr(labels, torch.float32, "labels"), _ptr(scores, torch.float32, "scores"), B, C, _ptr(ap),
-              _ptr(acc, torch.float64, "acc"), _stream())
+    _call("vtc_average_precision", _ptr(labels, torch.float32, "labels"), _ptr(scores, torch.float32, "scores"), B, C, _ptr(ap),
+              _ptr(acc, torch.float64, "acc"))
     return ap
 
 
@@ -284,7 +303,7 @@ def patch_similarity(tokens: torch.Tensor) -> torch.Tensor:
     B, N, D = tokens.shape
     scratch = torch.empty((B, D), dtype=torch.float32, device=tokens.device)
     sim = torch.empty((B, N, N), dtype=torch.float32, device=tokens.device)
-    _lib.call("vtc_patch_similarity", _ptr(tokens, torch.float32, "tokens"), _ptr(scratch), _ptr(sim), B, N, D, _stream())
+    _call("vtc_patch_similarity", _ptr(tokens, torch.float32, "tokens"), _ptr(scratch), _ptr(sim), B, N, D)
     return sim
 
 
@@ -295,7 +314,7 @@ def patchify_u8(x: torch.Tensor, patch: int, mean, std, split: bool = False) -> 
     assert S == S2 and Cin == 3 and x.dtype == torch.uint8
     g = S // patch
     out = torch.empty((B * g * g, 3 * patch * patch * (2 if split else 1)), dtype=torch.bfloat16, device=x.device)
-    _lib.call("vtc_patchify_u8", _ptr(x), (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std), _ptr(out), B, S, patch, int(split), _stream())
+    _call("vtc_patchify_u8", _ptr(x), (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std), _ptr(out), B, S, patch, int(split))
     return out
 
 
@@ -306,8 +325,8 @@ def fold_ln(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: torc
     wf = torch.empty((N, K), dtype=torch.bfloat16, device=w.device)
     g = torch.empty((N,), dtype=torch.float32, device=w.device)
     c = torch.empty((N,), dtype=torch.float32, device=w.device)
-    _lib.call("vtc_fold_ln", _ptr(w, torch.float32, "w"), _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(bias, torch.float32),
-              _ptr(wf), _ptr(g), _ptr(c), N, K, _stream())
+    _call("vtc_fold_ln", _ptr(w, torch.float32, "w"), _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(bias, torch.float32),
+              _ptr(wf), _ptr(g), _ptr(c), N, K)
     return wf, g, c
 
 
@@ -316,7 +335,7 @@ def residual_prep(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     rows, D = x.shape
     xb = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
     stats = torch.empty((rows, D // 128, 2), dtype=torch.float32, device=x.device)
-    _lib.call("vtc_residual_prep", _ptr(x, torch.float32, "x"), _ptr(xb), _ptr(stats), rows, D, _stream())
+    _call("vtc_residual_prep", _ptr(x, torch.float32, "x"), _ptr(xb), _ptr(stats), rows, D)
     return xb, stats
 
 
@@ -329,8 +348,8 @@ def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     ob = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     stats = torch.empty((M, N // 128, 2), dtype=torch.float32, device=a.device)
-    _lib.call("vtc_gemm_resid_ln", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32), _ptr(residual, torch.float32),
-              _ptr(out, torch.float32), _ptr(ob), _ptr(stats), M, N, K, _stream())
+    _call("vtc_gemm_resid_ln", _ptr(a, torch.bfloat16, "a"), _ptr(w, torch.bfloat16, "w"), _ptr(bias, torch.float32), _ptr(residual, torch.float32),
+              _ptr(out, torch.float32), _ptr(ob), _ptr(stats), M, N, K)
     return out, ob, stats
 
 
@@ -339,6 +358,6 @@ def gemm_lnfold(a: torch.Tensor, wf: torch.Tensor, c: torch.Tensor, g: torch.Ten
     M, K = a.shape
     N = wf.shape[0]
     out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-    _lib.call("vtc_gemm_lnfold", _ptr(a, torch.bfloat16, "a"), _ptr(wf, torch.bfloat16, "wf"), _ptr(c, torch.float32), _ptr(g, torch.float32),
-              _ptr(stats, torch.float32), eps, _ptr(out), M, N, K, int(gelu), _stream())
+    _call("vtc_gemm_lnfold", _ptr(a, torch.bfloat16, "a"), _ptr(wf, torch.bfloat16, "wf"), _ptr(c, torch.float32), _ptr(g, torch.float32),
+              _ptr(stats, torch.float32), eps, _ptr(out), M, N, K, int(gelu))
     return out

@@ -281,6 +281,7 @@ class _Engine:
         w.num_layers = L
         nbytes = self.lib.vtc_model_packed_bytes(self.handle)
         if self.packed is None or self.packed.device != device or self.packed.numel() < nbytes:
+            self.graphs.clear()          # captured graphs point into the old buffer
             self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _lib.check(self.lib.vtc_model_pack_weights(self.handle, ctypes.byref(w), self.packed.data_ptr(), nbytes,
                                                    torch.cuda.current_stream(device).cuda_stream), "vtc_model_pack_weights")
@@ -366,6 +367,11 @@ class VisionTransformer(nn.Module):
             raise NotImplementedError("non-zero dropout / drop-path: the fused inference path has no stochastic ops")
         if not qkv_bias:
             raise NotImplementedError("qkv_bias=False is not used by any reference factory")
+        # the fused forward computes scale = head_dim ** -0.5, erf-GELU and LayerNorm; anything else would be silently ignored
+        if qk_scale is not None and abs(float(qk_scale) - (embed_dim // num_heads) ** -0.5) > 1e-12:
+            raise NotImplementedError("qk_scale other than head_dim ** -0.5 is not used by any reference factory")
+        if act_layer is not None and act_layer is not nn.GELU:
+            raise NotImplementedError("act_layer other than nn.GELU (erf) is not supported by the fused forward")
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
         self.num_tokens = 1
@@ -385,6 +391,8 @@ class VisionTransformer(nn.Module):
                   norm_layer=norm_layer, act_layer=act_layer)
             for _ in range(depth)])
         self.norm = norm_layer(embed_dim)
+        if not (type(self.norm) is nn.LayerNorm and self.norm.elementwise_affine and self.norm.bias is not None):
+            raise NotImplementedError("norm_layer must build an affine nn.LayerNorm (any eps): the fused forward has no other norm")
         if representation_size:
             self.has_logits = True
             self.num_features = representation_size
@@ -486,10 +494,10 @@ class VisionTransformer(nn.Module):
         gkey = (tuple(x.shape), x.dtype, dev, self.precision, tuple(sorted(kw.items())))
         with torch.cuda.device(dev):
             eng.ensure_packed(self, dev)
-            ptrs = tuple(k[0] for k in eng.key[2])
+            ptrs = (eng.packed.data_ptr(),) + tuple(k[0] for k in eng.key[2])
             ent = eng.graphs.get(gkey)
             if ent is not None and ent[4] != ptrs:
-                ent = None                                   # parameters moved: the captured pointers are stale
+                ent = None                                   # parameters or the packed weights moved: the captured pointers are stale
             if ent is None:
                 static_x = x.clone()
                 cur = torch.cuda.current_stream(dev)
@@ -502,12 +510,35 @@ class VisionTransformer(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     out = call(static_x, **kw)
-                ent = (graph, static_x, out, eng.ws, ptrs)   # the workspace the graph points into stays alive with the entry
+                ent = (graph, static_x, out, eng.ws, ptrs, eng.packed)   # workspace and packed weights the graph points into stay alive with the entry
                 eng.graphs[gkey] = ent
             graph, static_x, out = ent[0], ent[1], ent[2]
             static_x.copy_(x, non_blocking=True)
             graph.replay()
         return out
+
+    @torch.no_grad()
+    def topk_heads(self, tokens: torch.Tensor, cls_map: torch.Tensor, gmax: Optional[torch.Tensor] = None,
+                   forced_topk: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """vit_model.py:372-422 on given inputs (`vtc_topk_heads`): tokens [B,N,D] fp32 (block-L output), cls_map [B,P] (the
+        renormalised CLS row of :366-371), gmax [1] (batch-global max, :372; None = per-image max)
+        -> (logits [B,C], hwp_logits [B,C], hwp_tokens [B,16,D], topk_idx [B,16] int32)."""
+        _require_cuda(tokens, "topk_heads")
+        if self._engine is None:
+            self._engine = _Engine(self)
+        eng, dev = self._engine, tokens.device
+        B, K, D, C = tokens.shape[0], eng.cfg.topk, eng.cfg.embed_dim, eng.cfg.num_classes
+        with torch.cuda.device(dev):
+            eng.ensure_packed(self, dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            logits, hwp, ori = torch.empty((B, C), **f32), torch.empty((B, C), **f32), torch.empty((B, K, D), **f32)
+            idx = torch.empty((B, K), dtype=torch.int32, device=dev)
+            tk = None if forced_topk is None else forced_topk.to(device=dev, dtype=torch.int32).contiguous()
+            tokens, cls_map = tokens.float().contiguous(), cls_map.float().contiguous()
+            _lib.check(eng.lib.vtc_topk_heads(eng.handle, tokens.data_ptr(), cls_map.data_ptr(), None if gmax is None else gmax.data_ptr(),
+                                              None if tk is None else tk.data_ptr(), logits.data_ptr(), hwp.data_ptr(), ori.data_ptr(),
+                                              idx.data_ptr(), B, torch.cuda.current_stream(dev).cuda_stream), "vtc_topk_heads")
+        return logits, hwp, ori, idx
 
     def kernel_profile(self, enable: Optional[bool] = None):
         """enable/disable CUDA-event timing of every kernel of the fused forward, or (no argument) read the accumulated
