@@ -19,7 +19,22 @@ import sys
 import tempfile
 import types
 
-REFERENCE_DIR = os.environ.get("VTC_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference() -> str:
+    """/root/reference in the build container; on the GPU box the byte-identical copy that oracle/make_ref.py wrote into the
+    git-ignored oracle/_ref/ (only vit_model.py travels: enough to run the reference model, not make_golden.py)."""
+    env = os.environ.get("VTC_REFERENCE_DIR")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "vit_model.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_DIR = _find_reference()
 
 
 def voc_palette():
@@ -77,6 +92,23 @@ def import_reference():
         os.chdir(cwd)
         torch.set_printoptions(threshold=popts)
     return ref
+
+
+class on_cpu:
+    """`with ref_shim.on_cpu():` runs the reference model on the host of a machine that HAS a GPU: its unconditional
+    `.cuda()` calls (vit_model.py:331,348,368) are the identity inside the block and restored afterwards (the same model
+    code then runs unmodified on the GPU for the on-box eager baseline)."""
+
+    def __enter__(self):
+        import torch
+        self._saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._saved
+        return False
 
 
 def reference_source_lines(fname: str, first: int, last: int) -> str:

@@ -153,11 +153,29 @@ def test_gloo_world_size_2_gather_and_reduce(tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (CPU oracle port of the reference) prints one JSON line with the contract's keys."""
+    """`bench.py --impl reference` (the reference's own vit_model.py from oracle/_ref when the recipe oracle/make_ref.py has
+    run, else the CPU oracle port) prints one JSON line with the contract's keys, at the batch it was asked for."""
     import json
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--batch", "8"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["batch_per_gpu"] == 8 and "1 step(s) x 8 images" in line["cpu_baseline"]["sample"]
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "vit_model.py")) or os.path.exists("/root/reference/vit_model.py")
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_copy_recipe_and_shim():
+    """oracle/make_ref.py writes a byte-identical, git-ignored copy of the reference model; the shim finds it."""
+    import hashlib
+    import json
+    from oracle import make_ref, ref_shim
+    if not os.path.exists("/root/reference/vit_model.py"):
+        pytest.skip("build container only")
+    assert make_ref.make()
+    man = json.load(open(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json")))
+    assert man["sha256"]["vit_model.py"] == hashlib.sha256(open("/root/reference/vit_model.py", "rb").read()).hexdigest()
+    assert ref_shim.available()
+    ignored = subprocess.run(["git", "-C", ROOT, "check-ignore", "oracle/_ref/vit_model.py"], capture_output=True, text=True)
+    assert ignored.returncode == 0            # never part of the history
