@@ -315,9 +315,9 @@ def other_configs(dev, rank, world, pk):
         x = torch.randn((Bc, 3, kw["img_size"], kw["img_size"]), generator=torch.Generator(device=dev).manual_seed(3000 + rank), device=dev)
 
         def step():
-            o = model.forward_cam(x, attn_mean=rollout)
+            o = model.forward_cam(x, rollout=rollout)
             cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)
-            return (cam, CAM.rollout_row(o.attn_mean)) if rollout else (cam,)
+            return (cam, o.rollout) if rollout else (cam,)
 
         for _ in range(3):
             step()

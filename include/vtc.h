@@ -121,6 +121,9 @@ typedef struct vtc_outputs {
     float*   attn_mean;   /* [L,B,N,N]   head-mean P_l (what rollout consumes)    predict.py:189-190 */
     uint8_t* bg;          /* [L,B,P]     background vector built after layer l (0 for l < mask_from) :337-342 */
     float*   cls_map;     /* [L,B,P]     renormalised head-mean CLS row (before /max)  vit_model.py:329-334 */
+    float*   rollout;     /* [B,P]       attention rollout row over the last min(L,12) layers, un-normalised: (e0^T A_{L-1} .. A_0)[1:],
+                                          A_l = (head-mean P_l + I) / rowsum; the head means stay in the workspace as bf16
+                                          "rollout operands" (half the bytes of attn_mean)              predict.py:215-232 */
 } vtc_outputs;
 
 typedef struct vtc_model vtc_model;   /* host-side handle: config, packed-weight pointers, TMA descriptors */
@@ -168,7 +171,7 @@ VTC_API int vtc_forward_u8(vtc_model* m, const uint8_t* x, const float* mean, co
 enum {
     VTC_PROF_PATCHIFY = 0, VTC_PROF_GEMM_PATCH = 1, VTC_PROF_LAYERNORM = 2, VTC_PROF_GEMM_QKV = 3, VTC_PROF_ATTENTION = 4,
     VTC_PROF_GEMM_PROJ = 5, VTC_PROF_GEMM_FC1 = 6, VTC_PROF_GEMM_FC2 = 7, VTC_PROF_CLS = 8, VTC_PROF_HEAD_MEAN = 9,
-    VTC_PROF_HEADS = 10, VTC_PROF_KINDS = 11
+    VTC_PROF_HEADS = 10, VTC_PROF_ROLLOUT = 11, VTC_PROF_KINDS = 12
 };
 VTC_API int vtc_model_profile(vtc_model* m, int32_t enable);
 VTC_API int vtc_model_profile_read(vtc_model* m, float* ms_per_kind, int32_t* launches_per_kind);
@@ -276,6 +279,15 @@ VTC_API int vtc_topk_heads(const vtc_model* m, const float* tokens, const float*
  * attention rollout (predict.py:215-232): attn_mean [L,B,N,N] -> row [B,P] = (e0^T A_{L-1} ... A_0)[1:] with
  * A_l = (mean_l + I)/rowsum, evaluated as a reverse vector-matrix chain. */
 VTC_API int vtc_rollout(const float* attn_mean, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream);
+/* The same chain on bf16 "rollout operands", the form the forward keeps the head means in: per layer
+ * bf16 [B,N,ldr], ldr = vtc_rollout_operand_ld(N) = N + 2 rounded up to 8; a row = N values | zero padding | the fp32 sum of
+ * the N rounded values in its last four bytes.  16-byte aligned rows: the kernel streams row blocks with bulk copies. */
+VTC_API int32_t vtc_rollout_operand_ld(int32_t n_tokens);
+VTC_API int vtc_rollout_operand_from_mean(const float* attn_mean, void* operand, int32_t batch, int32_t n_tokens, void* stream);
+VTC_API int vtc_rollout_operands(const void* operands, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream);
+/* vtc_attention_mean writing the rollout operand of the layer (attn_mean and / or operand non-NULL) */
+VTC_API int vtc_attention_mean_operand(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* operand,
+                               void* scratch, size_t scratch_bytes, int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream);
 /* per-layer CLS maps / bg map (predict.py:261-266, validate.py:225-237): cls_rows [L,B,H,N] ->
  * maps [B,P]: mean over layers [first,last) and heads, + identity on the CLS entry, / rowsum, patches, / max. */
 VTC_API int vtc_cls_layer_map(const float* cls_rows, float* map, int32_t layers, int32_t first, int32_t last, int32_t batch,

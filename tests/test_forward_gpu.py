@@ -202,6 +202,33 @@ def test_batch_256_against_the_oracle(env, regime):
     assert float(per_image.mean()) >= LABEL_AGREE
 
 
+def test_fused_rollout_output_matches_the_attn_mean_path_and_the_reference(env):
+    """forward_cam(rollout=True): the rollout row computed inside the forward from bf16 rollout operands == the row obtained
+    from the fp32 attn_mean output of the same forward (storage rounding only), in every configuration of requested outputs
+    (packed-P path, full-P path, both), and against the reference golden at the CAM bar."""
+    from vision_transformer_cam_b200 import cam as CAM
+    gold = np.load(os.path.join(GOLDEN, "masked_b1.npz"))
+    model = load(env, "masked")
+    x = env["VF"].make_images(0, 1).to(env["dev"])
+    forced = {4 + i: torch.from_numpy(gold["bg"][i]) for i in range(gold["bg"].shape[0])}
+    kw = dict(forced_bg=forced, forced_topk=torch.from_numpy(gold["topk_idx"]))
+    a = model.forward_cam(x, rollout=True, **kw)
+    b = model.forward_cam(x, rollout=True, attn_mean=True, **kw)
+    c = model.forward_cam(x, rollout=True, attn_layers=12, **kw)           # head means from the full fp32 P
+    d = model.forward_cam(x, rollout=True, attn_layers=3, attn_mean=True, **kw)
+    ref_row = CAM.rollout_row(b.attn_mean)
+    assert torch.equal(a.rollout, b.rollout) and torch.equal(a.logits, b.logits)
+    for o in (a, c, d):
+        assert relerr(o.rollout, ref_row) < 2e-3, relerr(o.rollout, ref_row)
+        assert cosine(o.rollout, gold["rollout_row"]) >= CAM_COS
+    assert cosine(CAM.rollout_map(a.rollout, (375, 500)), gold["rollout_up"].astype(np.float32)) >= CAM_COS
+    # batch of 5 with per-image normalisation == image by image
+    xs = env["VF"].make_images(20, 5).to(env["dev"])
+    full = model.forward_cam(xs, rollout=True, mask_norm="image")
+    one = model.forward_cam(xs[3:4], rollout=True, mask_norm="image")
+    assert torch.equal(full.rollout[3:4], one.rollout)
+
+
 def test_peaked_regime_teacher_forced_continuous_parity(env):
     gold = np.load(os.path.join(GOLDEN, "peaked_b3.npz"))
     model = load(env, "peaked")

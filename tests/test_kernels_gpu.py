@@ -294,8 +294,21 @@ def test_topk_heads_bit_exact(dev):
                 assert torch.equal(ref_idx, torch.from_numpy(gold["topk_idx"].astype(np.int64)))   # == what the reference chose
             gmax = None if per_image else c.max().reshape(1).to(dev)
             logits, hwp, ori, idx = model.topk_heads(tokens, c.to(dev), gmax)
-            assert torch.equal(idx.cpu().long(), ref_idx), (name, per_image)
-            ref_ori = torch.stack([tokens[j][ref_idx[j].to(dev) + 1] for j in range(B)])           # :381-389
+            idx = idx.cpu().long()
+            # the selected VALUES, in order, are torch.topk's bit for bit; the INDICES are identical wherever the order is
+            # defined.  Bit-equal fp32 quotients (one pair among these 256 x 16) have no defined order in torch.topk (its CPU
+            # and CUDA kernels disagree with each other); libvtc returns the smaller index first.
+            assert torch.equal(m14.gather(1, idx), m14.gather(1, ref_idx)), (name, per_image)
+            v = m14.gather(1, ref_idx)
+            tied = torch.zeros_like(v, dtype=torch.bool)
+            tied[:, 1:] |= v[:, 1:] == v[:, :-1]
+            tied[:, :-1] |= v[:, :-1] == v[:, 1:]
+            assert torch.equal(idx[~tied], ref_idx[~tied]), (name, per_image)
+            assert int(tied.sum()) <= 4 and bool((idx.sort(1).values == ref_idx.sort(1).values).all())     # same SET in every image
+            for b, k in tied.nonzero().tolist():
+                if k + 1 < 16 and v[b, k] == v[b, k + 1]:
+                    assert idx[b, k] < idx[b, k + 1]
+            ref_ori = torch.stack([tokens[j][idx[j].to(dev) + 1] for j in range(B)])               # :381-389
             assert torch.equal(ori, ref_ori)
             ref_hwp = F.linear(ref_ori.mean(dim=1), model.head1.weight, model.head1.bias)          # :392-393
             assert relerr(hwp, ref_hwp) <= 1e-6, relerr(hwp, ref_hwp)
@@ -355,6 +368,55 @@ def test_rollout_and_layer_maps(dev):
     assert float((bgm.cpu() - PP.bg_map(cls_rows.cpu())).abs().max()) < 1e-6
     lm = torch.stack([ops.cls_layer_map(cls_rows, l, l + 1) for l in range(L)])
     assert float((lm.cpu().view(L, B, 14, 14) - PP.layer_maps(P_list)).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("L,B,N", [(12, 3, 197), (12, 2, 785), (5, 4, 50), (1, 2, 197), (12, 1, 577)])
+def test_rollout_operand_streaming_kernel(dev, L, B, N):
+    """The forward's rollout path: head means as bf16 'rollout operands' (row = N values | zero padding | fp32 sum of the rounded
+    values), streamed by bulk copies.  (1) Exact on the values it is given: equal to the fp32 dense chain of predict.py:221-232
+    run on the SAME bf16-rounded matrices to 1e-5; (2) against the un-rounded fp32 chain the bf16 storage costs < 4e-3 relative
+    and the cosine stays > 0.99999 (bar 0.999)."""
+    from vision_transformer_cam_b200 import ops
+    from oracle import postproc as PP
+    g = torch.Generator().manual_seed(61 + N)
+    mean = torch.stack([(torch.randn((B, N, N), generator=g) * 2).softmax(-1) for _ in range(L)])          # [L,B,N,N]
+    opnd = ops.rollout_operand_from_mean(mean.to(dev))
+    ldr = ops.rollout_operand_ld(N)
+    assert opnd.shape == (L, B, N, ldr) and ldr % 8 == 0 and ldr >= N + 2
+    rounded = mean.bfloat16().float()
+    assert torch.equal(opnd[..., :N].float().cpu(), rounded) and float(opnd[..., N:ldr - 2].float().abs().max()) == 0.0
+    rs = opnd[..., ldr - 2:].contiguous().view(torch.float32)[..., 0].cpu()
+    assert float((rs - rounded.sum(-1)).abs().max()) < 1e-5
+    row = ops.rollout_operands(opnd, N).cpu()
+
+    def dense(m):                                              # predict.py:215-232 on head means m [L,B,N,N]
+        aug = m.double() + torch.eye(N, dtype=torch.float64)
+        aug = aug / aug.sum(-1, keepdim=True)
+        joint = aug[0]
+        for n in range(1, L):
+            joint = aug[n] @ joint
+        return joint[:, 0, 1:]
+
+    assert relerr(row, dense(rounded)) < 1e-5, relerr(row, dense(rounded))
+    full = dense(mean)
+    assert relerr(row, full) < 4e-3          # one bf16 rounding (2^-9) at most; it averages out over the chain for L > 1
+    cos = float((row.double().flatten() @ full.flatten()) / (row.double().norm() * full.norm()))
+    assert cos > 0.99999, cos
+    # and the fp32 entry point on the fp32 matrices
+    assert relerr(ops.rollout(mean.to(dev)).cpu(), full) < 1e-5
+
+
+def test_attention_mean_operand_equals_fp32_head_mean(dev):
+    """The packed-P head mean leaving as a rollout operand == bf16(fp32 head mean of the same kernel), plus its row sum."""
+    from vision_transformer_cam_b200 import ops
+    for B, N, H in ((3, 197, 12), (2, 577, 16)):
+        qkv = (_rand((B, N, 3 * H * 64), 90 + N, dev) * 1.5).bfloat16()
+        _, _, mean = ops.attention_mean(qkv, H, 0.125)
+        _, _, opnd = ops.attention_mean_operand(qkv, H, 0.125)
+        ldr = ops.rollout_operand_ld(N)
+        assert torch.equal(opnd[..., :N], mean.bfloat16())
+        rs = opnd[..., ldr - 2:].contiguous().view(torch.float32)[..., 0]
+        assert float((rs - mean.bfloat16().float().sum(-1)).abs().max()) < 1e-5 and float((rs - 1).abs().max()) < 5e-3
 
 
 def test_cam_project_upsample_label(dev):

@@ -15,7 +15,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_PATCH_EMBED = 0, 1, 2, 3
 FWD_MASK_NORM_IMAGE = 1 << 0
 FWD_FP32_SPLIT = 1 << 1
 PRECISION_BF16, PRECISION_FP32_SPLIT = 0, 1
-PROF_KINDS = ("patchify", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "cls", "head_mean", "heads")
+PROF_KINDS = ("patchify", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "cls", "head_mean", "heads", "rollout")
 
 c_f32p = C.c_void_p   # device pointers are passed as integers
 
@@ -51,7 +51,7 @@ class Forcing(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("logits", C.c_void_p), ("hwp_logits", C.c_void_p), ("hwp_tokens", C.c_void_p), ("topk_idx", C.c_void_p),
                 ("tokens", C.c_void_p), ("tokens_layers", C.c_int32), ("cls_rows", C.c_void_p), ("attn", C.c_void_p),
-                ("attn_layers", C.c_int32), ("attn_mean", C.c_void_p), ("bg", C.c_void_p), ("cls_map", C.c_void_p)]
+                ("attn_layers", C.c_int32), ("attn_mean", C.c_void_p), ("bg", C.c_void_p), ("cls_map", C.c_void_p), ("rollout", C.c_void_p)]
 
 
 _P, _I, _F, _Z, _U = C.c_void_p, C.c_int32, C.c_float, C.c_size_t, C.c_uint32
@@ -98,6 +98,10 @@ SIGNATURES = {
     "vtc_cls_mask": (C.c_int, [_P, _P, _P, _F, _I, _P, _P, _I, _I, _P]),
     "vtc_topk_heads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "vtc_rollout": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    "vtc_rollout_operand_ld": (C.c_int32, [_I]),
+    "vtc_rollout_operand_from_mean": (C.c_int, [_P, _P, _I, _I, _P]),
+    "vtc_rollout_operands": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    "vtc_attention_mean_operand": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _F, _P]),
     "vtc_cls_layer_map": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vtc_cam_project": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "vtc_normalize_max": (C.c_int, [_P, _I, _I, _P]),

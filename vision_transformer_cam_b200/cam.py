@@ -42,8 +42,9 @@ def rollout_row(attn_mean: torch.Tensor) -> torch.Tensor:
 
 
 def rollout_map(attn_mean: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-    """predict.py:229-247: rollout row / max, g x g, bilinear (cv2.resize == align_corners=False) to (H,W)."""
-    row = ops.normalize_max_(rollout_row(attn_mean))
+    """predict.py:229-247: rollout row / max, g x g, bilinear (cv2.resize == align_corners=False) to (H,W).  Takes the head
+    means [L,B,N,N] or an already computed rollout row [B,P] (`forward_cam(rollout=True).rollout`)."""
+    row = ops.normalize_max_(rollout_row(attn_mean) if attn_mean.dim() == 4 else attn_mean.clone())
     B, P = row.shape
     g = int(round(P ** 0.5))
     m = row.view(B, g, g)

@@ -452,10 +452,12 @@ int head_mean(const float* attn_in, float* mean, int batch, int heads, int n_tok
 // are added in order, so the result is bit-reproducible.  A segment leaves through a per-warp staging line because
 // [B,N,N] rows (N odd) are not 16-byte aligned: the global stores are 32 consecutive floats per instruction.
 constexpr int HMP_WARPS = 8;
-template <bool MTAB>
+// OPERAND: the row leaves as the bf16 rollout operand (ops.h: N values | zero padding | fp32 sum of the rounded values) with
+// one 16-byte store per lane; otherwise as fp32 [B,N,N] through the staging line.
+template <bool MTAB, bool OPERAND>
 __global__ void __launch_bounds__(HMP_WARPS * 32)
 head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ mtab, const float* __restrict__ mfin,
-                        const float* __restrict__ einv, float* __restrict__ mean, int B, int H, int N, int ld) {
+                        const float* __restrict__ einv, float* __restrict__ mean, uint4* __restrict__ operand, int B, int H, int N, int ld, int ldr) {
     __shared__ float stage[HMP_WARPS][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int vec_per_row = ld >> 3;                     // uint4 per row
@@ -466,8 +468,10 @@ head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ m
     for (int rid = blockIdx.x * HMP_WARPS + warp; rid < nrows; rid += gridDim.x * HMP_WARPS) {
         const int b = rid / N, r = rid - b * N;
         const size_t row0 = static_cast<size_t>(b) * H * N + r;          // (b, h = 0, r); + h * N per head
-        float* dst = mean + static_cast<size_t>(rid) * N;
-        for (int seg = 0; seg * 256 < N; ++seg) {
+        float* dst = OPERAND ? nullptr : mean + static_cast<size_t>(rid) * N;
+        uint4* odst = OPERAND ? operand + static_cast<size_t>(rid) * (ldr >> 3) : nullptr;
+        float rsum = 0.f;
+        for (int seg = 0; seg * 256 < (OPERAND ? ldr : N); ++seg) {
             const int v = seg * 32 + lane;                // my uint4 of the row; keys 8 v .. 8 v + 7, chunk v / 4
             float acc[8];
 #pragma unroll
@@ -499,19 +503,36 @@ head_mean_packed_kernel(const uint4* __restrict__ e, const float* __restrict__ m
                     }
                 }
             }
-            float4* s4 = reinterpret_cast<float4*>(st + lane * 8);
-            s4[0] = make_float4(acc[0] * invh, acc[1] * invh, acc[2] * invh, acc[3] * invh);
-            s4[1] = make_float4(acc[4] * invh, acc[5] * invh, acc[6] * invh, acc[7] * invh);
-            __syncwarp();
-            const int nseg = min(256, N - seg * 256);
-            for (int c = lane; c < nseg; c += 32) dst[seg * 256 + c] = st[c];
-            __syncwarp();
+            if (OPERAND) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = (8 * v + 2 * j < N) ? bf16_round(acc[2 * j] * invh) : 0.f;          // columns >= N: zero padding
+                    const float c = (8 * v + 2 * j + 1 < N) ? bf16_round(acc[2 * j + 1] * invh) : 0.f;
+                    rsum += a + c;
+                    pk[j] = pack_bf16x2(a, c);
+                }
+                const bool last_seg = (seg + 1) * 256 >= ldr;
+                if (last_seg) {                    // the row sum (of the rounded values) rides in the last four bytes of the row
+                    rsum = warp_sum(rsum);
+                    if (v == (ldr >> 3) - 1) pk[3] = __float_as_uint(rsum);
+                }
+                if (v < (ldr >> 3)) odst[v] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            } else {
+                float4* s4 = reinterpret_cast<float4*>(st + lane * 8);
+                s4[0] = make_float4(acc[0] * invh, acc[1] * invh, acc[2] * invh, acc[3] * invh);
+                s4[1] = make_float4(acc[4] * invh, acc[5] * invh, acc[6] * invh, acc[7] * invh);
+                __syncwarp();
+                const int nseg = min(256, N - seg * 256);
+                for (int c = lane; c < nseg; c += 32) dst[seg * 256 + c] = st[c];
+                __syncwarp();
+            }
         }
     }
 }
 
-int head_mean_packed(const PackedP& pk, float* mean, int batch, int heads, int n_tokens, int ld, cudaStream_t stream) {
-    VTC_REQUIRE(pk.e && pk.einv && mean && ((pk.mtab == nullptr) == (pk.mfin == nullptr)), VTC_ERR_ARG, "head_mean_packed: null pointer");
+static int head_mean_packed_launch(const PackedP& pk, float* mean, void* operand, int batch, int heads, int n_tokens, int ld, cudaStream_t stream) {
+    VTC_REQUIRE(pk.e && pk.einv && (mean || operand) && ((pk.mtab == nullptr) == (pk.mfin == nullptr)), VTC_ERR_ARG, "head_mean_packed: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0 && ld >= n_tokens && ld % 32 == 0, VTC_ERR_SHAPE, "head_mean_packed: bad shape");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
@@ -519,12 +540,22 @@ int head_mean_packed(const PackedP& pk, float* mean, int batch, int heads, int n
     int blocks = cdiv(nrows, HMP_WARPS);
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    if (pk.mtab) head_mean_packed_kernel<true><<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(pk.e), pk.mtab, pk.mfin, pk.einv, mean,
-                                                                                     batch, heads, n_tokens, ld);
-    else head_mean_packed_kernel<false><<<blocks, HMP_WARPS * 32, 0, stream>>>(static_cast<const uint4*>(pk.e), nullptr, nullptr, pk.einv, mean, batch,
-                                                                               heads, n_tokens, ld);
+    const int ldr = rollout_operand_ld(n_tokens);
+    const uint4* e = static_cast<const uint4*>(pk.e);
+    uint4* op = static_cast<uint4*>(operand);
+    if (operand) VTC_REQUIRE((reinterpret_cast<uintptr_t>(operand) & 15) == 0 && ldr <= ld + 8, VTC_ERR_ARG, "head_mean_packed: operand alignment / stride");
+    if (pk.mtab && operand) head_mean_packed_kernel<true, true><<<blocks, HMP_WARPS * 32, 0, stream>>>(e, pk.mtab, pk.mfin, pk.einv, nullptr, op, batch, heads, n_tokens, ld, ldr);
+    else if (pk.mtab) head_mean_packed_kernel<true, false><<<blocks, HMP_WARPS * 32, 0, stream>>>(e, pk.mtab, pk.mfin, pk.einv, mean, nullptr, batch, heads, n_tokens, ld, ldr);
+    else if (operand) head_mean_packed_kernel<false, true><<<blocks, HMP_WARPS * 32, 0, stream>>>(e, nullptr, nullptr, pk.einv, nullptr, op, batch, heads, n_tokens, ld, ldr);
+    else head_mean_packed_kernel<false, false><<<blocks, HMP_WARPS * 32, 0, stream>>>(e, nullptr, nullptr, pk.einv, mean, nullptr, batch, heads, n_tokens, ld, ldr);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
+}
+int head_mean_packed(const PackedP& pk, float* mean, int batch, int heads, int n_tokens, int ld, cudaStream_t stream) {
+    return head_mean_packed_launch(pk, mean, nullptr, batch, heads, n_tokens, ld, stream);
+}
+int head_mean_packed_operand(const PackedP& pk, void* operand, int batch, int heads, int n_tokens, int ld, cudaStream_t stream) {
+    return head_mean_packed_launch(pk, nullptr, operand, batch, heads, n_tokens, ld, stream);
 }
 
 // scratch layout of attention_mean: E | mtab | mfin | einv, every segment 256-byte aligned
@@ -551,7 +582,12 @@ size_t attention_mean_scratch_bytes(int batch, int n_tokens, int heads) {
 
 int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
                    int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse) {
-    VTC_REQUIRE(qkv && out && attn_mean && scratch, VTC_ERR_ARG, "attention_mean: null pointer");
+    return attention_mean_operand(qkv, key_bias, out, cls_rows, attn_mean, nullptr, scratch, scratch_bytes, batch, n_tokens, heads, scale, stream, reverse);
+}
+
+int attention_mean_operand(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* operand, void* scratch,
+                           size_t scratch_bytes, int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse) {
+    VTC_REQUIRE(qkv && out && (attn_mean || operand) && scratch, VTC_ERR_ARG, "attention_mean: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention_mean: bad shape");
     VTC_REQUIRE(n_tokens <= kAttentionFusedMeanMaxTokens, VTC_ERR_SHAPE, "attention_mean: %d tokens > %d", n_tokens, kAttentionFusedMeanMaxTokens);
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, VTC_ERR_WORKSPACE, "attention_mean: scratch must be 256-byte aligned");
@@ -560,7 +596,9 @@ int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls
     VTC_REQUIRE(scratch_bytes >= need, VTC_ERR_WORKSPACE, "attention_mean: scratch %zu bytes < required %zu", scratch_bytes, need);
     int rc = attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, &pk);
     if (rc != VTC_OK) return rc;
-    return head_mean_packed(pk, attn_mean, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream);
+    if (attn_mean && (rc = head_mean_packed(pk, attn_mean, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream)) != VTC_OK) return rc;
+    if (operand && (rc = head_mean_packed_operand(pk, operand, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream)) != VTC_OK) return rc;
+    return VTC_OK;
 }
 
 }  // namespace vtc
@@ -579,6 +617,11 @@ int vtc_attention_mean(const void* qkv, const float* key_bias, void* out, float*
                        int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream) {
     return vtc::attention_mean(qkv, key_bias, out, cls_rows, attn_mean, scratch, scratch_bytes, batch, n_tokens, heads, scale,
                                static_cast<cudaStream_t>(stream), 0);
+}
+int vtc_attention_mean_operand(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* operand, void* scratch,
+                               size_t scratch_bytes, int32_t batch, int32_t n_tokens, int32_t heads, float scale, void* stream) {
+    return vtc::attention_mean_operand(qkv, key_bias, out, cls_rows, attn_mean, operand, scratch, scratch_bytes, batch, n_tokens, heads, scale,
+                                       static_cast<cudaStream_t>(stream), 0);
 }
 int vtc_head_mean(const float* attn, float* mean, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
     return vtc::head_mean(attn, mean, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));

@@ -196,6 +196,12 @@ __device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- TMA ---------------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared (no descriptor): src / dst 16-byte aligned, bytes a multiple of 16; completes on `bar`
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

@@ -34,6 +34,7 @@ struct vtc_model {
 namespace vtc {
 
 static size_t seg(size_t elems, size_t elem_bytes) { return align_up(elems * elem_bytes, 256); }
+constexpr int kRolloutLayers = 12;      // the reference keeps the last 12 layers' attention (vit_model.py:322); predict.py rolls those out
 
 // VTC_LN_FUSION=1 (bf16 mode only) runs the forward without LayerNorm kernels: LayerNorm folded into the GEMMs either side
 // of it (gemm.cu).  Measured on B200 at B = 256: 2 % faster over a 10-step burst (10.21 vs 10.44 ms), no gain once the run
@@ -60,9 +61,10 @@ static bool fused_mean_ok(const vtc_model* m) {
 
 struct Workspace {
     __nv_bfloat16 *hbuf, *patches, *y, *qkv, *ao;
-    float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp, *stats;
+    float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp, *stats, *mean_tmp;
     void* mean_scratch;          // packed P of attention_mean
     size_t mean_scratch_bytes;
+    __nv_bfloat16* rollops;      // rollout operands of the last min(L,12) layers [Lr,B,N,ldr] (ops.h)
     size_t bytes;
 };
 
@@ -88,10 +90,17 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     ws.key_bias = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N, 4));
     ws.gmax = reinterpret_cast<float*>(take(m->L, 4));
     ws.stats = reinterpret_cast<float*>(take(M * (D / 128) * 2, 4));       // LayerNorm row statistics (bf16 mode)
-    const bool need_mean = o && o->attn_mean && !(o->attn && o->attn_layers >= m->L);       // some layer's mean is not a by-product of its full P
+    const bool want_mean = o && (o->attn_mean || o->rollout);
+    const bool need_mean = want_mean && !(o->attn && o->attn_layers >= m->L);       // some layer's mean is not a by-product of its full P
     ws.attn_tmp = (need_mean && !fused_mean_ok(m)) ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N * N, 4)) : nullptr;
     ws.mean_scratch_bytes = (need_mean && fused_mean_ok(m)) ? attention_mean_scratch_bytes(B, m->N, m->H) : 0;
     ws.mean_scratch = ws.mean_scratch_bytes ? take(ws.mean_scratch_bytes, 1) : nullptr;
+    // rollout output: operands of the layers the reference's rollout sees (the last 12, vit_model.py:322), and an fp32 [B,N,N]
+    // staging matrix for layers whose head mean comes from a full fp32 P while attn_mean itself is not an output
+    const int Lr = m->L < kRolloutLayers ? m->L : kRolloutLayers;
+    ws.rollops = (o && o->rollout) ? reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(Lr) * B * N * rollout_operand_ld(m->N), 2)) : nullptr;
+    ws.mean_tmp = (o && o->rollout && !o->attn_mean && (!fused_mean_ok(m) || (o->attn && o->attn_layers > 0)))
+                      ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * N, 4)) : nullptr;
     ws.bytes = off;
     return ws;
 }
@@ -150,6 +159,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     const int N = m->N, D = m->D, H = m->H, L = m->L, P = m->P, HID = m->HID;
     const int M = B * N;
     const size_t tok_elems = static_cast<size_t>(M) * D;
+    const int Lr = L < kRolloutLayers ? L : kRolloutLayers;
     const int Lt = o->tokens ? o->tokens_layers : 0;
     const int La = o->attn ? o->attn_layers : 0;
     VTC_REQUIRE(Lt >= 0 && Lt <= L && La >= 0 && La <= L, VTC_ERR_ARG, "forward: tokens_layers / attn_layers out of range");
@@ -192,16 +202,18 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
         const bool want_map = (l >= m->cfg.mask_from) || (l == L - 1) || (o->cls_map != nullptr);
         float* cls_l = o->cls_rows ? o->cls_rows + static_cast<size_t>(l) * B * H * N : (want_map ? ws.cls_rows : nullptr);
         float* attn_l = nullptr;
-        float* mean_l = nullptr;          // head mean via the packed P (short sequences, bf16 mode)
+        float* mean_l = o->attn_mean ? o->attn_mean + static_cast<size_t>(l) * B * N * N : nullptr;
+        __nv_bfloat16* op_l = (o->rollout && l >= L - Lr) ? ws.rollops + static_cast<size_t>(l - (L - Lr)) * B * N * rollout_operand_ld(N) : nullptr;
+        bool packed_mean = false;         // head mean / rollout operand via the packed P of the fast attention kernel (bf16 mode)
         if (o->attn && l >= L - La) attn_l = o->attn + static_cast<size_t>(l - (L - La)) * B * H * N * N;
-        else if (o->attn_mean && fused_mean) mean_l = o->attn_mean + static_cast<size_t>(l) * B * N * N;
-        else if (o->attn_mean) attn_l = ws.attn_tmp;
+        else if ((mean_l || op_l) && fused_mean) packed_mean = true;
+        else if (mean_l || op_l) attn_l = ws.attn_tmp;
 
         if (ln_fused) {
             // LayerNorm lives inside the GEMMs: ws.y = bf16(residual stream), ws.stats = its row statistics (gemm.cu)
             VTC_STEP(VTC_PROF_GEMM_QKV, gemm_lnfold(ws.y, pw.qkv, pw.qkv_c, pw.qkv_g, ws.stats, m->cfg.ln_eps, ws.qkv, M, 3 * D, D, 0, st, next_dir()));
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                   // vit_model.py:118
-            if (mean_l) VTC_STEP(VTC_PROF_ATTENTION, attention_mean(ws.qkv, kb, ws.ao, cls_l, mean_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
+            if (packed_mean) VTC_STEP(VTC_PROF_ATTENTION, attention_mean_operand(ws.qkv, kb, ws.ao, cls_l, mean_l, op_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
             else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
             if (fuse_proj) {
                 VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_resid_ln(ws.ao, pw.proj, w.proj_b, t_in, t_out, ws.y, ws.stats, M, D, D, st, next_dir()));
@@ -217,7 +229,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
             if (m->HD != 64) VTC_STEP(VTC_PROF_ATTENTION, attention_generic(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, m->HD, scale, st));
             else if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
-            else if (mean_l) VTC_STEP(VTC_PROF_ATTENTION, attention_mean(ws.qkv, kb, ws.ao, cls_l, mean_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
+            else if (packed_mean) VTC_STEP(VTC_PROF_ATTENTION, attention_mean_operand(ws.qkv, kb, ws.ao, cls_l, mean_l, op_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
             else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
             VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
             VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
@@ -226,7 +238,11 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
         }
         t_cur = t_out;
 
-        if (o->attn_mean && mean_l == nullptr) VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, o->attn_mean + static_cast<size_t>(l) * B * N * N, B, H, N, st));
+        if ((mean_l || op_l) && !packed_mean) {          // head mean from the full fp32 P of this layer
+            float* mdst = mean_l ? mean_l : ws.mean_tmp;
+            VTC_STEP(VTC_PROF_HEAD_MEAN, head_mean(attn_l, mdst, B, H, N, st));
+            if (op_l) VTC_STEP(VTC_PROF_HEAD_MEAN, rollout_operand_from_mean(mdst, op_l, B, N, st));
+        }
         if (want_map) {
             float* map_l = o->cls_map ? o->cls_map + static_cast<size_t>(l) * B * P : ws.cls_map;
             VTC_STEP(VTC_PROF_CLS, cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st));
@@ -241,6 +257,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     }
     HeadParams hp{m->w.norm_w, m->w.norm_b, m->w.pre_w, m->w.pre_b, m->w.head_w, m->w.head_b, m->w.head1_w, m->w.head1_b,
                   D, m->R, m->C, m->cfg.topk, N, m->cfg.ln_eps};
+    if (o->rollout) VTC_STEP(VTC_PROF_ROLLOUT, rollout_operand(ws.rollops, o->rollout, Lr, B, N, st));      // predict.py:215-232
     VTC_STEP(VTC_PROF_HEADS, topk_heads(hp, t_cur, last_map, per_image ? nullptr : ws.gmax + (L - 1), f ? f->topk_idx : nullptr, o->logits, o->hwp_logits, o->hwp_tokens, o->topk_idx, B, st));
     return VTC_OK;
 }

@@ -55,6 +55,19 @@ size_t attention_mean_scratch_bytes(int batch, int n_tokens, int heads);
 int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
                    int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse = 0);
 int head_mean_packed(const PackedP& packed, float* mean, int batch, int heads, int n_tokens, int ld, cudaStream_t stream);
+// "Rollout operand": the head mean of one layer as the rollout kernel streams it (bf16, half the bytes of the
+// fp32 [B,N,N] matrix): bf16 [B,N,ldr], ldr = rollout_operand_ld(N); a row holds N values, zero padding, and in its last
+// four bytes the fp32 sum of the N ROUNDED values (so that (Pbar + I) / rowsum is normalised exactly as stored).
+inline int rollout_operand_ld(int n_tokens) { return (n_tokens + 2 + 7) / 8 * 8; }
+int head_mean_packed_operand(const PackedP& packed, void* operand, int batch, int heads, int n_tokens, int ld, cudaStream_t stream);
+// attention_mean writing the rollout operand instead of (mean == nullptr) or next to the fp32 mean
+int attention_mean_operand(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* operand, void* scratch,
+                           size_t scratch_bytes, int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse = 0);
+// fp32 [B,N,N] head mean -> rollout operand (the path of the full-P / fp32-mode / general-shape forwards)
+int rollout_operand_from_mean(const float* mean, void* operand, int batch, int n_tokens, cudaStream_t stream);
+// r <- e0^T A_{L-1} ... A_0 from `layers` rollout operands [layers,B,N,ldr]; row [B,N-1]
+int rollout_operand(const void* operands, float* row, int layers, int batch, int n_tokens, cudaStream_t stream);
+int rollout(const float* attn_mean, float* row, int layers, int batch, int n_tokens, cudaStream_t stream);
 // KV-blocked kernel (attention_kv.cu): any n_tokens <= 2048; split = (hi, lo) bf16 operands: qkv [B,N,2,3,H,64], out [B*N,2,H*64]
 int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
                  float scale, bool split, cudaStream_t stream, int reverse = 0);

@@ -64,6 +64,172 @@ int rollout(const float* attn_mean, float* row, int layers, int batch, int n_tok
     return VTC_OK;
 }
 
+// ---- attention rollout, streaming version ------------------------------------------------------------------------
+// Same chain on the bf16 "rollout operands" (ops.h: row = N values | zero padding | fp32 row sum), the layout the forward
+// keeps for the rollout: half the bytes of fp32 [B,N,N] matrices and 16-byte aligned rows, so a block of rows is ONE bulk
+// copy (cp.async.bulk, no descriptor) into shared memory.  One CTA per image walks layers L-1 .. 0 and, inside a layer, row
+// blocks of <= 32 KB through a 3-stage ring: while block t is folded into the running vector (thread = column pair x row
+// parity, packed fp32x2 FMAs, conflict-free 4-byte shared loads), blocks t+1 and t+2 are in flight -- 64 KB per CTA, two
+// CTAs per SM, more than the ~45 KB per SM that the HBM latency-bandwidth product asks for.  Only the CLS row of the last
+// layer is read (the chain starts from e0).  Algorithmic bytes: (L-1) N ldr 2 + ldr 2 per image (0.87 MB at N = 197, L = 12).
+namespace rollop {
+constexpr int THREADS = 256;
+constexpr int STAGES = 3;
+constexpr int STAGE_BYTES = 32 * 1024;
+constexpr int MAX_PAIRS = 8;        // column pairs per thread: N <= 2048
+}  // namespace rollop
+
+__global__ void __launch_bounds__(rollop::THREADS, 2)
+rollout_operand_kernel(const __nv_bfloat16* __restrict__ ops, float* __restrict__ out, int L, int B, int N, int ldr, int rows_per_block,
+                       int blocks_per_layer) {
+    using namespace rollop;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* stage = smem_raw;                                                    // [STAGES][STAGE_BYTES]
+    float* r = reinterpret_cast<float*>(smem_raw + STAGES * STAGE_BYTES);         // [ldr]  running vector
+    float* part = r + ldr;                                                        // [ldr]  odd-row partial sums of a layer
+    float* w = part + ldr;                                                        // [rows_per_block] weights of the block in hand
+    uint64_t* bar = reinterpret_cast<uint64_t*>(w + ((rows_per_block + 1) & ~1));
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int pairs = ldr >> 1;
+    const int pcol = tid & 127, par = tid >> 7;            // my column pairs: pcol + 128 k; my rows of a block: par, par + 2, ...
+    const int T = 1 + (L - 1) * blocks_per_layer;          // block 0 = the CLS row of layer L-1, then whole layers L-2 .. 0
+
+    auto block_of = [&](int t, int& l, int& row0, int& nrows) {
+        if (t == 0) { l = L - 1; row0 = 0; nrows = 1; return; }
+        const int u = t - 1;
+        l = L - 2 - u / blocks_per_layer;
+        row0 = (u % blocks_per_layer) * rows_per_block;
+        nrows = min(rows_per_block, N - row0);
+    };
+    auto issue = [&](int t) {                               // one thread
+        int l, row0, nrows;
+        block_of(t, l, row0, nrows);
+        const uint32_t bytes = static_cast<uint32_t>(nrows) * ldr * 2;
+        const __nv_bfloat16* src = ops + ((static_cast<size_t>(l) * B + b) * N + row0) * ldr;
+        mbar_arrive_expect_tx(&bar[t % STAGES], bytes);
+        bulk_load_1d(stage + (t % STAGES) * STAGE_BYTES, src, bytes, &bar[t % STAGES]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        fence_barrier_init();
+        for (int t = 0; t < STAGES && t < T; ++t) issue(t);
+    }
+    for (int j = tid; j < ldr; j += THREADS) r[j] = (j == 0) ? 1.0f : 0.0f;
+    uint64_t acc[MAX_PAIRS];
+#pragma unroll
+    for (int k = 0; k < MAX_PAIRS; ++k) acc[k] = 0ull;
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        int l, row0, nrows;
+        block_of(t, l, row0, nrows);
+        const uint8_t* data = stage + (t % STAGES) * STAGE_BYTES;
+        mbar_wait(&bar[t % STAGES], (t / STAGES) & 1);
+        // weights of the block's rows: w_i = r_i / rowsum(Pbar_i + I), the row sum rides in the row's last four bytes
+        for (int i = tid; i < nrows; i += THREADS)
+            w[i] = r[row0 + i] / (*reinterpret_cast<const float*>(data + (static_cast<size_t>(i) * ldr + ldr - 2) * 2) + 1.0f);
+        __syncthreads();
+        const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
+#pragma unroll
+        for (int k = 0; k < MAX_PAIRS; ++k) {
+            const int p = pcol + 128 * k;
+            if (p < pairs) {
+                uint64_t a = acc[k];
+                for (int i = par; i < nrows; i += 2) {
+                    const uint32_t v = d32[i * pairs + p];
+                    const float wi = w[i];
+                    a = fma2(pack2(wi, wi), pack2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)), a);
+                }
+                if (par == 0) {      // the identity of Pbar + I: column j receives w_j when row j is in this block
+                    const int i0 = 2 * p - row0, i1 = 2 * p + 1 - row0;
+                    a = add2(a, pack2((i0 >= 0 && i0 < nrows) ? w[i0] : 0.f, (i1 >= 0 && i1 < nrows) ? w[i1] : 0.f));
+                }
+                acc[k] = a;
+            }
+        }
+        __syncthreads();                                     // the stage and w[] are free again
+        if (tid == 0 && t + STAGES < T) issue(t + STAGES);
+        const bool layer_done = (t == 0) || ((t - 1) % blocks_per_layer == blocks_per_layer - 1);
+        if (layer_done) {
+            // r_new = even-row sums + odd-row sums
+            if (par == 1) {
+#pragma unroll
+                for (int k = 0; k < MAX_PAIRS; ++k) {
+                    const int p = pcol + 128 * k;
+                    if (p < pairs) { float lo, hi; unpack2(acc[k], lo, hi); part[2 * p] = lo; part[2 * p + 1] = hi; acc[k] = 0ull; }
+                }
+            }
+            __syncthreads();
+            if (par == 0) {          // every read of the old r (the w[] of this layer's blocks) is behind the barriers above
+#pragma unroll
+                for (int k = 0; k < MAX_PAIRS; ++k) {
+                    const int p = pcol + 128 * k;
+                    if (p < pairs) {
+                        float lo, hi;
+                        unpack2(acc[k], lo, hi);
+                        acc[k] = 0ull;
+                        r[2 * p] = (2 * p < N) ? lo + part[2 * p] : 0.f;
+                        r[2 * p + 1] = (2 * p + 1 < N) ? hi + part[2 * p + 1] : 0.f;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid + 1; j < N; j += THREADS) out[static_cast<size_t>(b) * (N - 1) + j - 1] = r[j];
+}
+
+int rollout_operand(const void* operands, float* row, int layers, int batch, int n_tokens, cudaStream_t stream) {
+    using namespace rollop;
+    VTC_REQUIRE(operands && row, VTC_ERR_ARG, "rollout_operand: null pointer");
+    VTC_REQUIRE(layers > 0 && batch > 0 && n_tokens > 1 && n_tokens <= 2 * 128 * MAX_PAIRS - 2, VTC_ERR_SHAPE, "rollout_operand: bad shape");
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(operands) & 15) == 0, VTC_ERR_ARG, "rollout_operand: operands must be 16-byte aligned");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int ldr = rollout_operand_ld(n_tokens);
+    const int max_rows = STAGE_BYTES / (ldr * 2);
+    const int blocks_per_layer = cdiv(n_tokens, max_rows);
+    const int rows_per_block = cdiv(n_tokens, blocks_per_layer);
+    const size_t smem = static_cast<size_t>(STAGES) * STAGE_BYTES + sizeof(float) * (2 * ldr + ((rows_per_block + 1) & ~1)) + 8 * STAGES;
+    static SmemOptIn optin;
+    if ((rc = optin.ensure(reinterpret_cast<const void*>(rollout_operand_kernel), smem)) != VTC_OK) return rc;
+    rollout_operand_kernel<<<batch, THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(operands), row, layers, batch, n_tokens, ldr,
+                                                             rows_per_block, blocks_per_layer);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
+// fp32 [B,N,N] head mean -> rollout operand: warp per row (the forwards whose head mean comes from a full fp32 P)
+__global__ void rollout_operand_from_mean_kernel(const float* __restrict__ mean, __nv_bfloat16* __restrict__ op, int rows, int N, int ldr) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int rid = warp; rid < rows; rid += nwarps) {
+        const float* src = mean + static_cast<size_t>(rid) * N;
+        __nv_bfloat16* dst = op + static_cast<size_t>(rid) * ldr;
+        float s = 0.f;
+        for (int j = lane; j < ldr - 2; j += 32) {
+            const float v = j < N ? bf16_round(src[j]) : 0.f;
+            s += v;
+            dst[j] = __float2bfloat16_rn(v);
+        }
+        s = warp_sum(s);
+        if (lane == 0) *reinterpret_cast<float*>(dst + ldr - 2) = s;
+    }
+}
+
+int rollout_operand_from_mean(const float* mean, void* operand, int batch, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(mean && operand, VTC_ERR_ARG, "rollout_operand_from_mean: null pointer");
+    VTC_REQUIRE(batch > 0 && n_tokens > 1, VTC_ERR_SHAPE, "rollout_operand_from_mean: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    const int rows = batch * n_tokens;
+    rollout_operand_from_mean_kernel<<<grid_cap(cdiv(rows, 8), 8), 256, 0, stream>>>(mean, static_cast<__nv_bfloat16*>(operand), rows, n_tokens,
+                                                                                     rollout_operand_ld(n_tokens));
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 // ---- CLS-row maps (per-layer maps predict.py:261-266; layers-6..12 bg map validate.py:225-237) -----------------
 __global__ void cls_layer_map_kernel(const float* __restrict__ cls_rows, float* __restrict__ map, int first, int last, int B, int H, int N) {
     extern __shared__ float rowv[];      // [N]
@@ -615,6 +781,13 @@ int vtc_patch_similarity(const float* tokens, float* scratch, float* sim, int32_
 }
 int vtc_rollout(const float* attn_mean, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream) {
     return vtc::rollout(attn_mean, row, layers, batch, n_tokens, static_cast<cudaStream_t>(stream));
+}
+int32_t vtc_rollout_operand_ld(int32_t n_tokens) { return vtc::rollout_operand_ld(n_tokens); }
+int vtc_rollout_operand_from_mean(const float* attn_mean, void* operand, int32_t batch, int32_t n_tokens, void* stream) {
+    return vtc::rollout_operand_from_mean(attn_mean, operand, batch, n_tokens, static_cast<cudaStream_t>(stream));
+}
+int vtc_rollout_operands(const void* operands, float* row, int32_t layers, int32_t batch, int32_t n_tokens, void* stream) {
+    return vtc::rollout_operand(operands, row, layers, batch, n_tokens, static_cast<cudaStream_t>(stream));
 }
 int vtc_cls_layer_map(const float* cls_rows, float* map, int32_t layers, int32_t first, int32_t last, int32_t batch, int32_t heads,
                       int32_t n_tokens, void* stream) {

@@ -216,6 +216,41 @@ def rollout(attn_mean: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rollout_operand_ld(n_tokens: int) -> int:
+    return int(_lib.load().vtc_rollout_operand_ld(n_tokens))
+
+
+def rollout_operand_from_mean(attn_mean: torch.Tensor) -> torch.Tensor:
+    """fp32 head means [..., B, N, N] -> bf16 rollout operands [..., B, N, ldr] (row = N values | zero padding | fp32 row sum)."""
+    N = attn_mean.shape[-1]
+    rows = attn_mean.numel() // (N * N)
+    out = torch.empty(attn_mean.shape[:-1] + (rollout_operand_ld(N),), dtype=torch.bfloat16, device=attn_mean.device)
+    _call("vtc_rollout_operand_from_mean", _ptr(attn_mean, torch.float32, "attn_mean"), _ptr(out), rows, N)
+    return out
+
+
+def rollout_operands(operands: torch.Tensor, n_tokens: int) -> torch.Tensor:
+    """bf16 rollout operands [L,B,N,ldr] -> un-normalised rollout row [B,N-1] (the streaming kernel of the fused forward)."""
+    L, B, N, ldr = operands.shape
+    assert N == n_tokens and ldr == rollout_operand_ld(N)
+    out = torch.empty((B, N - 1), dtype=torch.float32, device=operands.device)
+    _call("vtc_rollout_operands", _ptr(operands, torch.bfloat16, "operands"), _ptr(out), L, B, N)
+    return out
+
+
+def attention_mean_operand(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Attention that leaves the head mean of P as a bf16 rollout operand: (out, cls_rows, operand [B,N,ldr])."""
+    B, N, D3 = qkv.shape
+    out = torch.empty((B, N, D3 // 3), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device)
+    op = torch.empty((B, N, rollout_operand_ld(N)), dtype=torch.bfloat16, device=qkv.device)
+    nbytes = int(_lib.load().vtc_attention_mean_scratch_bytes(B, N, heads))
+    scratch = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
+    _call("vtc_attention_mean_operand", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(out), _ptr(cls), None,
+          _ptr(op), _ptr(scratch), nbytes, B, N, heads, scale)
+    return out, cls, op
+
+
 def cls_layer_map(cls_rows: torch.Tensor, first: int, last: int) -> torch.Tensor:
     L, B, H, N = cls_rows.shape
     out = torch.empty((B, N - 1), dtype=torch.float32, device=cls_rows.device)

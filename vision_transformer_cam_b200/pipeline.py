@@ -95,8 +95,8 @@ class Prediction:
 def predict(model: VisionTransformer, x: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> Prediction:
     """predict.py:129-293 for a batch of normalised images (the reference runs batch 1)."""
     out_hw = out_hw or (x.shape[-2], x.shape[-1])
-    o = model.forward_cam(x, attn_mean=True)
-    return Prediction(logits=o.logits, hwp_scores=torch.sigmoid(o.hwp_logits), rollout=CAM.rollout_map(o.attn_mean, out_hw),
+    o = model.forward_cam(x, rollout=True)
+    return Prediction(logits=o.logits, hwp_scores=torch.sigmoid(o.hwp_logits), rollout=CAM.rollout_map(o.rollout, out_hw),
                       layer_maps=CAM.layer_maps(o.cls_rows, out_hw, as_u8=True),
                       cam=CAM.classic_cam(o.tokens_last, model.head1.weight.data))
 
@@ -150,11 +150,11 @@ def extract_cams_sharded(model: VisionTransformer, get_images: Callable[[int, in
     cams, rolls, hwps = [], [], []
     device = next(model.parameters()).device
     for x in DeviceFeeder(device).stream(get_images(b0, b1) for b0, b1 in D.batches(lo, hi, batch)):
-        o = model.forward_cam(x, attn_mean=with_rollout)
+        o = model.forward_cam(x, rollout=with_rollout)
         cams.append(CAM.classic_cam(o.tokens_last, model.head1.weight.data))
         hwps.append(o.hwp_logits)
         if with_rollout:
-            rolls.append(CAM.rollout_row(o.attn_mean))
+            rolls.append(o.rollout)
     out = {"cam": torch.cat(cams), "hwp_logits": torch.cat(hwps)}
     if with_rollout:
         out["rollout"] = torch.cat(rolls)

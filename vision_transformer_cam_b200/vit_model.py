@@ -194,6 +194,7 @@ class CamForward:
     attn_mean: Optional[torch.Tensor] = None  # [L,B,N,N]
     bg: Optional[torch.Tensor] = None         # [L,B,P] uint8
     cls_map: Optional[torch.Tensor] = None    # [L,B,P]
+    rollout: Optional[torch.Tensor] = None    # [B,P] un-normalised attention-rollout row over the last min(L,12) layers
 
     @property
     def tokens_last(self) -> torch.Tensor:
@@ -290,7 +291,7 @@ class _Engine:
 
     def run(self, model: "VisionTransformer", x: torch.Tensor, tokens_layers: int, attn_layers: int, attn_mean: bool, bg: bool,
             cls_map: bool, mask_norm: str, forced_bg: Optional[Dict[int, torch.Tensor]], forced_topk: Optional[torch.Tensor],
-            norm: Optional[Tuple[Tuple[float, float, float], Tuple[float, float, float]]] = None) -> CamForward:
+            norm: Optional[Tuple[Tuple[float, float, float], Tuple[float, float, float]]] = None, rollout: bool = False) -> CamForward:
         dev = x.device
         cfg = self.cfg
         B = x.shape[0]
@@ -311,11 +312,14 @@ class _Engine:
                 out.bg = torch.empty((L, B, P), dtype=torch.uint8, device=dev)
             if cls_map:
                 out.cls_map = torch.empty((L, B, P), **f32)
+            if rollout:
+                out.rollout = torch.empty((B, P), **f32)
             o = _lib.Outputs(logits=out.logits.data_ptr(), hwp_logits=out.hwp_logits.data_ptr(), hwp_tokens=out.hwp_tokens.data_ptr(),
                              topk_idx=out.topk_idx.data_ptr(), tokens=out.tokens.data_ptr(), tokens_layers=tokens_layers,
                              cls_rows=out.cls_rows.data_ptr(), attn=out.attn.data_ptr() if out.attn is not None else None,
                              attn_layers=attn_layers, attn_mean=out.attn_mean.data_ptr() if attn_mean else None,
-                             bg=out.bg.data_ptr() if bg else None, cls_map=out.cls_map.data_ptr() if cls_map else None)
+                             bg=out.bg.data_ptr() if bg else None, cls_map=out.cls_map.data_ptr() if cls_map else None,
+                             rollout=out.rollout.data_ptr() if rollout else None)
             forcing = None
             keep = []
             if forced_bg or forced_topk is not None:
@@ -445,13 +449,16 @@ class VisionTransformer(nn.Module):
     @torch.no_grad()
     def forward_cam(self, x: torch.Tensor, tokens_layers: int = 1, attn_layers: int = 0, attn_mean: bool = False,
                     bg: bool = False, cls_map: bool = False, mask_norm: str = "batch",
-                    forced_bg: Optional[Dict[int, torch.Tensor]] = None, forced_topk: Optional[torch.Tensor] = None) -> CamForward:
-        """Fused forward with compact outputs (no [B,H,N,N] tensors unless `attn_layers` > 0)."""
+                    forced_bg: Optional[Dict[int, torch.Tensor]] = None, forced_topk: Optional[torch.Tensor] = None,
+                    rollout: bool = False) -> CamForward:
+        """Fused forward with compact outputs (no [B,H,N,N] tensors unless `attn_layers` > 0).  `rollout=True` also returns the
+        attention-rollout row of predict.py:215-232 ([B,P], un-normalised) computed inside the call: the head means never
+        leave the workspace (bf16 rollout operands, half the bytes of `attn_mean`)."""
         assert mask_norm in ("batch", "image")
         x = self._check_input(x)
         if self._engine is None:
             self._engine = _Engine(self)
-        return self._engine.run(self, x, tokens_layers, attn_layers, attn_mean, bg, cls_map, mask_norm, forced_bg, forced_topk)
+        return self._engine.run(self, x, tokens_layers, attn_layers, attn_mean, bg, cls_map, mask_norm, forced_bg, forced_topk, rollout=rollout)
 
     @torch.no_grad()
     def forward_cam_u8(self, x: torch.Tensor, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), **kw) -> CamForward:
@@ -469,7 +476,7 @@ class VisionTransformer(nn.Module):
             self._engine = _Engine(self)
         return self._engine.run(self, x.detach().contiguous(), kw.pop("tokens_layers"), kw.pop("attn_layers", 0), kw.pop("attn_mean", False),
                                 kw.pop("bg", False), kw.pop("cls_map", False), kw.pop("mask_norm", "batch"), kw.pop("forced_bg", None),
-                                kw.pop("forced_topk", None), norm=(tuple(mean), tuple(std)))
+                                kw.pop("forced_topk", None), norm=(tuple(mean), tuple(std)), rollout=kw.pop("rollout", False))
 
     @torch.no_grad()
     def forward_cam_graphed(self, x: torch.Tensor, **kw) -> CamForward:
