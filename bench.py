@@ -387,8 +387,7 @@ def main():
     model = V.vit_base_patch16_224_in21k(num_classes=C, has_logits=False).to(dev).eval()
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_dev = torch.randn((B, 3, IMG, IMG), generator=g, device=dev)
-    GATHER_EVERY = 8       # steps per collective (dist.SideStreamGather): every CAM is gathered inside the timed region
-    gathered = torch.empty((world, GATHER_EVERY, B, C, 14, 14), device=dev) if world > 1 else None
+    GATHER_EVERY = 8       # steps per gather: every CAM is gathered inside the timed region
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
 
     def local_step(x):
@@ -396,8 +395,28 @@ def main():
         cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)
         return o, cam
 
+    # The CAM gather: peer-to-peer pushes by the copy engines into symmetric memory (dist.PeerPushGather: no SM is taken from
+    # the persistent kernels of the forward); VTC_BENCH_GATHER=nccl selects the NCCL all-gather on a side stream instead
+    # (also the fallback when symmetric memory cannot be set up on the box).
     from vision_transformer_cam_b200 import dist as VD
-    gatherer = VD.SideStreamGather(dev, every=GATHER_EVERY) if world > 1 else None
+    gatherer = gathered = None
+    gather_kind = "none (1 GPU)"
+    if world > 1:
+        want = os.environ.get("VTC_BENCH_GATHER", "push")
+        if want == "push":
+            try:
+                gatherer = VD.PeerPushGather(dev, every=GATHER_EVERY)
+                gathered = gatherer.alloc((world, GATHER_EVERY, B, C, 14, 14))
+                gather_kind = ("CAM maps pushed into every peer's symmetric-memory buffer by device-to-device copies (copy engines over NVLink, "
+                               "side stream) once per 8 steps + at the end")
+            except Exception as e:      # noqa: BLE001
+                print(f"bench: symmetric-memory gather unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+                gatherer = None
+        if gatherer is None:
+            gatherer = VD.SideStreamGather(dev, every=GATHER_EVERY)
+            gathered = torch.empty((world, GATHER_EVERY, B, C, 14, 14), device=dev)
+            gather_kind = "CAM maps all-gathered (NCCL) once per 8 steps on a side stream + at the end"
+        config["collectives"] = gather_kind + "; int64 counters all-reduced (NCCL) at the end; all inside the timed region, none inside the forward"
 
     def step(x):
         o, cam = local_step(x)
@@ -513,7 +532,15 @@ def main():
         del r
         if not args.no_extras:
             eager = gpu_eager_block(sd_ref, dev, B, ms / K)
-    del x_dev, gathered
+    if world > 1:       # the last gathered block really holds every rank's CAMs (checked outside the timed region)
+        torch.cuda.synchronize()
+        dist.barrier()
+        mine = gathered.view(world, -1)[rank].abs().sum()
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        seen = [float(gathered.view(world, -1)[r].abs().sum()) for r in range(world)]
+        assert all(abs(seen[r] - float(sums[r])) <= 1e-3 * max(1.0, abs(seen[r])) for r in range(world)), (seen, [float(v) for v in sums])
+    del x_dev, gathered, gatherer
     torch.cuda.empty_cache()
     configs = None if args.no_extras else other_configs(dev, rank, world, peaks())
 

@@ -1,4 +1,5 @@
-"""2 GPUs (gpurun --gpus 2): the sharded CAM extraction over NCCL equals the single-rank run."""
+"""2 .. 8 GPUs (gpurun --gpus N): the sharded CAM extraction over NCCL equals the single-rank run; the side-stream NCCL gather
+and the copy-engine peer-push gather deliver every rank's blocks."""
 import os
 import subprocess
 import sys
@@ -28,10 +29,10 @@ assert out["cam"].shape[0] == n and out["rollout"].shape == (n, 196)
 if rank == 0:
     # the same per-image calls on one rank (same outputs requested => same kernels => same bits)
     from vision_transformer_cam_b200 import cam as CAM
-    fwd = [model.forward_cam(get(i, i + 1), attn_mean=True) for i in range(n)]
+    fwd = [model.forward_cam(get(i, i + 1), rollout=True) for i in range(n)]
     ref = torch.cat([CAM.classic_cam(o.tokens_last, model.head1.weight.data) for o in fwd])
     assert torch.equal(ref, out["cam"]), float((ref - out["cam"]).abs().max())
-    assert torch.equal(torch.cat([CAM.rollout_row(o.attn_mean) for o in fwd]), out["rollout"])
+    assert torch.equal(torch.cat([o.rollout for o in fwd]), out["rollout"])
 # side-stream gather: same result as the in-stream collective, for several steps in flight
 g = D.SideStreamGather(dev)
 outs = [torch.empty((world * 3, 5), device=dev) for _ in range(4)]
@@ -62,6 +63,30 @@ for blk in range(2):
 tail = out3.view(-1)[: world * 15].view(world, 1, 3, 5).cpu()
 for r in range(world):
     assert torch.equal(tail[r, 0], torch.full((3, 5), float(600 + r)))
+# copy-engine peer push into symmetric memory: 2 steps per push, 5 steps => two pushes + a flush of one step
+pg = D.PeerPushGather(dev, every=2)
+outp = pg.alloc((world, 2, 3, 5))
+seenp = []
+for k in range(5):
+    local = torch.full((3, 5), float(1000 * k + rank), device=dev)
+    pg.gather(outp, local)
+    del local
+    if k % 2 == 1:
+        pg.wait()
+        torch.cuda.synchronize()
+        dist.barrier()                      # every peer's pushes have landed
+        seenp.append(outp.clone().cpu())
+        dist.barrier()                      # nobody overwrites before everybody has read
+pg.wait()
+torch.cuda.synchronize()
+dist.barrier()
+for blk in range(2):
+    for r in range(world):
+        for j in range(2):
+            assert torch.equal(seenp[blk][r, j], torch.full((3, 5), float(1000 * (2 * blk + j) + r))), (blk, r, j)
+tailp = outp.view(world, -1)[:, :15].cpu()
+for r in range(world):
+    assert torch.equal(tailp[r], torch.full((15,), float(4000 + r)))
 c = torch.tensor([rank + 1], dtype=torch.int64, device=dev)
 D.reduce_counters(c)
 assert int(c) == world * (world + 1) // 2
@@ -75,8 +100,9 @@ sys.stdout.write("rank %d ok\n" % rank); sys.stdout.flush()
 def test_nccl_sharded_extraction_equals_single_rank(tmp_path, lib_built):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    nproc = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", "29577", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert all(f"rank {k} ok" in r.stdout for k in range(nproc)), r.stdout[-2000:]

@@ -1,6 +1,6 @@
 """Time vtc_attention of two builds of libvtc on the same box (debug): python tools/ab_attn_lib.py libA.so libB.so"""
-import ctypes, sys, torch
-N, H, B = 197, 12, 256
+import ctypes, os, sys, torch
+N, H, B = (int(v) for v in os.environ.get("VTC_AB_SHAPE", "197,12,256").split(","))
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
 qkv = torch.randn((B, N, 3 * H * 64), generator=g, device=dev).bfloat16()

@@ -98,6 +98,83 @@ int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, 
     return VTC_OK;
 }
 
+// cls_stat + cls_mask in ONE launch (the forward, layers >= mask_from: 8 launches less per ViT-B forward).  Every block runs
+// the cls_stat body for its image, publishes its maximum (atomicMax) and draws a ticket; the batch-global maximum of
+// vit_model.py:335 is complete when all B tickets are drawn, so every block waits for that (all blocks of the grid are
+// co-resident: the host checks B against the occupancy limit and otherwise launches the two kernels) and then thresholds
+// its own image.  `ticket`: one zeroed unsigned int per launch (the forward zeroes one per layer next to gmax).
+__global__ void __launch_bounds__(256) cls_stat_mask_kernel(const float* __restrict__ cls_rows, float* __restrict__ cls_map, float* __restrict__ gmax,
+                                                            const uint8_t* __restrict__ forced, float thresh, int per_image, uint8_t* __restrict__ bg,
+                                                            float* __restrict__ key_bias, unsigned int* __restrict__ ticket, int B, int H, int N) {
+    __shared__ float red[32];
+    __shared__ float mapv[2048];       // this image's map (n_tokens <= 2049, checked by the host)
+    const int b = blockIdx.x;
+    const int P = N - 1;
+    const float* src = cls_rows + static_cast<size_t>(b) * H * N;
+    const float invH = 1.0f / H;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float s = 0.f;
+        for (int h = 0; h < H; ++h) s += src[h * N + j];
+        if (j > 0) mapv[j - 1] = s * invH;
+        part += s * invH;
+    }
+    const float rowsum = block_sum(part, red) + 1.0f;    // + identity on the CLS diagonal (vit_model.py:331-333)
+    float mx = 0.f;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {   // (block_sum synchronised the block: every mapv entry is visible)
+        const float v = mapv[j] / rowsum;
+        mapv[j] = v;
+        cls_map[static_cast<size_t>(b) * P + j] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    if (!per_image) {
+        if (threadIdx.x == 0) {
+            atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));      // values are >= 0
+            __threadfence();
+            atomicAdd(ticket, 1u);
+            while (*reinterpret_cast<volatile unsigned int*>(ticket) < static_cast<unsigned int>(B)) __nanosleep(64);
+            __threadfence();
+            red[0] = *reinterpret_cast<volatile float*>(gmax);
+        }
+        __syncthreads();
+        mx = red[0];
+    } else if (threadIdx.x == 0) {
+        atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));          // topk_heads may still want the batch-global value
+    }
+    if (threadIdx.x == 0) key_bias[static_cast<size_t>(b) * N] = 0.f;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+        const size_t e = static_cast<size_t>(b) * P + j;
+        const uint8_t isbg = forced ? (forced[e] != 0) : ((mapv[j] / mx) < thresh);          // torch.lt(mask_14 / max, 0.25)
+        if (bg != nullptr) bg[e] = isbg;
+        key_bias[static_cast<size_t>(b) * N + 1 + j] = isbg ? -100.0f : 0.0f;
+    }
+}
+
+int cls_stat_mask(const float* cls_rows, float* cls_map, float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
+                  float* key_bias, unsigned int* ticket, int batch, int heads, int n_tokens, cudaStream_t stream) {
+    VTC_REQUIRE(cls_rows && cls_map && gmax && key_bias && ticket, VTC_ERR_ARG, "cls_stat_mask: null pointer");
+    VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 1, VTC_ERR_SHAPE, "cls_stat_mask: bad shape");
+    int rc = check_arch();
+    if (rc != VTC_OK) return rc;
+    // the wait on the ticket needs every block of the grid resident at the same time
+    static std::atomic<int> per_sm[64];
+    int dev = 0;
+    VTC_CUDA(cudaGetDevice(&dev));
+    int bps = (dev >= 0 && dev < 64) ? per_sm[dev].load(std::memory_order_relaxed) : 0;
+    if (bps == 0) {
+        VTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cls_stat_mask_kernel, 256, 0));
+        if (dev >= 0 && dev < 64) per_sm[dev].store(bps, std::memory_order_relaxed);
+    }
+    if (n_tokens - 1 > 2048 || static_cast<long long>(batch) > static_cast<long long>(bps) * device_sm_count()) {
+        if ((rc = cls_stat(cls_rows, cls_map, gmax, batch, heads, n_tokens, stream)) != VTC_OK) return rc;
+        return cls_mask(cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, batch, n_tokens, stream);
+    }
+    cls_stat_mask_kernel<<<batch, 256, 0, stream>>>(cls_rows, cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, ticket, batch, heads, n_tokens);
+    VTC_CHECK_LAUNCH();
+    return VTC_OK;
+}
+
 // grid = B, block = 256.  Dynamic smem: [P] map copy + [D] mean token + [D] normalised CLS row + [R] pre-logits.
 // The map is divided by its maximum first (batch-global `*gmax`, or the image's own when gmax == nullptr) exactly as
 // vit_model.py:372 does before torch.topk (:377): the fp32 quotients, not the raw values, decide order and ties.
@@ -155,10 +232,21 @@ __global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__
     __syncthreads();
     if (topk_idx != nullptr && threadIdx.x < K) topk_idx[b * K + threadIdx.x] = idx_s[threadIdx.x];
 
-    // gather the K tokens (block-L output, pre final norm) and their mean
+    // gather the K tokens (block-L output, pre final norm) and their mean; the CLS row goes to shared memory once
     const float* tok = tokens + static_cast<size_t>(b) * N * D;
     const float invK = 1.0f / K;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) xn[d] = tok[d];
+    for (int d4 = threadIdx.x; d4 < (D >> 2); d4 += blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float4 v = ldg_f4(tok + static_cast<size_t>(1 + idx_s[k]) * D + 4 * d4);
+            st_f4(hwp_tokens + (static_cast<size_t>(b) * K + k) * D + 4 * d4, v);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        meanv[4 * d4] = s.x * invK; meanv[4 * d4 + 1] = s.y * invK; meanv[4 * d4 + 2] = s.z * invK; meanv[4 * d4 + 3] = s.w * invK;
+    }
+    for (int d = (D & ~3) + threadIdx.x; d < D; d += blockDim.x) {      // D not a multiple of 4 (never for a ViT)
         float s = 0.f;
         for (int k = 0; k < K; ++k) {
             const float v = tok[static_cast<size_t>(1 + idx_s[k]) * D + d];
@@ -167,14 +255,15 @@ __global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__
         }
         meanv[d] = s * invK;
     }
+    __syncthreads();
     // final LayerNorm of the CLS row only (vit_model.py:402 normalises all rows; only row 0 is consumed :406)
     float part = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) part += tok[d];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) part += xn[d];
     const float mean = block_sum(part, red) / D;
     part = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) { const float t = tok[d] - mean; part += t * t; }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { const float c = xn[d] - mean; part += c * c; }
     const float rstd = rsqrtf(block_sum(part, red) / D + hp.eps);
-    for (int d = threadIdx.x; d < D; d += blockDim.x) xn[d] = (tok[d] - mean) * rstd * hp.norm_w[d] + hp.norm_b[d];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) xn[d] = (xn[d] - mean) * rstd * hp.norm_w[d] + hp.norm_b[d];
     __syncthreads();
 
     const float* fin = xn;

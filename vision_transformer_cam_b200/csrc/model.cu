@@ -62,6 +62,7 @@ static bool fused_mean_ok(const vtc_model* m) {
 struct Workspace {
     __nv_bfloat16 *hbuf, *patches, *y, *qkv, *ao;
     float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp, *stats, *mean_tmp;
+    unsigned int* ticket;        // cls_stat_mask: one arrival counter per layer (zeroed with gmax)
     void* mean_scratch;          // packed P of attention_mean
     size_t mean_scratch_bytes;
     __nv_bfloat16* rollops;      // rollout operands of the last min(L,12) layers [Lr,B,N,ldr] (ops.h)
@@ -88,7 +89,8 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     ws.cls_rows = (o && o->cls_rows) ? nullptr : reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N, 4));
     ws.cls_map = (o && o->cls_map) ? nullptr : reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->P, 4));
     ws.key_bias = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N, 4));
-    ws.gmax = reinterpret_cast<float*>(take(m->L, 4));
+    ws.gmax = reinterpret_cast<float*>(take(2 * m->L, 4));
+    ws.ticket = ws.gmax ? reinterpret_cast<unsigned int*>(ws.gmax + m->L) : nullptr;
     ws.stats = reinterpret_cast<float*>(take(M * (D / 128) * 2, 4));       // LayerNorm row statistics (bf16 mode)
     const bool want_mean = o && (o->attn_mean || o->rollout);
     const bool need_mean = want_mean && !(o->attn && o->attn_layers >= m->L);       // some layer's mean is not a by-product of its full P
@@ -177,7 +179,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     else VTC_STEP(VTC_PROF_PATCHIFY, patchify(in.f32, ws.patches, B, m->cfg.in_c, m->cfg.img_size, m->cfg.patch_size, st, sp));
     VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));
     VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st, sp));
-    VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * L, st));
+    VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * 2 * L, st));      // + the per-layer tickets of cls_stat_mask
     if (o->bg) VTC_CUDA(cudaMemsetAsync(o->bg, 0, static_cast<size_t>(L) * B * P, st));
 
     bool have_bias = false;
@@ -245,13 +247,14 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
         }
         if (want_map) {
             float* map_l = o->cls_map ? o->cls_map + static_cast<size_t>(l) * B * P : ws.cls_map;
-            VTC_STEP(VTC_PROF_CLS, cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st));
             last_map = map_l;
             if (l >= m->cfg.mask_from) {                                                                        // vit_model.py:325
                 const uint8_t* forced = (f && f->bg && (f->bg_layer_mask >> l & 1u)) ? f->bg + static_cast<size_t>(l) * B * P : nullptr;
                 uint8_t* bg_l = o->bg ? o->bg + static_cast<size_t>(l) * B * P : nullptr;
-                VTC_STEP(VTC_PROF_CLS, cls_mask(map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, B, N, st));
+                VTC_STEP(VTC_PROF_CLS, cls_stat_mask(cls_l, map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, ws.ticket + l, B, H, N, st));
                 have_bias = true;
+            } else {
+                VTC_STEP(VTC_PROF_CLS, cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st));
             }
         }
     }

@@ -84,6 +84,9 @@ int head_mean(const float* attn, float* mean, int batch, int heads, int n_tokens
 int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int heads, int n_tokens, cudaStream_t stream);
 int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
              float* key_bias, int batch, int n_tokens, cudaStream_t stream);
+// both in one launch (the forward); `ticket`: a zeroed unsigned int that the kernel leaves zeroed
+int cls_stat_mask(const float* cls_rows, float* cls_map, float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
+                  float* key_bias, unsigned int* ticket, int batch, int heads, int n_tokens, cudaStream_t stream);
 
 struct HeadParams {
     const float* norm_w; const float* norm_b;

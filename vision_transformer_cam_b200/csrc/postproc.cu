@@ -298,18 +298,31 @@ __device__ __forceinline__ void split_pair(float2 v, uint32_t& hi, uint32_t& lo)
     lo = pack_bf16x2(v.x - __uint_as_float(hi << 16), v.y - __uint_as_float(hi & 0xffff0000u));
 }
 
-template <int NT>      // class tiles of 8: C <= 8 * NT
-__global__ void __launch_bounds__(512) cam_project_kernel(const float* __restrict__ tokens, const float* __restrict__ w, float* __restrict__ cam,
-                                                          int N, int D, int C, int relu, float eps) {
+// COS: the same product with PER-IMAGE weights (w + b * w_stride: the image's K high-weight tokens) and a cosine epilogue,
+// out[b,k,p] = <F_p, o_k> / (max(|F_p|, 1e-12) max(|o_k|, 1e-12)) (validate.py:157-175: F.normalize on both sides, then the
+// dot product); the patch norms are accumulated from the A fragments on the way.
+template <int NT, bool COS>      // class tiles of 8: C <= 8 * NT
+__global__ void __launch_bounds__(512) cam_project_kernel(const float* __restrict__ tokens, const float* __restrict__ w_all, size_t w_stride,
+                                                          float* __restrict__ cam, int N, int D, int C, int relu, float eps) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
+    __shared__ float wnorm[64];
     const int P = N - 1;
     const int wp = D + 8;                                                   // W row pitch (bf16)
     __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(sm_raw);          // [8 NT][wp]
     __nv_bfloat16* wlo = whi + static_cast<size_t>(8 * NT) * wp;
     float* raw = reinterpret_cast<float*>(wlo + static_cast<size_t>(8 * NT) * wp);      // [C][P]
     const int b = blockIdx.x;
+    const float* w = w_all + static_cast<size_t>(b) * w_stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
+    if (COS) {
+        for (int c = warp; c < C; c += nwarps) {
+            float s = 0.f;
+            for (int d = lane; d < D; d += 32) { const float v = __ldg(w + static_cast<size_t>(c) * D + d); s = fmaf(v, v, s); }
+            s = warp_sum(s);
+            if (lane == 0) wnorm[c] = fmaxf(sqrtf(s), 1e-12f);            // F.normalize eps
+        }
+    }
     for (int i = threadIdx.x; i < 8 * NT * (D / 2); i += blockDim.x) {
         const int c = i / (D / 2), d2 = i - c * (D / 2);
         uint32_t hi = 0u, lo = 0u;
@@ -326,13 +339,20 @@ __global__ void __launch_bounds__(512) cam_project_kernel(const float* __restric
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        float nn0 = 0.f, nn1 = 0.f;                     // COS: squared norms of patch rows p0 / p1 (this lane's 4 of every 16 columns)
 #pragma unroll 4
         for (int ks = 0; ks < D / 16; ++ks) {
             uint32_t ah[4], al[4];
-            split_pair(*reinterpret_cast<const float2*>(f0 + ks * 16), ah[0], al[0]);
-            split_pair(*reinterpret_cast<const float2*>(f1 + ks * 16), ah[1], al[1]);
-            split_pair(*reinterpret_cast<const float2*>(f0 + ks * 16 + 8), ah[2], al[2]);
-            split_pair(*reinterpret_cast<const float2*>(f1 + ks * 16 + 8), ah[3], al[3]);
+            const float2 a00 = *reinterpret_cast<const float2*>(f0 + ks * 16), a10 = *reinterpret_cast<const float2*>(f1 + ks * 16);
+            const float2 a01 = *reinterpret_cast<const float2*>(f0 + ks * 16 + 8), a11 = *reinterpret_cast<const float2*>(f1 + ks * 16 + 8);
+            if (COS) {
+                nn0 = fmaf(a00.x, a00.x, fmaf(a00.y, a00.y, fmaf(a01.x, a01.x, fmaf(a01.y, a01.y, nn0))));
+                nn1 = fmaf(a10.x, a10.x, fmaf(a10.y, a10.y, fmaf(a11.x, a11.x, fmaf(a11.y, a11.y, nn1))));
+            }
+            split_pair(a00, ah[0], al[0]);
+            split_pair(a10, ah[1], al[1]);
+            split_pair(a01, ah[2], al[2]);
+            split_pair(a11, ah[3], al[3]);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const size_t off = static_cast<size_t>(nt * 8 + g) * wp + ks * 16 + 2 * t;
@@ -343,17 +363,31 @@ __global__ void __launch_bounds__(512) cam_project_kernel(const float* __restric
                 mma_bf16_16816_acc(acc[nt], ah, bl0, bl1);
             }
         }
+        if (COS) {
+            nn0 += __shfl_xor_sync(0xffffffffu, nn0, 1); nn0 += __shfl_xor_sync(0xffffffffu, nn0, 2);
+            nn1 += __shfl_xor_sync(0xffffffffu, nn1, 1); nn1 += __shfl_xor_sync(0xffffffffu, nn1, 2);
+            nn0 = fmaxf(sqrtf(nn0), 1e-12f);
+            nn1 = fmaxf(sqrtf(nn1), 1e-12f);
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int c = nt * 8 + 2 * t;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int cc = c + (e & 1), pp = (e & 2) ? p1 : p0;
-                if (cc < C && pp < P) raw[cc * P + pp] = relu ? fmaxf(acc[nt][e], 0.f) : acc[nt][e];
+                if (cc < C && pp < P) {
+                    if (COS) raw[cc * P + pp] = acc[nt][e] / (((e & 2) ? nn1 : nn0) * wnorm[cc]);
+                    else raw[cc * P + pp] = relu ? fmaxf(acc[nt][e], 0.f) : acc[nt][e];
+                }
             }
         }
     }
     __syncthreads();
+    if (COS) {
+        float* dst = cam + static_cast<size_t>(b) * C * P;
+        for (int i = threadIdx.x; i < C * P; i += blockDim.x) dst[i] = raw[i];
+        return;
+    }
     for (int c = warp; c < C; c += nwarps) {
         float mn = INFINITY, mx = -INFINITY;
         for (int p = lane; p < P; p += 32) { const float v = raw[c * P + p]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
@@ -365,18 +399,18 @@ __global__ void __launch_bounds__(512) cam_project_kernel(const float* __restric
     }
 }
 
-template <int NT>
-static int launch_cam_project(const float* tokens, const float* w, float* cam, int batch, int n_tokens, int dim, int classes, int relu, float eps,
-                              cudaStream_t stream) {
+template <int NT, bool COS = false>
+static int launch_cam_project(const float* tokens, const float* w, size_t w_stride, float* cam, int batch, int n_tokens, int dim, int classes, int relu,
+                              float eps, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(2) * 8 * NT * (dim + 8) * 2 + sizeof(float) * static_cast<size_t>(classes) * (n_tokens - 1);
     VTC_REQUIRE(smem <= 220 * 1024, VTC_ERR_SHAPE, "cam_project: %zu bytes of smem", smem);
     static SmemOptIn optin;
-    int rc_ = optin.ensure(reinterpret_cast<const void*>(cam_project_kernel<NT>), smem);
+    int rc_ = optin.ensure(reinterpret_cast<const void*>(cam_project_kernel<NT, COS>), smem);
     if (rc_ != VTC_OK) return rc_;
     int warps = cdiv(n_tokens - 1, 16);
     if (warps > 16) warps = 16;
     if (warps < 1) warps = 1;
-    cam_project_kernel<NT><<<batch, warps * 32, smem, stream>>>(tokens, w, cam, n_tokens, dim, classes, relu, eps);
+    cam_project_kernel<NT, COS><<<batch, warps * 32, smem, stream>>>(tokens, w, w_stride, cam, n_tokens, dim, classes, relu, eps);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
@@ -389,14 +423,14 @@ int cam_project(const float* tokens, const float* w, float* cam, int batch, int 
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
     switch (cdiv(classes, 8)) {
-        case 1: return launch_cam_project<1>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        case 2: return launch_cam_project<2>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        case 3: return launch_cam_project<3>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        case 4: return launch_cam_project<4>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        case 5: return launch_cam_project<5>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        case 6: return launch_cam_project<6>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        case 7: return launch_cam_project<7>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
-        default: return launch_cam_project<8>(tokens, w, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 1: return launch_cam_project<1>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 2: return launch_cam_project<2>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 3: return launch_cam_project<3>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 4: return launch_cam_project<4>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 5: return launch_cam_project<5>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 6: return launch_cam_project<6>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        case 7: return launch_cam_project<7>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
+        default: return launch_cam_project<8>(tokens, w, 0, cam, batch, n_tokens, dim, classes, relu, eps, stream);
     }
 }
 
@@ -423,6 +457,13 @@ int normalize_max(float* maps, int rows, int p, cudaStream_t stream) {
 }
 
 // ---- bilinear upsampling, align_corners=False (F.interpolate validate.py:177,239 == cv2.resize INTER_LINEAR) ----------
+// The three pixel kernels below (full-resolution maps, CAM pseudo label, high-weight-patch segmentation) share one tiling:
+// a block owns PIX_ROWS output rows of one image and walks them in quads of four consecutive pixels, so that a thread's result
+// leaves as ONE 16-byte (fp32) or 4-byte (uint8) store and a warp writes 512 / 128 contiguous bytes.  Everything that depends
+// only on x (source column pair and weight) is tabulated once per block in shared memory next to the g x g source maps; what
+// depends only on y is computed once per quad.  The interpolation itself keeps the operation order of F.interpolate /
+// cv2.resize (horizontal pair first, then vertical).  Per output pixel and map: 4 shared loads + 6 flops (the first version
+// spent > 100 instructions per pixel on 64-bit index arithmetic and reloaded every class map for four pixels per thread).
 struct Lerp { int i0, i1; float w0, w1; };
 __device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
     float src = (dst + 0.5f) * scale - 0.5f;
@@ -437,104 +478,168 @@ __device__ __forceinline__ float bilerp(const float* m, int g, const Lerp& y, co
     return y.w0 * (x.w0 * m[y.i0 * g + x.i0] + x.w1 * m[y.i0 * g + x.i1]) + y.w1 * (x.w0 * m[y.i1 * g + x.i0] + x.w1 * m[y.i1 * g + x.i1]);
 }
 
+constexpr int PIX_ROWS = 16;          // output rows per block
+constexpr int PIX_THREADS = 256;
+// x tables of a block: xi[x] = i0 | i1 << 16, xw[x] = weight of i1 (the weight of i0 is 1 - xw, as in lerp_coord)
+__device__ __forceinline__ void pix_fill_x(uint32_t* xi, float* xw, int W, int g) {
+    const float sx = static_cast<float>(g) / W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const Lerp l = lerp_coord(x, sx, g);
+        xi[x] = static_cast<uint32_t>(l.i0) | (static_cast<uint32_t>(l.i1) << 16);
+        xw[x] = l.w1;
+    }
+}
+__device__ __forceinline__ float pix_bilerp(const float* r0, const float* r1, float wy0, float wy1, uint32_t xi, float xw1) {
+    const int i0 = xi & 0xffffu, i1 = xi >> 16;
+    const float xw0 = 1.0f - xw1;
+    return wy0 * (xw0 * r0[i0] + xw1 * r0[i1]) + wy1 * (xw0 * r1[i0] + xw1 * r1[i1]);
+}
+static size_t pix_table_bytes(int W) { return static_cast<size_t>(W) * 8; }
+
 template <bool U8>
-__global__ void upsample_kernel(const float* __restrict__ in, void* __restrict__ out, int g, int H, int W) {
-    extern __shared__ float m[];      // [g*g]
+__global__ void __launch_bounds__(PIX_THREADS) upsample_kernel(const float* __restrict__ in, void* __restrict__ out, int g, int H, int W) {
+    extern __shared__ __align__(16) uint8_t pix_sm[];
+    uint32_t* xi = reinterpret_cast<uint32_t*>(pix_sm);
+    float* xw = reinterpret_cast<float*>(xi + W);
+    float* m = xw + W;                                   // [g*g]
     const int n = blockIdx.y;
     for (int i = threadIdx.x; i < g * g; i += blockDim.x) m[i] = in[static_cast<size_t>(n) * g * g + i];
+    pix_fill_x(xi, xw, W, g);
     __syncthreads();
-    const float sy = static_cast<float>(g) / H, sx = static_cast<float>(g) / W;
-    const size_t hw = static_cast<size_t>(H) * W;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<size_t>(y) * W);
-        const float v = bilerp(m, g, lerp_coord(y, sy, g), lerp_coord(x, sx, g));
-        if (U8) static_cast<uint8_t*>(out)[n * hw + i] = static_cast<uint8_t>(v * 255.0f);     // .astype("uint8") truncation, predict.py:269
-        else static_cast<float*>(out)[n * hw + i] = v;
+    const float sy = static_cast<float>(g) / H;
+    const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
+    const int quads = (W + 3) >> 2;
+    const size_t base = static_cast<size_t>(n) * H * W;
+    const bool vec = (W & 3) == 0;
+    for (int it = threadIdx.x; it < rows * quads; it += blockDim.x) {
+        const int r = it / quads, x0 = (it - r * quads) * 4, y = y_first + r;
+        const Lerp ly = lerp_coord(y, sy, g);
+        const float* r0 = m + ly.i0 * g;
+        const float* r1 = m + ly.i1 * g;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int x = min(x0 + e, W - 1);
+            v[e] = pix_bilerp(r0, r1, ly.w0, ly.w1, xi[x], xw[x]);
+        }
+        const size_t o = base + static_cast<size_t>(y) * W + x0;
+        if (U8) {                                          // .astype("uint8") truncation, predict.py:269
+            uint8_t* dst = static_cast<uint8_t*>(out) + o;
+            const uint32_t p = static_cast<uint32_t>(static_cast<uint8_t>(v[0] * 255.0f)) | (static_cast<uint32_t>(static_cast<uint8_t>(v[1] * 255.0f)) << 8) |
+                               (static_cast<uint32_t>(static_cast<uint8_t>(v[2] * 255.0f)) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(v[3] * 255.0f)) << 24);
+            if (vec) *reinterpret_cast<uint32_t*>(dst) = p;
+            else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(p >> (8 * e));
+        } else {
+            float* dst = static_cast<float*>(out) + o;
+            if (vec) st_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
+            else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = v[e];
+        }
     }
 }
 
 template <bool U8>
 static int upsample(const float* in, void* out, int n, int g, int H, int W, cudaStream_t stream) {
     VTC_REQUIRE(in && out, VTC_ERR_ARG, "upsample: null pointer");
-    VTC_REQUIRE(n > 0 && g > 0 && H > 0 && W > 0 && g * g * 4 <= 48 * 1024 && n <= 65535, VTC_ERR_SHAPE, "upsample: bad shape n=%d g=%d", n, g);
+    const size_t smem = pix_table_bytes(W) + sizeof(float) * g * g;
+    VTC_REQUIRE(n > 0 && g > 0 && g < 65536 && H > 0 && W > 0 && smem <= 48 * 1024 && n <= 65535, VTC_ERR_SHAPE, "upsample: bad shape n=%d g=%d W=%d", n, g, W);
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, VTC_ERR_ARG, "upsample: output must be 16-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    int bx = cdiv(H * W, 256 * 4);
-    if (bx < 1) bx = 1;
-    upsample_kernel<U8><<<dim3(bx, n), 256, sizeof(float) * g * g, stream>>>(in, out, g, H, W);
+    upsample_kernel<U8><<<dim3(cdiv(H, PIX_ROWS), n), PIX_THREADS, smem, stream>>>(in, out, g, H, W);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
 
 // ---- CAM pseudo label: fused upsample + argmax over [bg_thresh, labelled classes] -----------------------------------
-__global__ void cam_label_kernel(const float* __restrict__ cam, const uint8_t* __restrict__ labels, float bg_thresh, uint8_t* __restrict__ out,
-                                 int C, int g, int H, int W) {
-    extern __shared__ float m[];      // [C][g*g]
+// Only the maps of the image's own classes (utils.py:100-108; 1.5 per VOC image on average) are staged in shared memory.
+__global__ void __launch_bounds__(PIX_THREADS) cam_label_kernel(const float* __restrict__ cam, const uint8_t* __restrict__ labels, float bg_thresh,
+                                                               uint8_t* __restrict__ out, int C, int g, int H, int W) {
+    extern __shared__ __align__(16) uint8_t pix_sm[];
     __shared__ int active[64];
     __shared__ int nactive;
+    uint32_t* xi = reinterpret_cast<uint32_t*>(pix_sm);
+    float* xw = reinterpret_cast<float*>(xi + W);
+    float* m = xw + W;                                   // [nactive][g*g]
     const int b = blockIdx.y;
     const int gg = g * g;
-    for (int i = threadIdx.x; i < C * gg; i += blockDim.x) m[i] = cam[static_cast<size_t>(b) * C * gg + i];
     if (threadIdx.x == 0) {
         int k = 0;
         for (int c = 0; c < C; ++c)
             if (labels[b * C + c]) active[k++] = c;
         nactive = k;
     }
+    pix_fill_x(xi, xw, W, g);
     __syncthreads();
-    const float sy = static_cast<float>(g) / H, sx = static_cast<float>(g) / W;
-    const size_t hw = static_cast<size_t>(H) * W;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<size_t>(y) * W);
-        const Lerp ly = lerp_coord(y, sy, g), lx = lerp_coord(x, sx, g);
-        float best = bg_thresh;
-        int lab = 0;
-        for (int k = 0; k < nactive; ++k) {
-            const int c = active[k];
-            const float v = bilerp(m + c * gg, g, ly, lx);
-            if (v > best) { best = v; lab = c + 1; }       // strict: ties keep the earlier entry like torch.argmax
+    const int na = nactive;
+    for (int i = threadIdx.x; i < na * gg; i += blockDim.x) {
+        const int k = i / gg;
+        m[i] = cam[(static_cast<size_t>(b) * C + active[k]) * gg + (i - k * gg)];
+    }
+    __syncthreads();
+    const float sy = static_cast<float>(g) / H;
+    const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
+    const int quads = (W + 3) >> 2;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const bool vec = (W & 3) == 0;
+    for (int it = threadIdx.x; it < rows * quads; it += blockDim.x) {
+        const int r = it / quads, x0 = (it - r * quads) * 4, y = y_first + r;
+        const Lerp ly = lerp_coord(y, sy, g);
+        uint32_t xii[4];
+        float xww[4], best[4];
+        uint32_t lab = 0u;                                 // four labels, one per byte
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int x = min(x0 + e, W - 1);
+            xii[e] = xi[x];
+            xww[e] = xw[x];
+            best[e] = bg_thresh;
         }
-        out[b * hw + i] = static_cast<uint8_t>(lab);
+        for (int k = 0; k < na; ++k) {
+            const float* r0 = m + k * gg + ly.i0 * g;
+            const float* r1 = m + k * gg + ly.i1 * g;
+            const uint32_t code = static_cast<uint32_t>(active[k] + 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = pix_bilerp(r0, r1, ly.w0, ly.w1, xii[e], xww[e]);
+                if (v > best[e]) {                        // strict: ties keep the earlier entry like torch.argmax
+                    best[e] = v;
+                    lab = (lab & ~(0xffu << (8 * e))) | (code << (8 * e));
+                }
+            }
+        }
+        uint8_t* dst = out + base + static_cast<size_t>(y) * W + x0;
+        if (vec) *reinterpret_cast<uint32_t*>(dst) = lab;
+        else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(lab >> (8 * e));
     }
 }
 
 int cam_label(const float* cam, const uint8_t* labels, float bg_thresh, uint8_t* out, int batch, int classes, int g, int H, int W, cudaStream_t stream) {
     VTC_REQUIRE(cam && labels && out, VTC_ERR_ARG, "cam_label: null pointer");
-    VTC_REQUIRE(batch > 0 && batch <= 65535 && classes > 0 && classes <= 64 && g > 0 && H > 0 && W > 0, VTC_ERR_SHAPE, "cam_label: bad shape");
-    const size_t smem = sizeof(float) * classes * g * g;
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && classes > 0 && classes <= 64 && g > 0 && g < 65536 && H > 0 && W > 0, VTC_ERR_SHAPE, "cam_label: bad shape");
+    const size_t smem = pix_table_bytes(W) + sizeof(float) * classes * g * g;
     VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "cam_label: %zu bytes of smem", smem);
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, VTC_ERR_ARG, "cam_label: output must be 4-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    int bx = cdiv(H * W, 256 * 4);
-    if (bx < 1) bx = 1;
-    cam_label_kernel<<<dim3(bx, batch), 256, smem, stream>>>(cam, labels, bg_thresh, out, classes, g, H, W);
+    cam_label_kernel<<<dim3(cdiv(H, PIX_ROWS), batch), PIX_THREADS, smem, stream>>>(cam, labels, bg_thresh, out, classes, g, H, W);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
 
 // ---- high-weight-patch class vote + cosine maps (validate.py:132-175) -------------------------------------------------
 constexpr int HWP_MAXK = 16;
-__global__ void __launch_bounds__(256) hwp_cos_vote_kernel(const float* __restrict__ hwp_logits, const float* __restrict__ w1,
-                                                           const float* __restrict__ ori, const float* __restrict__ tokens, float sig_thresh,
-                                                           int32_t* __restrict__ p2c, float* __restrict__ cosm, int N, int D, int C, int K) {
-    extern __shared__ float sm[];
-    float* os = sm;                       // [K][D] hw tokens
-    float* onorm = os + K * D;            // [K]
-    int* votes = reinterpret_cast<int*>(onorm + HWP_MAXK);   // [K][C]
+// One block per image: class vote of the K high-weight patches (validate.py:132-153).  The cosine maps (validate.py:157-175)
+// are a [P x D] x [D x K] product per image with per-image weights: cam_project_kernel<.., COS> above (warp-level tensor cores,
+// fp32-equivalent split operands), which replaced a shared-memory-bound FMA version of this kernel (282 -> see profiles/).
+__global__ void __launch_bounds__(256) hwp_vote_kernel(const float* __restrict__ hwp_logits, const float* __restrict__ w1, const float* __restrict__ ori,
+                                                       float sig_thresh, int32_t* __restrict__ p2c, int D, int C, int K) {
+    __shared__ int votes[HWP_MAXK * 64];   // [K][C]
     __shared__ int pred[64];
-    const int b = blockIdx.x, P = N - 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
     const float* ob = ori + static_cast<size_t>(b) * K * D;
-    for (int i = threadIdx.x; i < K * D / 4; i += blockDim.x) reinterpret_cast<float4*>(os)[i] = ldg_f4(ob + 4 * i);
     for (int i = threadIdx.x; i < K * C; i += blockDim.x) votes[i] = 0;
     if (threadIdx.x < C) pred[threadIdx.x] = (1.0f / (1.0f + expf(-hwp_logits[b * C + threadIdx.x]))) >= sig_thresh;   // validate.py:132-134
     __syncthreads();
-    for (int k = warp; k < K; k += 8) {
-        float s = 0.f;
-        for (int d = lane; d < D; d += 32) s += os[k * D + d] * os[k * D + d];
-        s = warp_sum(s);
-        if (lane == 0) onorm[k] = fmaxf(sqrtf(s), 1e-12f);                        // F.normalize eps
-    }
     // feature vote: class of feature d (argmax over predicted classes' head1 rows) goes to the hw patch owning d
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float bw = -INFINITY;
@@ -546,7 +651,7 @@ __global__ void __launch_bounds__(256) hwp_cos_vote_kernel(const float* __restri
         float bo = -INFINITY;
         int bk = 0;
         for (int k = 0; k < K; ++k) {
-            const float v = os[k * D + d];
+            const float v = __ldg(ob + static_cast<size_t>(k) * D + d);
             if (v > bo) { bo = v; bk = k; }                                       // validate.py:148
         }
         atomicAdd(&votes[bk * C + bc], 1);
@@ -558,36 +663,6 @@ __global__ void __launch_bounds__(256) hwp_cos_vote_kernel(const float* __restri
             if (votes[threadIdx.x * C + c] > best) { best = votes[threadIdx.x * C + c]; bc = c; }   // mode, ties -> smallest class
         p2c[b * K + threadIdx.x] = bc;                                            // -1: patch owns no feature
     }
-    // cosine maps
-    const float* F = tokens + (static_cast<size_t>(b) * N + 1) * D;
-    const int nv = D / 128;
-    for (int p = warp; p < P; p += 8) {
-        float acc[HWP_MAXK];
-#pragma unroll
-        for (int k = 0; k < HWP_MAXK; ++k) acc[k] = 0.f;
-        float nn = 0.f;
-        const float* row = F + static_cast<size_t>(p) * D;
-        for (int i = 0; i < nv; ++i) {
-            const int d = (lane + 32 * i) * 4;
-            const float4 f = ld_stream_f4(row + d);
-            nn = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, nn))));
-#pragma unroll
-            for (int k = 0; k < HWP_MAXK; ++k) {
-                if (k < K) {
-                    const float4 o = *reinterpret_cast<const float4*>(os + k * D + d);
-                    acc[k] = fmaf(f.x, o.x, fmaf(f.y, o.y, fmaf(f.z, o.z, fmaf(f.w, o.w, acc[k]))));
-                }
-            }
-        }
-        nn = fmaxf(sqrtf(warp_sum(nn)), 1e-12f);
-#pragma unroll
-        for (int k = 0; k < HWP_MAXK; ++k) {
-            if (k < K) {
-                const float s = warp_sum(acc[k]);
-                if (lane == 0) cosm[(static_cast<size_t>(b) * K + k) * P + p] = s / (nn * onorm[k]);
-            }
-        }
-    }
 }
 
 int hwp_cos_vote(const float* hwp_logits, const float* head1_w, const float* hwp_tokens, const float* tokens, float sig_thresh,
@@ -595,57 +670,87 @@ int hwp_cos_vote(const float* hwp_logits, const float* head1_w, const float* hwp
     VTC_REQUIRE(hwp_logits && head1_w && hwp_tokens && tokens && patch_to_cls && cosm, VTC_ERR_ARG, "hwp_cos_vote: null pointer");
     VTC_REQUIRE(batch > 0 && n_tokens > 1 && dim % 128 == 0 && classes > 0 && classes <= 64 && k > 0 && k <= HWP_MAXK, VTC_ERR_SHAPE,
                 "hwp_cos_vote: dim %d classes %d k %d", dim, classes, k);
+    VTC_REQUIRE(((reinterpret_cast<uintptr_t>(tokens) | reinterpret_cast<uintptr_t>(hwp_tokens)) & 7) == 0, VTC_ERR_ARG, "hwp_cos_vote: pointers must be 8-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(k) * dim + HWP_MAXK) + sizeof(int) * k * classes;
-    VTC_REQUIRE(smem <= 200 * 1024, VTC_ERR_SHAPE, "hwp_cos_vote: %zu bytes of smem", smem);
-    static SmemOptIn optin;
-    if ((rc = optin.ensure(reinterpret_cast<const void*>(hwp_cos_vote_kernel), smem)) != VTC_OK) return rc;
-    hwp_cos_vote_kernel<<<batch, 256, smem, stream>>>(hwp_logits, head1_w, hwp_tokens, tokens, sig_thresh, patch_to_cls, cosm, n_tokens, dim, classes, k);
+    hwp_vote_kernel<<<batch, 256, 0, stream>>>(hwp_logits, head1_w, hwp_tokens, sig_thresh, patch_to_cls, dim, classes, k);
     VTC_CHECK_LAUNCH();
-    return VTC_OK;
+    const size_t stride = static_cast<size_t>(k) * dim;
+    if (k <= 8) return launch_cam_project<1, true>(tokens, hwp_tokens, stride, cosm, batch, n_tokens, dim, k, 0, 0.f, stream);
+    return launch_cam_project<2, true>(tokens, hwp_tokens, stride, cosm, batch, n_tokens, dim, k, 0, 0.f, stream);
 }
 
 // ---- validate.py:177-258 fused: upsample K cosine maps + argmax + fg/bg thresholds -> uint8 label map ------------------
-__global__ void hwp_seg_kernel(const float* __restrict__ cosm, const int32_t* __restrict__ p2c, const float* __restrict__ bg_map, float cos_thresh,
-                               float bg_thresh, uint8_t* __restrict__ out, int K, int g, int H, int W) {
-    extern __shared__ float m[];      // [K][g*g] + [g*g]
+// Same tiling as above; K + 1 maps per image in shared memory, K bilinear samples per pixel (inherent: the argmax is taken at
+// output resolution, validate.py:177-180).
+__global__ void __launch_bounds__(PIX_THREADS) hwp_seg_kernel(const float* __restrict__ cosm, const int32_t* __restrict__ p2c, const float* __restrict__ bg_map,
+                                                             float cos_thresh, float bg_thresh, uint8_t* __restrict__ out, int K, int g, int H, int W) {
+    extern __shared__ __align__(16) uint8_t pix_sm[];
     __shared__ int cls_s[HWP_MAXK];
+    uint32_t* xi = reinterpret_cast<uint32_t*>(pix_sm);
+    float* xw = reinterpret_cast<float*>(xi + W);
+    float* m = xw + W;                                   // [K][g*g] + [g*g]
     const int b = blockIdx.y;
     const int gg = g * g;
     for (int i = threadIdx.x; i < K * gg; i += blockDim.x) m[i] = cosm[static_cast<size_t>(b) * K * gg + i];
     for (int i = threadIdx.x; i < gg; i += blockDim.x) m[K * gg + i] = bg_map[static_cast<size_t>(b) * gg + i];
     if (threadIdx.x < K) cls_s[threadIdx.x] = p2c[b * K + threadIdx.x];
+    pix_fill_x(xi, xw, W, g);
     __syncthreads();
-    const float sy = static_cast<float>(g) / H, sx = static_cast<float>(g) / W;
-    const size_t hw = static_cast<size_t>(H) * W;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<size_t>(y) * W);
-        const Lerp ly = lerp_coord(y, sy, g), lx = lerp_coord(x, sx, g);
-        float best = -INFINITY;
-        int bk = 0;
-        for (int k = 0; k < K; ++k) {
-            const float v = bilerp(m + k * gg, g, ly, lx);
-            if (v > best) { best = v; bk = k; }                                   // validate.py:179-180
+    const float sy = static_cast<float>(g) / H;
+    const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
+    const int quads = (W + 3) >> 2;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const bool vec = (W & 3) == 0;
+    for (int it = threadIdx.x; it < rows * quads; it += blockDim.x) {
+        const int r = it / quads, x0 = (it - r * quads) * 4, y = y_first + r;
+        const Lerp ly = lerp_coord(y, sy, g);
+        uint32_t xii[4];
+        float xww[4], best[4];
+        int bk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int x = min(x0 + e, W - 1);
+            xii[e] = xi[x];
+            xww[e] = xw[x];
+            best[e] = -INFINITY;
+            bk[e] = 0;
         }
-        const bool fg = best >= cos_thresh;                                       // validate.py:183-186
-        const bool keep = bilerp(m + K * gg, g, ly, lx) >= bg_thresh;             // validate.py:239-246
-        const int c = cls_s[bk];
-        out[b * hw + i] = (fg && keep && c >= 0) ? static_cast<uint8_t>(c + 1) : 0;   // validate.py:190-258
+        for (int k = 0; k < K; ++k) {
+            const float* r0 = m + k * gg + ly.i0 * g;
+            const float* r1 = m + k * gg + ly.i1 * g;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = pix_bilerp(r0, r1, ly.w0, ly.w1, xii[e], xww[e]);
+                if (v > best[e]) { best[e] = v; bk[e] = k; }                      // validate.py:179-180
+            }
+        }
+        const float* b0 = m + K * gg + ly.i0 * g;
+        const float* b1 = m + K * gg + ly.i1 * g;
+        uint32_t lab = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool fg = best[e] >= cos_thresh;                                                    // validate.py:183-186
+            const bool keep = pix_bilerp(b0, b1, ly.w0, ly.w1, xii[e], xww[e]) >= bg_thresh;          // validate.py:239-246
+            const int c = cls_s[bk[e]];
+            lab |= ((fg && keep && c >= 0) ? static_cast<uint32_t>(c + 1) : 0u) << (8 * e);         // validate.py:190-258
+        }
+        uint8_t* dst = out + base + static_cast<size_t>(y) * W + x0;
+        if (vec) *reinterpret_cast<uint32_t*>(dst) = lab;
+        else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(lab >> (8 * e));
     }
 }
 
 int hwp_seg(const float* cosm, const int32_t* p2c, const float* bg_map, float cos_thresh, float bg_thresh, uint8_t* out, int batch, int k, int g,
             int H, int W, cudaStream_t stream) {
     VTC_REQUIRE(cosm && p2c && bg_map && out, VTC_ERR_ARG, "hwp_seg: null pointer");
-    VTC_REQUIRE(batch > 0 && batch <= 65535 && k > 0 && k <= HWP_MAXK && g > 0 && H > 0 && W > 0, VTC_ERR_SHAPE, "hwp_seg: bad shape");
-    const size_t smem = sizeof(float) * (k + 1) * g * g;
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && k > 0 && k <= HWP_MAXK && g > 0 && g < 65536 && H > 0 && W > 0, VTC_ERR_SHAPE, "hwp_seg: bad shape");
+    const size_t smem = pix_table_bytes(W) + sizeof(float) * (k + 1) * g * g;
     VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "hwp_seg: %zu bytes of smem", smem);
+    VTC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, VTC_ERR_ARG, "hwp_seg: output must be 4-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    int bx = cdiv(H * W, 256 * 4);
-    if (bx < 1) bx = 1;
-    hwp_seg_kernel<<<dim3(bx, batch), 256, smem, stream>>>(cosm, p2c, bg_map, cos_thresh, bg_thresh, out, k, g, H, W);
+    hwp_seg_kernel<<<dim3(cdiv(H, PIX_ROWS), batch), PIX_THREADS, smem, stream>>>(cosm, p2c, bg_map, cos_thresh, bg_thresh, out, k, g, H, W);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }

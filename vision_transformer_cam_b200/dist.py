@@ -157,6 +157,77 @@ class SideStreamGather:
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
 
 
+class PeerPushGather:
+    """The same gather without a collective kernel: every rank WRITES its staged block straight into the result buffer of
+    every peer with plain device-to-device copies over NVLink (copy engines; no SM is taken from the persistent kernels of
+    the forward, which is what made the NCCL all-gather cost 7 % at 2 GPUs).  The result buffers are symmetric memory
+    (`torch.distributed._symmetric_memory`: one allocation per rank, mapped into every peer of the box), allocated by
+    `alloc()`.  Interface of SideStreamGather: `gather(out, local)` stages one step, every `every`-th call pushes the staged
+    steps on a side stream; `wait()` pushes what is left and makes the caller's stream wait for this rank's copies.  The
+    peers' copies into MY buffer are ordered by the next collective of the caller (bench.py: the all-reduce of the counters,
+    which every rank enqueues after its own `wait()`): when that collective has completed here, every peer had reached it,
+    i.e. had finished its pushes.  Raises at construction if symmetric memory cannot be set up (the caller then uses
+    SideStreamGather)."""
+
+    def __init__(self, device, every: int = 1, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.every = max(int(every), 1)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._stage = [None, None]
+        self._sent = [None, None]
+        self._flip = 0
+        self._k = 0
+        self._peers = None          # views of every peer's result buffer
+        self._out = None
+
+    def alloc(self, shape, dtype=torch.float32) -> torch.Tensor:
+        """Result buffer [world, every, ...] in symmetric memory; collective (every rank calls it with the same shape)."""
+        out = self._symm.empty(tuple(shape), dtype=dtype, device=self.device)
+        hdl = self._symm.rendezvous(out, self.group)
+        self._peers = [out if r == self.rank else hdl.get_buffer(r, tuple(shape), dtype) for r in range(self.world)]
+        self._hdl = hdl
+        self._out = out
+        return out
+
+    def gather(self, out: torch.Tensor, local: torch.Tensor) -> None:
+        assert self._out is not None and out.data_ptr() == self._out.data_ptr(), "out must come from alloc()"
+        cur = torch.cuda.current_stream(self.device)
+        st = self._stage[self._flip]
+        if st is None or st.shape[1:] != local.shape or st.dtype != local.dtype:
+            st = self._stage[self._flip] = torch.empty((self.every,) + tuple(local.shape), dtype=local.dtype, device=self.device)
+        if self._k == 0 and self._sent[self._flip] is not None:
+            cur.wait_event(self._sent[self._flip])
+        st[self._k].copy_(local)
+        self._k += 1
+        if self._k == self.every:
+            self._flush()
+
+    def _flush(self) -> None:
+        n = self._k
+        if n == 0:
+            return
+        st = self._stage[self._flip][:n]
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for r in range(self.world):
+                dst = self._peers[r].view(self.world, -1)[self.rank, : st.numel()]
+                dst.copy_(st.reshape(-1), non_blocking=True)          # contiguous same-dtype copy: cudaMemcpyAsync, peer-mapped destination
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._sent[self._flip] = ev
+        self._flip ^= 1
+        self._k = 0
+
+    def wait(self) -> None:
+        self._flush()
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 def reduce_counters(counters: torch.Tensor) -> torch.Tensor:
     """Sum int64 counters (21x21 confusion matrix, AP sum / count, top-1 hits ...) over all ranks, in place."""
     if rank_world()[1] > 1:
