@@ -478,61 +478,147 @@ __device__ __forceinline__ float bilerp(const float* m, int g, const Lerp& y, co
     return y.w0 * (x.w0 * m[y.i0 * g + x.i0] + x.w1 * m[y.i0 * g + x.i1]) + y.w1 * (x.w0 * m[y.i1 * g + x.i0] + x.w1 * m[y.i1 * g + x.i1]);
 }
 
-constexpr int PIX_ROWS = 16;          // output rows per block
+constexpr int PIX_ROWS = 32;          // output rows per block
+constexpr int PIX_RV = 4;             // consecutive rows per thread item (one quad of columns x PIX_RV rows = 16 pixels)
 constexpr int PIX_THREADS = 256;
-// x tables of a block: xi[x] = i0 | i1 << 16, xw[x] = weight of i1 (the weight of i0 is 1 - xw, as in lerp_coord)
-__device__ __forceinline__ void pix_fill_x(uint32_t* xi, float* xw, int W, int g) {
-    const float sx = static_cast<float>(g) / W;
+// Shared memory of a block: xi[W] (byte offset of source column i0) | xw[W] (weight of i0 + 1) | yi[PIX_ROWS] (byte offset of
+// source row i0) | yw[PIX_ROWS] (weight of row i0 + 1) | maps.  A source map is staged PADDED, (g+1) x (g+1) floats with its
+// last column and row duplicated, so that the second tap is always "+1 column" / "+1 row" (lerp_coord clamps i1 to i0 on the
+// border, where both taps then read the same value: identical arithmetic) and a sample needs ONE address computation.
+__device__ __forceinline__ int pix_pitch(int g) { return g + 1; }
+__device__ __forceinline__ float* pix_fill_tables(uint8_t* sm, int W, int H, int g, int y_first, uint32_t*& xi, float*& xw, uint32_t*& yi, float*& yw) {
+    xi = reinterpret_cast<uint32_t*>(sm);
+    xw = reinterpret_cast<float*>(xi + W);
+    yi = reinterpret_cast<uint32_t*>(xw + W);
+    yw = reinterpret_cast<float*>(yi + PIX_ROWS);
+    const float sx = static_cast<float>(g) / W, sy = static_cast<float>(g) / H;
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         const Lerp l = lerp_coord(x, sx, g);
-        xi[x] = static_cast<uint32_t>(l.i0) | (static_cast<uint32_t>(l.i1) << 16);
+        xi[x] = static_cast<uint32_t>(l.i0) * 4u;
         xw[x] = l.w1;
     }
+    if (threadIdx.x < PIX_ROWS) {
+        const Lerp l = lerp_coord(min(y_first + static_cast<int>(threadIdx.x), H - 1), sy, g);
+        yi[threadIdx.x] = static_cast<uint32_t>(l.i0 * pix_pitch(g)) * 4u;
+        yw[threadIdx.x] = l.w1;
+    }
+    return yw + PIX_ROWS;
 }
-__device__ __forceinline__ float pix_bilerp(const float* r0, const float* r1, float wy0, float wy1, uint32_t xi, float xw1) {
-    const int i0 = xi & 0xffffu, i1 = xi >> 16;
-    const float xw0 = 1.0f - xw1;
-    return wy0 * (xw0 * r0[i0] + xw1 * r0[i1]) + wy1 * (xw0 * r1[i0] + xw1 * r1[i1]);
+// stage `n` g x g maps (map k at src + k * src_stride floats) padded into dst
+__device__ __forceinline__ void pix_stage_maps(float* dst, const float* __restrict__ src, size_t src_stride, int n, int g) {
+    const int pitch = pix_pitch(g), pp = pitch * pitch;
+    for (int i = threadIdx.x; i < n * pp; i += blockDim.x) {
+        const int k = i / pp, r = i - k * pp, y = r / pitch, x = r - y * pitch;
+        dst[i] = src[k * src_stride + min(y, g - 1) * g + min(x, g - 1)];
+    }
 }
-static size_t pix_table_bytes(int W) { return static_cast<size_t>(W) * 8; }
+static size_t pix_table_bytes(int W) { return static_cast<size_t>(W) * 8 + PIX_ROWS * 8; }
+static size_t pix_map_bytes(int g, int n) { return sizeof(float) * static_cast<size_t>(n) * (g + 1) * (g + 1); }
+
+// One thread item: rows r0 .. r0+3 of the block x the four columns of one quad.
+struct PixItem {
+    uint32_t xo[4];        // byte offsets of the source columns
+    float xw[4];           // weights of column i0 + 1
+    uint32_t yo[PIX_RV];   // byte offsets of the source rows
+    float yw[PIX_RV];      // weights of row i0 + 1
+    bool same;             // the four rows lie in the same source cell
+    int r0, x0;
+};
+// item index -> item; false when it starts below the last row of the tile
+__device__ __forceinline__ bool pix_decode(int it, int quads, int rows, int W, const uint32_t* xi, const float* xw, const uint32_t* yi, const float* yw, PixItem& p) {
+    const int rg = it / quads;
+    p.r0 = rg * PIX_RV;
+    if (p.r0 >= rows) return false;
+    p.x0 = (it - rg * quads) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int x = min(p.x0 + e, W - 1);
+        p.xo[e] = xi[x];
+        p.xw[e] = xw[x];
+    }
+#pragma unroll
+    for (int r = 0; r < PIX_RV; ++r) {
+        p.yo[r] = yi[p.r0 + r];
+        p.yw[r] = yw[p.r0 + r];
+    }
+    p.same = (p.yo[1] == p.yo[0]) && (p.yo[2] == p.yo[0]) && (p.yo[3] == p.yo[0]);
+    return true;
+}
+// The 16 bilinear samples of an item of ONE padded map m: f(r, e, value).  When the four rows lie in the same source cell (26
+// of 27 row groups at 375 rows from a 14 x 14 map) the horizontal interpolation of the two source rows is done once for the
+// item (16 instead of 64 loads); the operation order per sample is the reference's in both paths (horizontal pair first, then
+// vertical).
+template <typename Fn>
+__device__ __forceinline__ void pix_item(const float* m, uint32_t pitch_bytes, const PixItem& p, Fn&& f) {
+    const uint8_t* mb = reinterpret_cast<const uint8_t*>(m);
+    if (p.same) {
+        float ha[4], hb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float* a = reinterpret_cast<const float*>(mb + p.yo[0] + p.xo[e]);
+            const float* c = reinterpret_cast<const float*>(mb + p.yo[0] + p.xo[e] + pitch_bytes);
+            const float w1 = p.xw[e], w0 = 1.0f - w1;
+            ha[e] = w0 * a[0] + w1 * a[1];
+            hb[e] = w0 * c[0] + w1 * c[1];
+        }
+#pragma unroll
+        for (int r = 0; r < PIX_RV; ++r) {
+            const float v1 = p.yw[r], v0 = 1.0f - v1;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f(r, e, v0 * ha[e] + v1 * hb[e]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < PIX_RV; ++r) {
+            const float v1 = p.yw[r], v0 = 1.0f - v1;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float* a = reinterpret_cast<const float*>(mb + p.yo[r] + p.xo[e]);
+                const float* c = reinterpret_cast<const float*>(mb + p.yo[r] + p.xo[e] + pitch_bytes);
+                const float w1 = p.xw[e], w0 = 1.0f - w1;
+                f(r, e, v0 * (w0 * a[0] + w1 * a[1]) + v1 * (w0 * c[0] + w1 * c[1]));
+            }
+        }
+    }
+}
+__device__ __forceinline__ void pix_store_u8(uint8_t* dst, uint32_t packed, int x0, int W, bool vec) {
+    if (vec) *reinterpret_cast<uint32_t*>(dst) = packed;
+    else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(packed >> (8 * e));
+}
 
 template <bool U8>
 __global__ void __launch_bounds__(PIX_THREADS) upsample_kernel(const float* __restrict__ in, void* __restrict__ out, int g, int H, int W) {
     extern __shared__ __align__(16) uint8_t pix_sm[];
-    uint32_t* xi = reinterpret_cast<uint32_t*>(pix_sm);
-    float* xw = reinterpret_cast<float*>(xi + W);
-    float* m = xw + W;                                   // [g*g]
-    const int n = blockIdx.y;
-    for (int i = threadIdx.x; i < g * g; i += blockDim.x) m[i] = in[static_cast<size_t>(n) * g * g + i];
-    pix_fill_x(xi, xw, W, g);
-    __syncthreads();
-    const float sy = static_cast<float>(g) / H;
+    uint32_t *xi, *yi;
+    float *xw, *yw;
     const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
+    float* m = pix_fill_tables(pix_sm, W, H, g, y_first, xi, xw, yi, yw);      // one padded map
+    const int n = blockIdx.y;
+    pix_stage_maps(m, in + static_cast<size_t>(n) * g * g, 0, 1, g);
+    __syncthreads();
+    const uint32_t pitch_bytes = pix_pitch(g) * 4;
     const int quads = (W + 3) >> 2;
     const size_t base = static_cast<size_t>(n) * H * W;
     const bool vec = (W & 3) == 0;
-    for (int it = threadIdx.x; it < rows * quads; it += blockDim.x) {
-        const int r = it / quads, x0 = (it - r * quads) * 4, y = y_first + r;
-        const Lerp ly = lerp_coord(y, sy, g);
-        const float* r0 = m + ly.i0 * g;
-        const float* r1 = m + ly.i1 * g;
-        float v[4];
+    for (int it = threadIdx.x; it < (PIX_ROWS / PIX_RV) * quads; it += blockDim.x) {
+        PixItem p;
+        if (!pix_decode(it, quads, rows, W, xi, xw, yi, yw, p)) break;
+        const int r0 = p.r0, x0 = p.x0;
+        float v[PIX_RV][4];
+        pix_item(m, pitch_bytes, p, [&](int r, int e, float s) { v[r][e] = s; });
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int x = min(x0 + e, W - 1);
-            v[e] = pix_bilerp(r0, r1, ly.w0, ly.w1, xi[x], xw[x]);
-        }
-        const size_t o = base + static_cast<size_t>(y) * W + x0;
-        if (U8) {                                          // .astype("uint8") truncation, predict.py:269
-            uint8_t* dst = static_cast<uint8_t*>(out) + o;
-            const uint32_t p = static_cast<uint32_t>(static_cast<uint8_t>(v[0] * 255.0f)) | (static_cast<uint32_t>(static_cast<uint8_t>(v[1] * 255.0f)) << 8) |
-                               (static_cast<uint32_t>(static_cast<uint8_t>(v[2] * 255.0f)) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(v[3] * 255.0f)) << 24);
-            if (vec) *reinterpret_cast<uint32_t*>(dst) = p;
-            else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(p >> (8 * e));
-        } else {
-            float* dst = static_cast<float*>(out) + o;
-            if (vec) st_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
-            else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = v[e];
+        for (int r = 0; r < PIX_RV; ++r) {
+            if (r0 + r >= rows) break;
+            const size_t o = base + static_cast<size_t>(y_first + r0 + r) * W + x0;
+            if (U8) {                                      // .astype("uint8") truncation, predict.py:269
+                const uint32_t p = static_cast<uint32_t>(static_cast<uint8_t>(v[r][0] * 255.0f)) | (static_cast<uint32_t>(static_cast<uint8_t>(v[r][1] * 255.0f)) << 8) |
+                                   (static_cast<uint32_t>(static_cast<uint8_t>(v[r][2] * 255.0f)) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(v[r][3] * 255.0f)) << 24);
+                pix_store_u8(static_cast<uint8_t*>(out) + o, p, x0, W, vec);
+            } else {
+                float* dst = static_cast<float*>(out) + o;
+                if (vec) st_f4(dst, make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+                else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = v[r][e];
+            }
         }
     }
 }
@@ -540,8 +626,8 @@ __global__ void __launch_bounds__(PIX_THREADS) upsample_kernel(const float* __re
 template <bool U8>
 static int upsample(const float* in, void* out, int n, int g, int H, int W, cudaStream_t stream) {
     VTC_REQUIRE(in && out, VTC_ERR_ARG, "upsample: null pointer");
-    const size_t smem = pix_table_bytes(W) + sizeof(float) * g * g;
-    VTC_REQUIRE(n > 0 && g > 0 && g < 65536 && H > 0 && W > 0 && smem <= 48 * 1024 && n <= 65535, VTC_ERR_SHAPE, "upsample: bad shape n=%d g=%d W=%d", n, g, W);
+    const size_t smem = pix_table_bytes(W) + pix_map_bytes(g, 1);
+    VTC_REQUIRE(n > 0 && g > 0 && g < 1024 && H > 0 && W > 0 && smem <= 48 * 1024 && n <= 65535, VTC_ERR_SHAPE, "upsample: bad shape n=%d g=%d W=%d", n, g, W);
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, VTC_ERR_ARG, "upsample: output must be 16-byte aligned");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
@@ -557,66 +643,59 @@ __global__ void __launch_bounds__(PIX_THREADS) cam_label_kernel(const float* __r
     extern __shared__ __align__(16) uint8_t pix_sm[];
     __shared__ int active[64];
     __shared__ int nactive;
-    uint32_t* xi = reinterpret_cast<uint32_t*>(pix_sm);
-    float* xw = reinterpret_cast<float*>(xi + W);
-    float* m = xw + W;                                   // [nactive][g*g]
+    uint32_t *xi, *yi;
+    float *xw, *yw;
+    const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
+    float* m = pix_fill_tables(pix_sm, W, H, g, y_first, xi, xw, yi, yw);      // [nactive] padded maps
     const int b = blockIdx.y;
-    const int gg = g * g;
+    const int gg = g * g, pp = pix_pitch(g) * pix_pitch(g);
+    const uint32_t pitch_bytes = pix_pitch(g) * 4;
     if (threadIdx.x == 0) {
         int k = 0;
         for (int c = 0; c < C; ++c)
             if (labels[b * C + c]) active[k++] = c;
         nactive = k;
     }
-    pix_fill_x(xi, xw, W, g);
     __syncthreads();
     const int na = nactive;
-    for (int i = threadIdx.x; i < na * gg; i += blockDim.x) {
-        const int k = i / gg;
-        m[i] = cam[(static_cast<size_t>(b) * C + active[k]) * gg + (i - k * gg)];
-    }
+    for (int k = 0; k < na; ++k) pix_stage_maps(m + k * pp, cam + (static_cast<size_t>(b) * C + active[k]) * gg, 0, 1, g);
     __syncthreads();
-    const float sy = static_cast<float>(g) / H;
-    const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
     const int quads = (W + 3) >> 2;
     const size_t base = static_cast<size_t>(b) * H * W;
     const bool vec = (W & 3) == 0;
-    for (int it = threadIdx.x; it < rows * quads; it += blockDim.x) {
-        const int r = it / quads, x0 = (it - r * quads) * 4, y = y_first + r;
-        const Lerp ly = lerp_coord(y, sy, g);
-        uint32_t xii[4];
-        float xww[4], best[4];
-        uint32_t lab = 0u;                                 // four labels, one per byte
+    for (int it = threadIdx.x; it < (PIX_ROWS / PIX_RV) * quads; it += blockDim.x) {
+        PixItem p;
+        if (!pix_decode(it, quads, rows, W, xi, xw, yi, yw, p)) break;
+        const int r0 = p.r0, x0 = p.x0;
+        float best[PIX_RV][4];
+        uint32_t lab[PIX_RV];                              // four labels per row, one per byte
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int x = min(x0 + e, W - 1);
-            xii[e] = xi[x];
-            xww[e] = xw[x];
-            best[e] = bg_thresh;
+        for (int r = 0; r < PIX_RV; ++r) {
+            lab[r] = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) best[r][e] = bg_thresh;
         }
         for (int k = 0; k < na; ++k) {
-            const float* r0 = m + k * gg + ly.i0 * g;
-            const float* r1 = m + k * gg + ly.i1 * g;
             const uint32_t code = static_cast<uint32_t>(active[k] + 1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float v = pix_bilerp(r0, r1, ly.w0, ly.w1, xii[e], xww[e]);
-                if (v > best[e]) {                        // strict: ties keep the earlier entry like torch.argmax
-                    best[e] = v;
-                    lab = (lab & ~(0xffu << (8 * e))) | (code << (8 * e));
+            pix_item(m + k * pp, pitch_bytes, p, [&](int r, int e, float s) {
+                if (s > best[r][e]) {                      // strict: ties keep the earlier entry like torch.argmax
+                    best[r][e] = s;
+                    lab[r] = (lab[r] & ~(0xffu << (8 * e))) | (code << (8 * e));
                 }
-            }
+            });
         }
-        uint8_t* dst = out + base + static_cast<size_t>(y) * W + x0;
-        if (vec) *reinterpret_cast<uint32_t*>(dst) = lab;
-        else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(lab >> (8 * e));
+#pragma unroll
+        for (int r = 0; r < PIX_RV; ++r) {
+            if (r0 + r >= rows) break;
+            pix_store_u8(out + base + static_cast<size_t>(y_first + r0 + r) * W + x0, lab[r], x0, W, vec);
+        }
     }
 }
 
 int cam_label(const float* cam, const uint8_t* labels, float bg_thresh, uint8_t* out, int batch, int classes, int g, int H, int W, cudaStream_t stream) {
     VTC_REQUIRE(cam && labels && out, VTC_ERR_ARG, "cam_label: null pointer");
-    VTC_REQUIRE(batch > 0 && batch <= 65535 && classes > 0 && classes <= 64 && g > 0 && g < 65536 && H > 0 && W > 0, VTC_ERR_SHAPE, "cam_label: bad shape");
-    const size_t smem = pix_table_bytes(W) + sizeof(float) * classes * g * g;
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && classes > 0 && classes <= 64 && g > 0 && g < 1024 && H > 0 && W > 0, VTC_ERR_SHAPE, "cam_label: bad shape");
+    const size_t smem = pix_table_bytes(W) + pix_map_bytes(g, classes);
     VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "cam_label: %zu bytes of smem", smem);
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, VTC_ERR_ARG, "cam_label: output must be 4-byte aligned");
     int rc = check_arch();
@@ -687,65 +766,62 @@ __global__ void __launch_bounds__(PIX_THREADS) hwp_seg_kernel(const float* __res
                                                              float cos_thresh, float bg_thresh, uint8_t* __restrict__ out, int K, int g, int H, int W) {
     extern __shared__ __align__(16) uint8_t pix_sm[];
     __shared__ int cls_s[HWP_MAXK];
-    uint32_t* xi = reinterpret_cast<uint32_t*>(pix_sm);
-    float* xw = reinterpret_cast<float*>(xi + W);
-    float* m = xw + W;                                   // [K][g*g] + [g*g]
-    const int b = blockIdx.y;
-    const int gg = g * g;
-    for (int i = threadIdx.x; i < K * gg; i += blockDim.x) m[i] = cosm[static_cast<size_t>(b) * K * gg + i];
-    for (int i = threadIdx.x; i < gg; i += blockDim.x) m[K * gg + i] = bg_map[static_cast<size_t>(b) * gg + i];
-    if (threadIdx.x < K) cls_s[threadIdx.x] = p2c[b * K + threadIdx.x];
-    pix_fill_x(xi, xw, W, g);
-    __syncthreads();
-    const float sy = static_cast<float>(g) / H;
+    uint32_t *xi, *yi;
+    float *xw, *yw;
     const int y_first = blockIdx.x * PIX_ROWS, rows = min(PIX_ROWS, H - y_first);
+    float* m = pix_fill_tables(pix_sm, W, H, g, y_first, xi, xw, yi, yw);      // K padded cosine maps + the padded background map
+    const int b = blockIdx.y;
+    const int gg = g * g, pp = pix_pitch(g) * pix_pitch(g);
+    const uint32_t pitch_bytes = pix_pitch(g) * 4;
+    pix_stage_maps(m, cosm + static_cast<size_t>(b) * K * gg, gg, K, g);
+    pix_stage_maps(m + K * pp, bg_map + static_cast<size_t>(b) * gg, 0, 1, g);
+    if (threadIdx.x < K) cls_s[threadIdx.x] = p2c[b * K + threadIdx.x];
+    __syncthreads();
     const int quads = (W + 3) >> 2;
     const size_t base = static_cast<size_t>(b) * H * W;
     const bool vec = (W & 3) == 0;
-    for (int it = threadIdx.x; it < rows * quads; it += blockDim.x) {
-        const int r = it / quads, x0 = (it - r * quads) * 4, y = y_first + r;
-        const Lerp ly = lerp_coord(y, sy, g);
-        uint32_t xii[4];
-        float xww[4], best[4];
-        int bk[4];
+    for (int it = threadIdx.x; it < (PIX_ROWS / PIX_RV) * quads; it += blockDim.x) {
+        PixItem p;
+        if (!pix_decode(it, quads, rows, W, xi, xw, yi, yw, p)) break;
+        const int r0 = p.r0, x0 = p.x0;
+        float best[PIX_RV][4];
+        uint32_t bk[PIX_RV];                               // arg max per pixel, one byte each
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int x = min(x0 + e, W - 1);
-            xii[e] = xi[x];
-            xww[e] = xw[x];
-            best[e] = -INFINITY;
-            bk[e] = 0;
+        for (int r = 0; r < PIX_RV; ++r) {
+            bk[r] = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) best[r][e] = -INFINITY;
         }
         for (int k = 0; k < K; ++k) {
-            const float* r0 = m + k * gg + ly.i0 * g;
-            const float* r1 = m + k * gg + ly.i1 * g;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float v = pix_bilerp(r0, r1, ly.w0, ly.w1, xii[e], xww[e]);
-                if (v > best[e]) { best[e] = v; bk[e] = k; }                      // validate.py:179-180
-            }
+            pix_item(m + k * pp, pitch_bytes, p, [&](int r, int e, float s) {
+                if (s > best[r][e]) {                      // validate.py:179-180
+                    best[r][e] = s;
+                    bk[r] = (bk[r] & ~(0xffu << (8 * e))) | (static_cast<uint32_t>(k) << (8 * e));
+                }
+            });
         }
-        const float* b0 = m + K * gg + ly.i0 * g;
-        const float* b1 = m + K * gg + ly.i1 * g;
-        uint32_t lab = 0u;
+        uint32_t lab[PIX_RV];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool fg = best[e] >= cos_thresh;                                                    // validate.py:183-186
-            const bool keep = pix_bilerp(b0, b1, ly.w0, ly.w1, xii[e], xww[e]) >= bg_thresh;          // validate.py:239-246
-            const int c = cls_s[bk[e]];
-            lab |= ((fg && keep && c >= 0) ? static_cast<uint32_t>(c + 1) : 0u) << (8 * e);         // validate.py:190-258
+        for (int r = 0; r < PIX_RV; ++r) lab[r] = 0u;
+        pix_item(m + K * pp, pitch_bytes, p, [&](int r, int e, float s) {
+            const bool fg = best[r][e] >= cos_thresh;                              // validate.py:183-186
+            const bool keep = s >= bg_thresh;                                      // validate.py:239-246
+            const int c = cls_s[(bk[r] >> (8 * e)) & 0xffu];
+            lab[r] |= ((fg && keep && c >= 0) ? static_cast<uint32_t>(c + 1) : 0u) << (8 * e);    // validate.py:190-258
+        });
+#pragma unroll
+        for (int r = 0; r < PIX_RV; ++r) {
+            if (r0 + r >= rows) break;
+            pix_store_u8(out + base + static_cast<size_t>(y_first + r0 + r) * W + x0, lab[r], x0, W, vec);
         }
-        uint8_t* dst = out + base + static_cast<size_t>(y) * W + x0;
-        if (vec) *reinterpret_cast<uint32_t*>(dst) = lab;
-        else for (int e = 0; e < 4 && x0 + e < W; ++e) dst[e] = static_cast<uint8_t>(lab >> (8 * e));
     }
 }
 
 int hwp_seg(const float* cosm, const int32_t* p2c, const float* bg_map, float cos_thresh, float bg_thresh, uint8_t* out, int batch, int k, int g,
             int H, int W, cudaStream_t stream) {
     VTC_REQUIRE(cosm && p2c && bg_map && out, VTC_ERR_ARG, "hwp_seg: null pointer");
-    VTC_REQUIRE(batch > 0 && batch <= 65535 && k > 0 && k <= HWP_MAXK && g > 0 && g < 65536 && H > 0 && W > 0, VTC_ERR_SHAPE, "hwp_seg: bad shape");
-    const size_t smem = pix_table_bytes(W) + sizeof(float) * (k + 1) * g * g;
+    VTC_REQUIRE(batch > 0 && batch <= 65535 && k > 0 && k <= HWP_MAXK && g > 0 && g < 1024 && H > 0 && W > 0, VTC_ERR_SHAPE, "hwp_seg: bad shape");
+    const size_t smem = pix_table_bytes(W) + pix_map_bytes(g, k + 1);
     VTC_REQUIRE(smem <= 48 * 1024, VTC_ERR_SHAPE, "hwp_seg: %zu bytes of smem", smem);
     VTC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, VTC_ERR_ARG, "hwp_seg: output must be 4-byte aligned");
     int rc = check_arch();
