@@ -40,3 +40,11 @@ for w in (0, 1, 2, 4, 5, 6, 8, 12):
 for w in (16, 17):
     print(f"MMA {w-16} mean (clk): " + "  ".join(f"{n} {float((d[:, :, w, k+1]-d[:, :, w, k]).mean()):.0f}" for k, n in enumerate(mma_names)),
           " period", float((d[:, 1:, w, 0] - d[:, :-1, w, 0]).mean()))
+print("---- absolute timeline of CTA %d (clk since step 0): softmax slots S_ready / chunks_done / p_arrive / O_ready / item_done; MMA slots QK_issued / P_ready / PV_issued" % cta)
+for s in range(4, 10):
+    for w, name in ((0, "g0 part0"), (4, "g0 part1"), (8, "g1 part0"), (12, "g1 part1")):
+        r = t[cta, s, w] - t0
+        print(f"  step {s} {name}: top {float(r[0]):8.0f}  S_ready {float(r[1]):8.0f}  chunks_done {float(r[2]):8.0f}  p_arrive {float(r[4]):8.0f}  O_ready {float(r[5]):8.0f}  done {float(r[6]):8.0f}")
+    for w in (16, 17):
+        r = t[cta, s, w] - t0
+        print(f"  step {s} MMA g{w-16}  : top {float(r[0]):8.0f}  O_free {float(r[1]):8.0f}  QK_issue {float(r[2]):8.0f}  QK_done_issue {float(r[3]):8.0f}  P_ready {float(r[4]):8.0f}  PV_issue {float(r[5]):8.0f}")
