@@ -47,4 +47,4 @@ for s in range(4, 10):
         print(f"  step {s} {name}: top {float(r[0]):8.0f}  S_ready {float(r[1]):8.0f}  chunks_done {float(r[2]):8.0f}  p_arrive {float(r[4]):8.0f}  O_ready {float(r[5]):8.0f}  done {float(r[6]):8.0f}")
     for w in (16, 17):
         r = t[cta, s, w] - t0
-        print(f"  step {s} MMA g{w-16}  : top {float(r[0]):8.0f}  O_free {float(r[1]):8.0f}  QK_issue {float(r[2]):8.0f}  QK_done_issue {float(r[3]):8.0f}  P_ready {float(r[4]):8.0f}  PV_issue {float(r[5]):8.0f}")
+        print(f"  step {s} MMA g{w-16}  : top {float(r[0]):8.0f}  O_free {float(r[1]):8.0f}  QK_issue {float(r[2]):8.0f}  QK_done_issue {float(r[3]):8.0f}  P_ready {float(r[4]):8.0f}  PV_issue {float(r[5]):8.0f}  | producer: K_load_issued {float(r[6]):8.0f}  V_load_issued {float(r[7]):8.0f}")

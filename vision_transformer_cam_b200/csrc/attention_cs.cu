@@ -318,11 +318,14 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     __syncwarp();
                 }
                 if (lane == 0) {
+                    unsigned long long* tr = (p.trace && step < 64) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + step) * (SM_WARPS + GROUPS) + SM_WARPS + g) * 8 : nullptr;
                     mbar_arrive_expect_tx(k_full, kv_bytes);
                     tma_load_3d(gsm + OFF_K, &tmKV, k_full, D + h * HD, j * KB, b);
+                    if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tr[6] = tt; }      // debug: K load issued
                     mbar_wait_fast(v_empty, ph ^ 1);
                     mbar_arrive_expect_tx(v_full, kv_bytes);
                     tma_load_3d(gsm + OFF_V, &tmKV, v_full, 2 * D + h * HD, j * KB, b);
+                    if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tr[7] = tt; }      // debug: V load issued
                 }
                 __syncwarp();
             }
