@@ -104,6 +104,22 @@ def test_dropin_module_surface_and_state_dict():
     pickle.loads(pickle.dumps(m2))
 
 
+def test_unsupported_constructor_arguments_are_rejected_not_ignored():
+    """The fused forward computes scale = head_dim ** -0.5, erf-GELU and LayerNorm; a constructor argument it cannot honour
+    must raise instead of being silently dropped (the module-level Attention would honour it, the fused path would not)."""
+    import torch.nn as nn
+    from functools import partial
+    import vision_transformer_cam_b200 as V
+    kw = dict(img_size=32, patch_size=16, embed_dim=256, depth=1, num_heads=4, num_classes=3)
+    V.VisionTransformer(**kw)                                              # fine
+    V.VisionTransformer(qk_scale=64 ** -0.5, **kw)                         # the default value spelled out: fine
+    V.VisionTransformer(norm_layer=partial(nn.LayerNorm, eps=1e-5), **kw)  # any eps: fine (passed to the kernels)
+    for bad in (dict(qk_scale=0.3), dict(act_layer=nn.ReLU), dict(norm_layer=nn.BatchNorm1d), dict(qkv_bias=False), dict(distilled=True),
+                dict(drop_ratio=0.1), dict(norm_layer=partial(nn.LayerNorm, elementwise_affine=False))):
+        with pytest.raises(NotImplementedError):
+            V.VisionTransformer(**bad, **kw)
+
+
 def test_shard_ranges_and_batches():
     from vision_transformer_cam_b200 import dist as D
     assert D.shard_sizes(10582, 8) == [1323] * 6 + [1322] * 2

@@ -106,3 +106,39 @@ def test_nccl_sharded_extraction_equals_single_rank(tmp_path, lib_built):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert all(f"rank {k} ok" in r.stdout for k in range(nproc)), r.stdout[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_single_process_model_on_second_device(lib_built):
+    """One process, two devices: a model living on cuda:1 runs while torch's current device is cuda:0 (the library keeps its
+    shared-memory opt-in per device and every op launches on the stream of the device its tensors live on), and gives the bits
+    of the same model on cuda:0."""
+    import vision_transformer_cam_b200 as V
+    from vision_transformer_cam_b200 import cam as CAM
+    from oracle import vit_forward as VF
+    torch.cuda.set_device(0)
+    torch.manual_seed(0)
+    m0 = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).eval()
+    sd = {k: v.clone() for k, v in m0.state_dict().items()}
+    m0 = m0.to("cuda:0")
+    torch.manual_seed(0)
+    m1 = V.vit_base_patch16_224_in21k(num_classes=20, has_logits=False).eval()
+    m1.load_state_dict(sd)
+    m1 = m1.to("cuda:1")
+    x = VF.make_images(0, 3)
+    a = m0.forward_cam(x.to("cuda:0"), rollout=True)
+    assert torch.cuda.current_device() == 0
+    b = m1.forward_cam(x.to("cuda:1"), rollout=True)              # first use of every kernel on device 1
+    assert b.logits.device == torch.device("cuda:1") and torch.cuda.current_device() == 0
+    assert torch.equal(a.logits.cpu(), b.logits.cpu()) and torch.equal(a.rollout.cpu(), b.rollout.cpu())
+    ca = CAM.classic_cam(a.tokens_last, m0.head1.weight.data)
+    cb = CAM.classic_cam(b.tokens_last, m1.head1.weight.data)     # ops.py wrappers on device 1 with device 0 current
+    lab = torch.zeros((3, 20)); lab[:, 3] = 1
+    la = CAM.cam_pseudo_label(ca, lab.to("cuda:0"), (64, 80))
+    lb = CAM.cam_pseudo_label(cb, lab.to("cuda:1"), (64, 80))
+    sa = CAM.hwp_pseudo_seg(a, m0.head1.weight.data, (64, 80))
+    sb = CAM.hwp_pseudo_seg(b, m1.head1.weight.data, (64, 80))
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert torch.equal(ca.cpu(), cb.cpu()) and torch.equal(la.cpu(), lb.cpu()) and torch.equal(sa.cpu(), sb.cpu())
+    with pytest.raises(RuntimeError):
+        CAM.classic_cam(a.tokens_last, m1.head1.weight.data)      # tensors on different devices: loud

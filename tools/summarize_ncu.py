@@ -121,7 +121,7 @@ def zoo(path, traffic_out=None):
             n = s[0]
             if "gemm2_bf16_kernel<0" in n or "gemm2_bf16_kernel<(int)0" in n: kinds["gemm_qkv"].append(s)
             elif "gemm2_bf16_kernel<1" in n or "gemm2_bf16_kernel<(int)1" in n: kinds["gemm_fc1"].append(s)
-            elif "gemm2_bf16_kernel<4" in n or "gemm2_bf16_kernel<(int)4" in n: kinds["gemm_patch"].append(s)
+            elif "gemm2_bf16_kernel<5" in n or "gemm2_bf16_kernel<(int)5" in n: kinds["gemm_patch"].append(s)
             elif s in resid: kinds["gemm_proj" if s[1] < med else "gemm_fc2"].append(s)
         for k, v in kinds.items():
             if v:
