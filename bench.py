@@ -378,7 +378,8 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
-        os.environ.setdefault("NCCL_MAX_CTAS", "2")    # the gather is 4 MB per step: two CTAs move it, the forward keeps 146 SMs
+        if world == 2:      # two ranks: NCCL would spread the 4 MB-per-step gather over many channels; two CTAs move it and the
+            os.environ.setdefault("NCCL_MAX_CTAS", "2")      # forward keeps 146 SMs.  (At 8 ranks the cap makes the collective itself slow.)
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -396,8 +397,8 @@ def main():
         cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)
         return o, cam
 
-    # The CAM gather: one NCCL all-gather per 8 steps on a side stream (dist.SideStreamGather; NCCL capped at two CTAs so that it
-    # takes at most two SMs from the persistent kernels of the forward).  VTC_BENCH_GATHER=push selects peer-to-peer pushes by the
+    # The CAM gather: one NCCL all-gather per 8 steps on a side stream (dist.SideStreamGather; at 2 ranks NCCL is capped at two CTAs
+    # so that it takes at most two SMs from the persistent kernels of the forward).  VTC_BENCH_GATHER=push selects peer-to-peer pushes by the
     # copy engines into symmetric memory instead (dist.PeerPushGather: no SM at all) -- measured at 2 GPUs: 11.15 ms per step
     # against 10.88 (NCCL) and 10.77 (NCCL, 2 CTAs); DESIGN.md section 6.
     from vision_transformer_cam_b200 import dist as VD
@@ -417,7 +418,7 @@ def main():
         if gatherer is None:
             gatherer = VD.SideStreamGather(dev, every=GATHER_EVERY)
             gathered = torch.empty((world, GATHER_EVERY, B, C, 14, 14), device=dev)
-            gather_kind = f"CAM maps all-gathered (NCCL, NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}) once per 8 steps on a side stream + at the end"
+            gather_kind = f"CAM maps all-gathered (NCCL, NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS', 'default')}) once per 8 steps on a side stream + at the end"
         config["collectives"] = gather_kind + "; int64 counters all-reduced (NCCL) at the end; all inside the timed region, none inside the forward"
 
     def step(x):
