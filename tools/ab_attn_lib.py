@@ -27,6 +27,8 @@ for rep in range(3):
             e1.record()
             torch.cuda.synchronize()
             print(f"{path.split('/')[-1]:24s} bias={'yes' if bias is not None else 'no '}: {e0.elapsed_time(e1) * 100:.1f} us")
+if os.environ.get("VTC_AB_PLAIN_ONLY") == "1":
+    sys.exit(0)
 print("---- vtc_attention_mean (attention + packed P + head mean)")
 Z = ctypes.c_size_t
 mean = torch.empty((B, N, N), device=dev)

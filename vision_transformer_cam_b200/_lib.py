@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvtc.so")
+LIB_PATH = os.environ.get("VTC_LIB_PATH") or os.path.join(HERE, "libvtc.so")      # VTC_LIB_PATH: an instrumented build (tools/build_ablate.sh)
 
 VTC_OK = 0
 ERR_NAMES = {-1: "VTC_ERR_ARG", -2: "VTC_ERR_SHAPE", -3: "VTC_ERR_ARCH", -4: "VTC_ERR_CUDA", -5: "VTC_ERR_WORKSPACE"}

@@ -38,6 +38,13 @@
 namespace vtc {
 
 namespace acs {
+// Ablation switches for timing experiments (tools/ab_attn_lib.py on libraries built with -DVTC_ACS_ABLATE=k; results are WRONG
+// by construction): bit 0 = no softmax arithmetic (a chunk is stored back as loaded), bit 1 = no tcgen05.ld of the scores,
+// bit 2 = one P V k-step instead of all, bit 3 = no tcgen05.ld of O in the epilogue.  0 in every shipped build.
+#ifndef VTC_ACS_ABLATE
+#define VTC_ACS_ABLATE 0
+#endif
+constexpr int ABLATE = VTC_ACS_ABLATE;
 constexpr int HD = 64;
 constexpr int NMAX = 2048;
 constexpr int KBMAX = 208;                 // keys per block when the whole sequence fits one block
@@ -62,10 +69,27 @@ constexpr int OFF_V = OFF_K + KV_BYTES;
 constexpr int OFF_QAUG = OFF_V + KV_BYTES;
 constexpr int OFF_KAUG = OFF_QAUG + QAUG_BYTES;
 constexpr int GROUP_BYTES = ((OFF_KAUG + KAUG_BYTES + 1023) / 1024) * 1024;
-constexpr int OFF_CLS = GROUPS * GROUP_BYTES;                  // [GROUPS][NMAX] floats: raw logits of the CLS row
+// Output staging: the normalised bf16 O tile of an item (128 rows x 128 B, 128-byte swizzle) leaves through ONE bulk tensor
+// store per item.  Stored straight from registers, a lane's 64 bytes go to a different 128-byte line than its neighbours'
+// (token rows are 2 D bytes apart): 32 memory transactions per store instruction, and the timeline showed the eight warps of a
+// group queueing on the load-store unit for ~1,000 clk per item (profiles/r02_attention_trace.txt, "done" -> next "top").
+#ifndef VTC_ACS_TMA_OUT
+#define VTC_ACS_TMA_OUT 1
+#endif
+constexpr bool OUT_TMA = VTC_ACS_TMA_OUT != 0;
+constexpr int OST_BYTES = 128 * 128;
+constexpr int OFF_OST = GROUPS * GROUP_BYTES;                  // [GROUPS][OST_BYTES]
+constexpr int OFF_CLS = OFF_OST + GROUPS * OST_BYTES;          // [GROUPS][NMAX] floats: raw logits of the CLS row
 constexpr int OFF_XCH = OFF_CLS + GROUPS * NMAX * 4;           // [GROUPS][PARTS][128 rows] float2 (m, sum)
 constexpr int OFF_BAR = OFF_XCH + GROUPS * PARTS * 128 * 8;
-constexpr int BARS_PER_GROUP = 10;
+constexpr int BARS_PER_GROUP = 11;
+// Experiment kept in the tree (off by default: measured no gain): -DVTC_ACS_EARLY_QK=1 issues the score MMA of the
+// next item in two pieces so that it does not wait for the epilogue of the current one.  Only S columns >= O_COL overlap the O
+// accumulator: keys [0, O_COL) go straight behind P V of the previous item (in-order tensor pipe), the <= 16 keys beyond once
+// the softmax warps have read O out (second barrier s_tail, waited on only before a warp's chunk that starts at O_COL).
+#ifndef VTC_ACS_EARLY_QK
+#define VTC_ACS_EARLY_QK 0
+#endif
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && KV_BYTES % 1024 == 0 && GROUP_BYTES % 1024 == 0, "swizzle atoms need 1024-byte tiles");
 static_assert(SMEM_BYTES <= 232448, "attention_cs smem budget");
@@ -214,7 +238,8 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
 // fold away at compile time.
 template <bool DUMP, bool SINGLE>
 __global__ void __launch_bounds__(THREADS, 1)
-attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const Params p) {
+attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO,
+                    const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5;
@@ -232,6 +257,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* p_full = bars + 7;     // P(s) stored by all softmax warps of the group
     uint64_t* o_full = bars + 8;     // O of an item complete
     uint64_t* o_empty = bars + 9;    // O of an item read out (all softmax warps of the group)
+    uint64_t* s_tail = bars + 10;    // EARLY_QK: S columns [O_COL, nmma) of an item ready
+    constexpr bool EARLY_QK = (VTC_ACS_EARLY_QK != 0) && !(DUMP && SINGLE);      // the single-block packed-P epilogue still reads P from the S columns
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + GROUPS * BARS_PER_GROUP * 8);
     uint8_t* gsm = smem + g * GROUP_BYTES;
 
@@ -261,6 +288,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmKV);
+            tma_prefetch_desc(&tmO);
             uint64_t* all = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
             for (int gg = 0; gg < GROUPS; ++gg)
                 for (int i = 0; i < BARS_PER_GROUP; ++i) mbar_init(all + gg * BARS_PER_GROUP + i, (i == 7 || i == 9) ? GROUP_WARPS : 1);      // p_full, o_empty: one arrival per softmax warp
@@ -356,18 +384,33 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tr[slot] = tt; }
                     };
                     stamp(0);
-                    if (j == 0 && i > 0) mbar_wait_fast(o_empty, (i - 1) & 1);
+                    if (!EARLY_QK && j == 0 && i > 0) mbar_wait_fast(o_empty, (i - 1) & 1);
                     stamp(1);
                     mbar_wait_fast(k_full, ph);
                     tc_fence_after();
                     stamp(2);
-                    const uint32_t idesc_s = make_idesc_bf16(128, nmma, 0, 0);
+                    const int n_main = (EARLY_QK && nmma > O_COL) ? O_COL : nmma;
+                    const uint32_t idesc_s = make_idesc_bf16(128, n_main, 0, 0);
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
                         umma_bf16(tmem_base, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s,
                                   k != 0 ? 1u : 0u);
                     if (has_bias) umma_bf16(tmem_base, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr, 256, 128, 0), idesc_s, 1u);
                     umma_commit(s_full);
+                    if constexpr (EARLY_QK) {
+                        // O of the previous item must have been read out before S reaches into its columns and before P V overwrites it
+                        if (j == 0 && i > 0) mbar_wait_fast(o_empty, (i - 1) & 1);
+                        if (n_main < nmma) {
+                            const uint32_t idesc_t = make_idesc_bf16(128, nmma - O_COL, 0, 0);
+                            const uint32_t k_tail = k_addr + O_COL * 128;          // key row O_COL: a whole number of 8-row swizzle atoms
+#pragma unroll
+                            for (int k = 0; k < HD / 16; ++k)
+                                umma_bf16(tmem_base + O_COL, make_smem_desc_sw128(q_addr + k * 32, 1024, 16), make_smem_desc_sw128(k_tail + k * 32, 1024, 16),
+                                          idesc_t, k != 0 ? 1u : 0u);
+                            if (has_bias) umma_bf16(tmem_base + O_COL, make_smem_desc(qa_addr, 256, 128, 0), make_smem_desc(ka_addr + (O_COL >> 3) * 256, 256, 128, 0), idesc_t, 1u);
+                            umma_commit(s_tail);
+                        }
+                    }
                     umma_commit(k_empty);
                     if (j == nb - 1) umma_commit(q_empty);
                     // ---- O (+)= P(s) V(s)
@@ -377,7 +420,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     mbar_wait_fast(v_full, ph);
                     tc_fence_after();
                     stamp(5);
-                    const int ksteps = nmma >> 4;
+                    const int ksteps = (ABLATE & 4) ? 1 : (nmma >> 4);
                     // every part packs its bf16 P from (16 columns past) its own first S column on: chunk c of the part that starts at
                     // chunk pb sits at column 32 pb + 16 (c - pb) + 16, i.e. k-step ks reads column 16 + 8 ks + 16 pb
                     static_assert(PARTS == 2, "the P address below assumes two column parts");
@@ -448,11 +491,30 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     for (int c = c0; c < c1; ++c) {
                         uint32_t cur[32];
                         const int nvalid = vj - c * 32;
-                        if (nvalid > 16) tmem_ld_32x32b_x32(t_s + c * 32, cur);
-                        else tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
-                        tmem_ld_wait();
-                        chunk<DUMP_LOOP>(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
-                                         (DUMP_LOOP && erow) ? erow + j * KB + c * 32 : nullptr, (DUMP_LOOP && mrow) ? mrow + ((j * KB) >> 5) + c : nullptr);
+                        if constexpr (EARLY_QK) {
+                            if (c * 32 >= O_COL) {          // these columns come from the second piece of Q K^T (one per item)
+                                mbar_wait_fast(s_tail, i & 1);
+                                tc_fence_after();
+                            }
+                        }
+                        if constexpr ((ABLATE & 2) != 0) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) cur[q] = __float_as_uint(static_cast<float>(q + lane) * 0.01f);
+                        } else {
+                            if (nvalid > 16) tmem_ld_32x32b_x32(t_s + c * 32, cur);
+                            else tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
+                            tmem_ld_wait();
+                        }
+                        if constexpr ((ABLATE & 1) != 0) {
+                            uint32_t pk0[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) pk0[q] = cur[q] & 0x3f803f80u;
+                            tmem_st_32x32b_x16(t_p + (c - c0) * 16, pk0);
+                            sum2 = add2(sum2, pack2(1.0f, 1.0f));
+                        } else {
+                            chunk<DUMP_LOOP>(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
+                                             (DUMP_LOOP && erow) ? erow + j * KB + c * 32 : nullptr, (DUMP_LOOP && mrow) ? mrow + ((j * KB) >> 5) + c : nullptr);
+                        }
                     }
                     stamp(2);
                     // ---- the warps that share these rows agree on the row maximum (and, at the end, on the row sum)
@@ -508,8 +570,13 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tc_fence_after();
             if (warp_active) {
                 uint32_t o[OCOLS];
-                tmem_ld_cols(t_s + O_COL + part * OCOLS, o);
-                tmem_ld_wait();
+                if constexpr ((ABLATE & 8) != 0) {
+#pragma unroll
+                    for (int q = 0; q < OCOLS; ++q) o[q] = __float_as_uint(static_cast<float>(q + lane));
+                } else {
+                    tmem_ld_cols(t_s + O_COL + part * OCOLS, o);
+                    tmem_ld_wait();
+                }
                 if constexpr (DUMP && SINGLE) {
                     // the bf16 exponentials of my column range are still in TMEM (P V has retired): one 64-byte row segment per
                     // 32-key chunk, two full 32-byte sectors per lane
@@ -538,18 +605,37 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_empty);
                 if (row < N) {
+                    // OUT_TMA: my 64 bytes of the staged tile row (16-byte chunk index XOR row % 8: the 128-byte swizzle of the store's
+                    // tensor map; a quarter warp writes eight different chunks: no bank conflict)
+                    uint8_t* srow = smem + OFF_OST + g * OST_BYTES + r_local * 128;
                     __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * N + row) * D + h * HD + part * OCOLS;
 #pragma unroll
-                    for (int g4 = 0; g4 < OCOLS / 8; ++g4)
-                        st_u4(dst + 8 * g4, make_uint4(pack_bf16x2(__uint_as_float(o[8 * g4]) * inv, __uint_as_float(o[8 * g4 + 1]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 2]) * inv, __uint_as_float(o[8 * g4 + 3]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 4]) * inv, __uint_as_float(o[8 * g4 + 5]) * inv),
-                                                       pack_bf16x2(__uint_as_float(o[8 * g4 + 6]) * inv, __uint_as_float(o[8 * g4 + 7]) * inv)));
+                    for (int g4 = 0; g4 < OCOLS / 8; ++g4) {
+                        const uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[8 * g4]) * inv, __uint_as_float(o[8 * g4 + 1]) * inv),
+                                                   pack_bf16x2(__uint_as_float(o[8 * g4 + 2]) * inv, __uint_as_float(o[8 * g4 + 3]) * inv),
+                                                   pack_bf16x2(__uint_as_float(o[8 * g4 + 4]) * inv, __uint_as_float(o[8 * g4 + 5]) * inv),
+                                                   pack_bf16x2(__uint_as_float(o[8 * g4 + 6]) * inv, __uint_as_float(o[8 * g4 + 7]) * inv));
+                        if constexpr (OUT_TMA) st_u4(srow + (((part * (OCOLS / 8) + g4) ^ (r_local & 7)) << 4), v);
+                        else st_u4(dst + 8 * g4, v);
+                    }
                 }
             } else {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_empty);
+            }
+            if constexpr (OUT_TMA) {
+                // all eight warps of the group have staged their rows -> one thread stores the tile (token rows >= N are clipped by
+                // the tensor map).  The staging tile is reused by the next item: the storing thread waits until the store has READ it;
+                // that wait is ordered before every later write by this thread's own arrival on p_full of the next item (-> P V ->
+                // o_full, which every warp waits for before it gets here again).
+                fence_proxy_async_smem();
+                named_bar_sync(9 + g, GROUP_WARPS * 32);
+                if ((warp % GROUP_WARPS) == 0 && lane == 0) {
+                    tma_store_3d(&tmO, smem + OFF_OST + g * OST_BYTES, h * HD, qt * 128, b);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                }
             }
             if (cls_warp) named_bar_sync(row_bar, 32 * PARTS);     // the CLS staging buffer may be overwritten by the next item
             if (tre) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tre[6] = tt; }
@@ -602,12 +688,16 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     const int D = heads * HD;
     uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)n_tokens, (uint64_t)batch};
     uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)n_tokens * 3 * D * 2};
-    CUtensorMap tmQ, tmKV;
+    CUtensorMap tmQ, tmKV, tmO;
     uint32_t boxq[3] = {HD, 128, 1};
     uint32_t boxkv[3] = {HD, static_cast<uint32_t>(p.KB), 1};
     rc = make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq);
     if (rc != VTC_OK) return rc;
     rc = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxkv);
+    if (rc != VTC_OK) return rc;
+    uint64_t odims[3] = {(uint64_t)D, (uint64_t)n_tokens, (uint64_t)batch};
+    uint64_t ostrides[2] = {(uint64_t)D * 2, (uint64_t)n_tokens * D * 2};
+    rc = make_tmap_bf16(&tmO, out, 3, odims, ostrides, boxq);
     if (rc != VTC_OK) return rc;
     static SmemOptIn optin[4];
     if ((rc = optin[0].ensure(reinterpret_cast<const void*>(attention_cs_kernel<false, false>), SMEM_BYTES)) != VTC_OK) return rc;
@@ -618,10 +708,10 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     int grid = cdiv(items, GROUPS);
     if (grid > device_sm_count()) grid = device_sm_count();
     const bool single = p.nb == 1;
-    if (packed && single) attention_cs_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
-    else if (packed) attention_cs_kernel<true, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
-    else if (single) attention_cs_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
-    else attention_cs_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+    if (packed && single) attention_cs_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, p);
+    else if (packed) attention_cs_kernel<true, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, p);
+    else if (single) attention_cs_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, p);
+    else attention_cs_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, p);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
