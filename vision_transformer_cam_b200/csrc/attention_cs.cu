@@ -164,6 +164,11 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
     if (nvalid >= 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) mc = fmaxf(mc, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+    } else if (nvalid <= 8) {
+        // short tail (197 tokens: 5 keys): eight columns, branch-free (the generic partial-chunk path below costs as much as a
+        // full chunk, and this chunk sits on the critical path of the column part that owns it)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mc = fmaxf(mc, j < nvalid ? __uint_as_float(cur[j]) : -INFINITY);
     } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -201,6 +206,15 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
             pk[(j >> 1) + 1] = pack_bf16x2(e[j + 2], e[j + 3]);
         }
         sum2 = add2(sum2, add2(sa, sb));
+    } else if (nvalid <= 8) {
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? ex2_approx(fmaf(__uint_as_float(cur[j]), sc, negm)) : 0.f;
+        sum2 = add2(sum2, add2(add2(pack2(e[0], e[1]), pack2(e[2], e[3])), add2(pack2(e[4], e[5]), pack2(e[6], e[7]))));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+#pragma unroll
+        for (int j = 4; j < 16; ++j) pk[j] = 0u;
     } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -502,7 +516,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             for (int q = 0; q < 32; ++q) cur[q] = __float_as_uint(static_cast<float>(q + lane) * 0.01f);
                         } else {
                             if (nvalid > 16) tmem_ld_32x32b_x32(t_s + c * 32, cur);
-                            else tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
+                            else if (nvalid > 8) tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
+                            else tmem_ld_32x32b_x8(t_s + c * 32, reinterpret_cast<uint32_t(&)[8]>(cur));
                             tmem_ld_wait();
                         }
                         if constexpr ((ABLATE & 1) != 0) {
