@@ -269,6 +269,20 @@ VTC_API int vtc_cls_stat(const float* cls_rows, float* cls_map, float* gmax, int
  * per_image); key_bias[b,0] = 0, key_bias[b,1+p] = -100*bg.  forced_bg [B,P] overrides the decision when non-NULL. */
 VTC_API int vtc_cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image,
                  uint8_t* bg, float* key_bias, int32_t batch, int32_t n_tokens, void* stream);
+/* vtc_cls_stat + vtc_cls_mask in ONE launch (what the forward runs per layer >= mask_from): `ticket` = one zeroed uint32 per
+ * call (left non-zero); batch must not exceed what is resident at once (else the two kernels are launched).  mask_operands
+ * (optional, zeroed once by the caller, batch * vtc_attention_mask_operand_bytes(n_tokens) bytes): the additive mask of
+ * vit_model.py:348-361 as the ready-made tensor-core operands of the fast attention kernel, K_aug[key] = bias / scale and
+ * Q_aug[row] = [row not masked] (inv_scale = 1 / attention scale), which vtc_attention_masked then fetches with bulk copies
+ * instead of rebuilding them from key_bias for every (head, query tile). */
+VTC_API size_t vtc_attention_mask_operand_bytes(int32_t n_tokens);
+VTC_API int vtc_cls_stat_mask(const float* cls_rows, float* cls_map, float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image,
+                      uint8_t* bg, float* key_bias, uint32_t* ticket, void* mask_operands, float inv_scale, int32_t batch, int32_t heads,
+                      int32_t n_tokens, void* stream);
+/* vtc_attention (fast path: no full P) with the precomputed mask operands of vtc_cls_stat_mask; bit-identical to
+ * vtc_attention(qkv, key_bias, ...) */
+VTC_API int vtc_attention_masked(const void* qkv, const float* key_bias, const void* mask_operands, void* out, float* cls_rows, int32_t batch,
+                         int32_t n_tokens, int32_t heads, float scale, void* stream);
 /* high-weight-patch head + final norm + head (vit_model.py:374-422). tokens [B,N,D] fp32 (block-L output).  The top-16
  * runs on cls_map / max exactly like vit_model.py:372,377 (max = gmax[0], the batch-global one, or the image's own when
  * gmax is NULL): descending, ties to the smaller index, NaN ranked first (torch.topk). */

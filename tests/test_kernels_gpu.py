@@ -271,6 +271,33 @@ def test_cls_stat_and_mask(dev):
     assert torch.equal(bg_f, forced)
 
 
+@pytest.mark.parametrize("B,N,H", [(5, 197, 12), (3, 785, 12), (2, 577, 16), (4, 50, 12)])
+def test_cls_stat_mask_one_launch_and_precomputed_mask_operands(dev, B, N, H):
+    """The forward's one-launch mask builder == cls_stat + cls_mask, and the fast attention kernel fed with the mask operands it
+    precomputes (bulk copies in the producer) is BIT-IDENTICAL to the kernel that rebuilds them from key_bias per item."""
+    from vision_transformer_cam_b200 import ops
+    g = torch.Generator().manual_seed(70 + N)
+    cls_rows = torch.rand((B, H, N), generator=g).softmax(-1)
+    cls_rows[:, :, 5:N // 3] *= 6
+    cls_rows = (cls_rows / cls_rows.sum(-1, keepdim=True)).contiguous().to(dev)
+    cmap0, gmax0 = ops.cls_stat(cls_rows)
+    for per_image in (False, True):
+        bg0, kb0 = ops.cls_mask(cmap0, gmax0, 0.25, per_image=per_image)
+        cmap, gmax, bg, kb, aug = ops.cls_stat_mask(cls_rows, 0.25, per_image=per_image, scale=0.125)
+        assert torch.equal(cmap, cmap0) and torch.equal(gmax, gmax0) and torch.equal(bg, bg0) and torch.equal(kb, kb0)
+        assert 0.05 < float(bg.float().mean()) < 0.95
+        qkv = (_rand((B, N, 3 * H * 64), 71, dev) * 1.5).bfloat16()
+        o0, c0, _ = ops.attention(qkv, H, 0.125, key_bias=kb)
+        o1, c1 = ops.attention_masked(qkv, H, 0.125, kb, aug)
+        assert torch.equal(o0, o1) and torch.equal(c0, c1)
+    forced = (torch.arange(B * (N - 1)).reshape(B, N - 1) % 3 == 0).to(torch.uint8).to(dev)
+    _, _, bgf, kbf, augf = ops.cls_stat_mask(cls_rows, 0.25, forced_bg=forced, scale=0.125)
+    assert torch.equal(bgf, forced)
+    o0, c0, _ = ops.attention(qkv, H, 0.125, key_bias=kbf)
+    o1, c1 = ops.attention_masked(qkv, H, 0.125, kbf, augf)
+    assert torch.equal(o0, o1) and torch.equal(c0, c1)
+
+
 def test_topk_heads_bit_exact(dev):
     """vit_model.py:372-393 is index work: on the reference's own CLS maps (golden c_last of the B = 256 runs, where the
     batch-global max of :372 spans 256 images) `vtc_topk_heads` must return torch.topk's indices IN ORDER, gather the

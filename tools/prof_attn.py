@@ -26,3 +26,20 @@ for bias in (None, kb):
     us = e0.elapsed_time(e1) * 100
     print(f"N={N} H={H} B={B} bias={'yes' if bias is not None else 'no'} kv={kv}: {us:.1f} us / call, "
           f"{4 * H * N * N * 64 * B / us / 1e6:.1f} TFLOP/s")
+
+if not kv:
+    # masked layers as the forward runs them: mask operands precomputed once per layer by cls_stat_mask, fetched by bulk copies
+    from vision_transformer_cam_b200 import _lib
+    aug = torch.zeros((B, int(_lib.load().vtc_attention_mask_operand_bytes(N))), dtype=torch.uint8, device=dev)
+    cls_rows = torch.rand((B, H, N), device=dev).softmax(-1).contiguous()
+    _, _, _, kb2, aug = ops.cls_stat_mask(cls_rows, 0.9, scale=0.125)
+    for _ in range(3):
+        ops.attention_masked(qkv, H, 0.125, kb2, aug)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.attention_masked(qkv, H, 0.125, kb2, aug)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"N={N} H={H} B={B} bias=yes (precomputed mask operands, bg fraction {float((kb2 != 0).float().mean()):.2f}): {e0.elapsed_time(e1) * 100:.1f} us / call")

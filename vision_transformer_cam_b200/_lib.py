@@ -97,6 +97,9 @@ SIGNATURES = {
     "vtc_cls_stat": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "vtc_cls_mask": (C.c_int, [_P, _P, _P, _F, _I, _P, _P, _I, _I, _P]),
     "vtc_topk_heads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "vtc_attention_mask_operand_bytes": (_Z, [_I]),
+    "vtc_cls_stat_mask": (C.c_int, [_P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _F, _I, _I, _I, _P]),
+    "vtc_attention_masked": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "vtc_rollout": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "vtc_rollout_operand_ld": (C.c_int32, [_I]),
     "vtc_rollout_operand_from_mean": (C.c_int, [_P, _P, _I, _I, _P]),

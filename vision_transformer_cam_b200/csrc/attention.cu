@@ -386,12 +386,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_out, int batch, int n_tokens, int heads,
-              float scale, cudaStream_t stream, int reverse) {
+              float scale, cudaStream_t stream, int reverse, const void* aug) {
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
     VTC_REQUIRE(scale > 0.f, VTC_ERR_ARG, "attention: scale must be positive");
     if (attn_out == nullptr)              // fast path: two-group column-split kernel (attention_cs.cu), any sequence length
-        return attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse);
+        return attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, nullptr, aug);
     if (n_tokens > attn2::MAXN)           // full P of long sequences: KV-blocked two-sweep kernel (attention_kv.cu)
         return attention_kv(qkv, key_bias, out, cls_rows, attn_out, batch, n_tokens, heads, scale, false, stream, reverse);
     // full P, N <= 256: the whole row of scores sits in TMEM, the normalised probabilities are a third read of it
@@ -582,11 +582,11 @@ size_t attention_mean_scratch_bytes(int batch, int n_tokens, int heads) {
 
 int attention_mean(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* scratch, size_t scratch_bytes,
                    int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse) {
-    return attention_mean_operand(qkv, key_bias, out, cls_rows, attn_mean, nullptr, scratch, scratch_bytes, batch, n_tokens, heads, scale, stream, reverse);
+    return attention_mean_operand(qkv, key_bias, out, cls_rows, attn_mean, nullptr, scratch, scratch_bytes, batch, n_tokens, heads, scale, stream, reverse, nullptr);
 }
 
 int attention_mean_operand(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* operand, void* scratch,
-                           size_t scratch_bytes, int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse) {
+                           size_t scratch_bytes, int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse, const void* aug) {
     VTC_REQUIRE(qkv && out && (attn_mean || operand) && scratch, VTC_ERR_ARG, "attention_mean: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention_mean: bad shape");
     VTC_REQUIRE(n_tokens <= kAttentionFusedMeanMaxTokens, VTC_ERR_SHAPE, "attention_mean: %d tokens > %d", n_tokens, kAttentionFusedMeanMaxTokens);
@@ -594,7 +594,7 @@ int attention_mean_operand(const void* qkv, const float* key_bias, void* out, fl
     size_t need = 0;
     const PackedP pk = carve_packed(scratch, batch, n_tokens, heads, &need);
     VTC_REQUIRE(scratch_bytes >= need, VTC_ERR_WORKSPACE, "attention_mean: scratch %zu bytes < required %zu", scratch_bytes, need);
-    int rc = attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, &pk);
+    int rc = attention_cs(qkv, key_bias, out, cls_rows, batch, n_tokens, heads, scale, stream, reverse, &pk, aug);
     if (rc != VTC_OK) return rc;
     if (attn_mean && (rc = head_mean_packed(pk, attn_mean, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream)) != VTC_OK) return rc;
     if (operand && (rc = head_mean_packed_operand(pk, operand, batch, heads, n_tokens, attention_packed_ld(n_tokens), stream)) != VTC_OK) return rc;
@@ -609,6 +609,10 @@ __attribute__((visibility("default"))) void vtc_debug_set_attention_trace(void* 
 int vtc_attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int32_t batch, int32_t n_tokens,
                   int32_t heads, float scale, void* stream) {
     return vtc::attention(qkv, key_bias, out, cls_rows, attn, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream), 0);
+}
+int vtc_attention_masked(const void* qkv, const float* key_bias, const void* mask_operands, void* out, float* cls_rows, int32_t batch, int32_t n_tokens,
+                         int32_t heads, float scale, void* stream) {
+    return vtc::attention(qkv, key_bias, out, cls_rows, nullptr, batch, n_tokens, heads, scale, static_cast<cudaStream_t>(stream), 0, mask_operands);
 }
 size_t vtc_attention_mean_scratch_bytes(int32_t batch, int32_t n_tokens, int32_t heads) {
     return vtc::attention_mean_scratch_bytes(batch, n_tokens, heads);

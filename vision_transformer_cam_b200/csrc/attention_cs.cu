@@ -97,6 +97,8 @@ static_assert(KBLONG <= O_COL && KBMAX + 16 <= REGION_COLS, "TMEM region layout"
 
 struct Params {
     const float* key_bias;   // [B,N] or null
+    const uint8_t* aug;      // precomputed mask operands of every image (ops.h: AugLayout) or null: then the producer builds them from key_bias
+    size_t aug_per_image;
     __nv_bfloat16* out;      // [B,N,H*64]
     float* cls_rows;         // [B,H,N] or null
     // Head-mean support ("packed P"): the un-normalised bf16 exponentials E the P V product consumes and 1 / rowsum;
@@ -283,6 +285,10 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int first = GROUPS * static_cast<int>(blockIdx.x) + g, stride = GROUPS * static_cast<int>(gridDim.x);
     const int my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
     const bool has_bias = p.key_bias != nullptr;
+#ifndef VTC_ACS_NO_PREAUG
+#define VTC_ACS_NO_PREAUG 0
+#endif
+    const bool pre_aug = (VTC_ACS_NO_PREAUG == 0) && has_bias && p.aug != nullptr;      // (the macro: A/B of the producer code, tools/build_ablate.sh)
     const int D = H * HD;
     const uint32_t kv_bytes = static_cast<uint32_t>(KB) * 128u;
     // With an even number of query tiles per (image, head) the tile index of `first + i * stride` would be the same for every
@@ -326,7 +332,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float* kb = has_bias ? p.key_bias + static_cast<size_t>(b) * N : nullptr;
             if (lane == 0) mbar_wait_fast(q_empty, (i & 1) ^ 1);
             __syncwarp();
-            if (has_bias) {
+            if (has_bias && !pre_aug) {
                 // no-swizzle K-major core matrices: 8 rows x 16 B, LBO (K direction) 128 B, SBO (8-row groups) 256 B
                 uint8_t* qa = gsm + OFF_QAUG;
                 for (int r = lane; r < 128; r += 32) {
@@ -340,14 +346,17 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 __syncwarp();
             }
             if (lane == 0) {
-                mbar_arrive_expect_tx(q_full, Q_BYTES);
+                mbar_arrive_expect_tx(q_full, Q_BYTES + (pre_aug ? QAUG_BYTES : 0));
                 tma_load_3d(gsm + OFF_Q, &tmQ, q_full, h * HD, qt * 128, b);
+                if (pre_aug)      // the image's precomputed Q_aug tile (written once per layer by cls_stat_mask): a bulk copy, no generic stores
+                    bulk_load_1d(gsm + OFF_QAUG, p.aug + static_cast<size_t>(b) * p.aug_per_image + static_cast<size_t>(nb) * KB * 32 + static_cast<size_t>(qt) * QAUG_BYTES,
+                                 QAUG_BYTES, q_full);
             }
             for (int j = 0; j < nb; ++j, ++step) {
                 const uint32_t ph = step & 1;
                 if (lane == 0) mbar_wait_fast(k_empty, ph ^ 1);
                 __syncwarp();
-                if (has_bias) {
+                if (has_bias && !pre_aug) {
                     uint8_t* ka = gsm + OFF_KAUG;
                     for (int r = lane; r < KB; r += 32) {
                         const int key = j * KB + r;
@@ -361,8 +370,10 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 if (lane == 0) {
                     unsigned long long* tr = (p.trace && step < 64) ? p.trace + ((static_cast<size_t>(blockIdx.x) * 64 + step) * (SM_WARPS + GROUPS) + SM_WARPS + g) * 8 : nullptr;
-                    mbar_arrive_expect_tx(k_full, kv_bytes);
+                    mbar_arrive_expect_tx(k_full, kv_bytes + (pre_aug ? static_cast<uint32_t>(KB) * 32u : 0u));
                     tma_load_3d(gsm + OFF_K, &tmKV, k_full, D + h * HD, j * KB, b);
+                    if (pre_aug)
+                        bulk_load_1d(gsm + OFF_KAUG, p.aug + static_cast<size_t>(b) * p.aug_per_image + static_cast<size_t>(j) * KB * 32, static_cast<uint32_t>(KB) * 32u, k_full);
                     if (tr) { unsigned long long tt; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt)); tr[6] = tt; }      // debug: K load issued
                     mbar_wait_fast(v_empty, ph ^ 1);
                     mbar_arrive_expect_tx(v_full, kv_bytes);
@@ -664,7 +675,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }  // namespace acs
 
 int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
-                 cudaStream_t stream, int reverse, const PackedP* packed) {
+                 cudaStream_t stream, int reverse, const PackedP* packed, const void* aug) {
     using namespace acs;
     VTC_REQUIRE(qkv && out, VTC_ERR_ARG, "attention: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 0, VTC_ERR_SHAPE, "attention: bad shape");
@@ -676,6 +687,7 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     if (rc != VTC_OK) return rc;
     Params p{};
     p.key_bias = key_bias;
+    p.aug = key_bias ? static_cast<const uint8_t*>(aug) : nullptr;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.cls_rows = cls_rows;
     if (packed) {
@@ -693,6 +705,12 @@ int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_r
     } else {
         p.nb = cdiv(n_tokens, KBLONG);
         p.KB = (cdiv(n_tokens, p.nb) + 31) & ~31;
+    }
+    {
+        const AugLayout al = attention_aug_layout(n_tokens);
+        VTC_REQUIRE(al.KB == p.KB && al.nb == p.nb, VTC_ERR_SHAPE, "attention: mask-operand layout out of sync with the key blocking");
+        VTC_REQUIRE(!p.aug || (reinterpret_cast<uintptr_t>(p.aug) & 15) == 0, VTC_ERR_ARG, "attention: mask operands must be 16-byte aligned");
+        p.aug_per_image = al.per_image;
     }
     p.lde = attention_packed_ld(n_tokens);
     VTC_REQUIRE(p.lde == (p.nb == 1 ? ((n_tokens + 31) & ~31) : p.nb * p.KB), VTC_ERR_SHAPE, "attention: packed-P row stride out of sync with the key blocking");

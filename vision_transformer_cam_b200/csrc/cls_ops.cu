@@ -105,7 +105,8 @@ int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, 
 // its own image.  `ticket`: one zeroed unsigned int per launch (the forward zeroes one per layer next to gmax).
 __global__ void __launch_bounds__(256) cls_stat_mask_kernel(const float* __restrict__ cls_rows, float* __restrict__ cls_map, float* __restrict__ gmax,
                                                             const uint8_t* __restrict__ forced, float thresh, int per_image, uint8_t* __restrict__ bg,
-                                                            float* __restrict__ key_bias, unsigned int* __restrict__ ticket, int B, int H, int N) {
+                                                            float* __restrict__ key_bias, unsigned int* __restrict__ ticket, int B, int H, int N,
+                                                            uint8_t* __restrict__ aug, AugLayout al, float inv_scale) {
     __shared__ float red[32];
     __shared__ float mapv[2048];       // this image's map (n_tokens <= 2049, checked by the host)
     const int b = blockIdx.x;
@@ -142,35 +143,56 @@ __global__ void __launch_bounds__(256) cls_stat_mask_kernel(const float* __restr
     } else if (threadIdx.x == 0) {
         atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));          // topk_heads may still want the batch-global value
     }
-    if (threadIdx.x == 0) key_bias[static_cast<size_t>(b) * N] = 0.f;
+    // mask operands of the fast attention kernel (ops.h: AugLayout): K_aug[key] = bias / scale, Q_aug[row] = [row not masked];
+    // only the first bf16 of a row's first 16-byte half ever changes (the buffer was zeroed at the start of the forward)
+    uint8_t* ak = aug ? aug + static_cast<size_t>(b) * al.per_image : nullptr;
+    uint8_t* aq = aug ? ak + al.nb * al.k_block_bytes : nullptr;
+    auto put_aug = [&](int token, bool masked) {
+        const int jb = token / al.KB, rk = token - jb * al.KB;
+        *reinterpret_cast<uint32_t*>(ak + jb * al.k_block_bytes + (rk >> 3) * 256 + (rk & 7) * 16) = pack_bf16x2(masked ? -100.0f * inv_scale : 0.f, 0.f);
+        const int qt = token >> 7, rq = token & 127;
+        *reinterpret_cast<uint32_t*>(aq + qt * al.q_tile_bytes + (rq >> 3) * 256 + (rq & 7) * 16) = pack_bf16x2(masked ? 0.f : 1.0f, 0.f);
+    };
+    if (threadIdx.x == 0) {
+        key_bias[static_cast<size_t>(b) * N] = 0.f;
+        if (aug) put_aug(0, false);
+    }
     for (int j = threadIdx.x; j < P; j += blockDim.x) {
         const size_t e = static_cast<size_t>(b) * P + j;
         const uint8_t isbg = forced ? (forced[e] != 0) : ((mapv[j] / mx) < thresh);          // torch.lt(mask_14 / max, 0.25)
         if (bg != nullptr) bg[e] = isbg;
         key_bias[static_cast<size_t>(b) * N + 1 + j] = isbg ? -100.0f : 0.0f;
+        if (aug) put_aug(1 + j, isbg != 0);
     }
 }
 
+// largest batch the one-launch kernel serves on the current device: every block of the grid must be resident at the same time
+int cls_stat_mask_capacity() {
+    static std::atomic<int> per_sm[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int bps = (dev >= 0 && dev < 64) ? per_sm[dev].load(std::memory_order_relaxed) : 0;
+    if (bps == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cls_stat_mask_kernel, 256, 0) != cudaSuccess) return 0;
+        if (dev >= 0 && dev < 64) per_sm[dev].store(bps, std::memory_order_relaxed);
+    }
+    return bps * device_sm_count();
+}
+
 int cls_stat_mask(const float* cls_rows, float* cls_map, float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
-                  float* key_bias, unsigned int* ticket, int batch, int heads, int n_tokens, cudaStream_t stream) {
+                  float* key_bias, unsigned int* ticket, int batch, int heads, int n_tokens, cudaStream_t stream, void* aug, float inv_scale) {
     VTC_REQUIRE(cls_rows && cls_map && gmax && key_bias && ticket, VTC_ERR_ARG, "cls_stat_mask: null pointer");
     VTC_REQUIRE(batch > 0 && heads > 0 && n_tokens > 1, VTC_ERR_SHAPE, "cls_stat_mask: bad shape");
     int rc = check_arch();
     if (rc != VTC_OK) return rc;
-    // the wait on the ticket needs every block of the grid resident at the same time
-    static std::atomic<int> per_sm[64];
-    int dev = 0;
-    VTC_CUDA(cudaGetDevice(&dev));
-    int bps = (dev >= 0 && dev < 64) ? per_sm[dev].load(std::memory_order_relaxed) : 0;
-    if (bps == 0) {
-        VTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cls_stat_mask_kernel, 256, 0));
-        if (dev >= 0 && dev < 64) per_sm[dev].store(bps, std::memory_order_relaxed);
-    }
-    if (n_tokens - 1 > 2048 || static_cast<long long>(batch) > static_cast<long long>(bps) * device_sm_count()) {
+    const int capacity = cls_stat_mask_capacity();
+    VTC_REQUIRE(!aug || (n_tokens - 1 <= 2048 && batch <= capacity), VTC_ERR_SHAPE, "cls_stat_mask: mask operands need the one-launch path (batch %d)", batch);
+    if (n_tokens - 1 > 2048 || batch > capacity) {
         if ((rc = cls_stat(cls_rows, cls_map, gmax, batch, heads, n_tokens, stream)) != VTC_OK) return rc;
         return cls_mask(cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, batch, n_tokens, stream);
     }
-    cls_stat_mask_kernel<<<batch, 256, 0, stream>>>(cls_rows, cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, ticket, batch, heads, n_tokens);
+    cls_stat_mask_kernel<<<batch, 256, 0, stream>>>(cls_rows, cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, ticket, batch, heads, n_tokens,
+                                                    static_cast<uint8_t*>(aug), attention_aug_layout(n_tokens), inv_scale);
     VTC_CHECK_LAUNCH();
     return VTC_OK;
 }
@@ -311,6 +333,12 @@ int topk_heads(const HeadParams& hp, const float* tokens, const float* cls_map, 
 extern "C" {
 int vtc_cls_stat(const float* cls_rows, float* cls_map, float* gmax, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
     return vtc::cls_stat(cls_rows, cls_map, gmax, batch, heads, n_tokens, static_cast<cudaStream_t>(stream));
+}
+size_t vtc_attention_mask_operand_bytes(int32_t n_tokens) { return n_tokens > 0 ? vtc::attention_aug_layout(n_tokens).per_image : 0; }
+int vtc_cls_stat_mask(const float* cls_rows, float* cls_map, float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image, uint8_t* bg,
+                      float* key_bias, uint32_t* ticket, void* mask_operands, float inv_scale, int32_t batch, int32_t heads, int32_t n_tokens, void* stream) {
+    return vtc::cls_stat_mask(cls_rows, cls_map, gmax, forced_bg, thresh, per_image, bg, key_bias, ticket, batch, heads, n_tokens,
+                              static_cast<cudaStream_t>(stream), mask_operands, inv_scale);
 }
 int vtc_cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int32_t per_image, uint8_t* bg,
                  float* key_bias, int32_t batch, int32_t n_tokens, void* stream) {

@@ -63,6 +63,8 @@ struct Workspace {
     __nv_bfloat16 *hbuf, *patches, *y, *qkv, *ao;
     float *tok, *cls_rows, *cls_map, *key_bias, *gmax, *attn_tmp, *stats, *mean_tmp;
     unsigned int* ticket;        // cls_stat_mask: one arrival counter per layer (zeroed with gmax)
+    uint8_t* aug;                // attention mask operands of every image (ops.h: AugLayout), bf16 fast path only
+    size_t aug_bytes;
     void* mean_scratch;          // packed P of attention_mean
     size_t mean_scratch_bytes;
     __nv_bfloat16* rollops;      // rollout operands of the last min(L,12) layers [Lr,B,N,ldr] (ops.h)
@@ -92,6 +94,8 @@ static Workspace carve(const vtc_model* m, int B, const vtc_outputs* o, uint8_t*
     ws.gmax = reinterpret_cast<float*>(take(2 * m->L, 4));
     ws.ticket = ws.gmax ? reinterpret_cast<unsigned int*>(ws.gmax + m->L) : nullptr;
     ws.stats = reinterpret_cast<float*>(take(M * (D / 128) * 2, 4));       // LayerNorm row statistics (bf16 mode)
+    ws.aug_bytes = (!m->split && m->HD == 64 && m->L > m->cfg.mask_from + 1) ? static_cast<size_t>(B) * attention_aug_layout(m->N).per_image : 0;
+    ws.aug = ws.aug_bytes ? take(ws.aug_bytes, 1) : nullptr;
     const bool want_mean = o && (o->attn_mean || o->rollout);
     const bool need_mean = want_mean && !(o->attn && o->attn_layers >= m->L);       // some layer's mean is not a by-product of its full P
     ws.attn_tmp = (need_mean && !fused_mean_ok(m)) ? reinterpret_cast<float*>(take(static_cast<size_t>(B) * m->H * N * N, 4)) : nullptr;
@@ -180,6 +184,10 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
     VTC_STEP(VTC_PROF_PATCHIFY, cls_token_rows(m->w.cls_token, m->w.pos_embed, t_cur, B, N, D, st));
     VTC_STEP(VTC_PROF_GEMM_PATCH, gemm_bf16(ws.patches, m->patch_w, m->w.patch_b, nullptr, m->w.pos_embed, t_cur, B * P, D, m->KP, VTC_EPI_PATCH_EMBED, N, st, sp));
     VTC_CUDA(cudaMemsetAsync(ws.gmax, 0, sizeof(float) * 2 * L, st));      // + the per-layer tickets of cls_stat_mask
+    // mask operands: written per layer by cls_stat_mask (one launch, every block resident), fetched by the attention producer
+    const bool use_aug = ws.aug != nullptr && B <= cls_stat_mask_capacity() && N - 1 <= 2048;
+    if (use_aug) VTC_CUDA(cudaMemsetAsync(ws.aug, 0, ws.aug_bytes, st));
+    const void* aug = use_aug ? ws.aug : nullptr;
     if (o->bg) VTC_CUDA(cudaMemsetAsync(o->bg, 0, static_cast<size_t>(L) * B * P, st));
 
     bool have_bias = false;
@@ -215,8 +223,8 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             // LayerNorm lives inside the GEMMs: ws.y = bf16(residual stream), ws.stats = its row statistics (gemm.cu)
             VTC_STEP(VTC_PROF_GEMM_QKV, gemm_lnfold(ws.y, pw.qkv, pw.qkv_c, pw.qkv_g, ws.stats, m->cfg.ln_eps, ws.qkv, M, 3 * D, D, 0, st, next_dir()));
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                   // vit_model.py:118
-            if (packed_mean) VTC_STEP(VTC_PROF_ATTENTION, attention_mean_operand(ws.qkv, kb, ws.ao, cls_l, mean_l, op_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
-            else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
+            if (packed_mean) VTC_STEP(VTC_PROF_ATTENTION, attention_mean_operand(ws.qkv, kb, ws.ao, cls_l, mean_l, op_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir(), aug));
+            else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir(), aug));
             if (fuse_proj) {
                 VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_resid_ln(ws.ao, pw.proj, w.proj_b, t_in, t_out, ws.y, ws.stats, M, D, D, st, next_dir()));
             } else {      // A/B: proj through the L2 reduction + a row pass that produces bf16(t) and its statistics
@@ -231,8 +239,8 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             const float* kb = (l > m->cfg.mask_from && have_bias) ? ws.key_bias : nullptr;                       // vit_model.py:118
             if (m->HD != 64) VTC_STEP(VTC_PROF_ATTENTION, attention_generic(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, m->HD, scale, st));
             else if (sp) VTC_STEP(VTC_PROF_ATTENTION, attention_kv(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, true, st, next_dir()));
-            else if (packed_mean) VTC_STEP(VTC_PROF_ATTENTION, attention_mean_operand(ws.qkv, kb, ws.ao, cls_l, mean_l, op_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir()));
-            else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir()));
+            else if (packed_mean) VTC_STEP(VTC_PROF_ATTENTION, attention_mean_operand(ws.qkv, kb, ws.ao, cls_l, mean_l, op_l, ws.mean_scratch, ws.mean_scratch_bytes, B, N, H, scale, st, next_dir(), aug));
+            else VTC_STEP(VTC_PROF_ATTENTION, attention(ws.qkv, kb, ws.ao, cls_l, attn_l, B, N, H, scale, st, next_dir(), aug));
             VTC_STEP(VTC_PROF_GEMM_PROJ, gemm_bf16(ws.ao, pw.proj, w.proj_b, t_in, nullptr, t_out, M, D, D, VTC_EPI_BIAS_RESIDUAL, 0, st, sp, next_dir()));
             VTC_STEP(VTC_PROF_LAYERNORM, layernorm_bf16(t_out, w.norm2_w, w.norm2_b, ws.y, M, D, m->cfg.ln_eps, st, sp, next_dir()));
             VTC_STEP(VTC_PROF_GEMM_FC1, gemm_bf16(ws.y, pw.fc1, w.fc1_b, nullptr, nullptr, ws.hbuf, M, HID, D, VTC_EPI_BIAS_GELU, 0, st, sp, next_dir()));
@@ -251,7 +259,7 @@ static int forward(vtc_model* m, const ImageInput& in, int B, const vtc_outputs*
             if (l >= m->cfg.mask_from) {                                                                        // vit_model.py:325
                 const uint8_t* forced = (f && f->bg && (f->bg_layer_mask >> l & 1u)) ? f->bg + static_cast<size_t>(l) * B * P : nullptr;
                 uint8_t* bg_l = o->bg ? o->bg + static_cast<size_t>(l) * B * P : nullptr;
-                VTC_STEP(VTC_PROF_CLS, cls_stat_mask(cls_l, map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, ws.ticket + l, B, H, N, st));
+                VTC_STEP(VTC_PROF_CLS, cls_stat_mask(cls_l, map_l, ws.gmax + l, forced, m->cfg.mask_thresh, per_image, bg_l, ws.key_bias, ws.ticket + l, B, H, N, st, use_aug ? ws.aug : nullptr, 1.0f / scale));
                 have_bias = true;
             } else {
                 VTC_STEP(VTC_PROF_CLS, cls_stat(cls_l, map_l, ws.gmax + l, B, H, N, st));

@@ -31,8 +31,29 @@ int patchify_u8(const uint8_t* x, const float* mean, const float* std, void* pat
 int cls_token_rows(const float* cls_token, const float* pos_embed, float* tokens, int batch, int n_tokens, int dim, cudaStream_t stream);
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int dim, float eps, cudaStream_t stream,
                    int split = 0, int reverse = 0);
+// Precomputed mask operands of the fast attention kernel (attention_cs.cu applies the reference's additive mask through one
+// extra tensor-core K-step with Q_aug[i] = [v_i == 0], K_aug[j] = key_bias[j] / scale).  cls_stat_mask writes them per image in
+// the exact shared-memory image of that K-step (no-swizzle core matrices: row r at (r >> 3) * 256 + (r & 7) * 16, second
+// 16-byte half 128 bytes further, always zero), so that the attention producer fetches them with two bulk copies per item
+// instead of rebuilding them with generic stores for every (head, query tile): image b at aug + b * per_image =
+// [nb key blocks x KB rows x 32 B] then [qtiles x 128 rows x 32 B].  The buffer must be zeroed once (padding rows / halves).
+struct AugLayout {
+    int KB, nb, qtiles;
+    size_t k_block_bytes, q_tile_bytes, per_image;
+};
+constexpr int kAttentionSingleBlockKeysFwd = 208, kAttentionLongBlockKeysFwd = 192;      // == kAttentionSingleBlockKeys / kAttentionLongBlockKeys below
+inline AugLayout attention_aug_layout(int n_tokens) {
+    AugLayout a{};
+    if (n_tokens <= kAttentionSingleBlockKeysFwd) { a.nb = 1; a.KB = (n_tokens + 15) & ~15; }
+    else { a.nb = (n_tokens + kAttentionLongBlockKeysFwd - 1) / kAttentionLongBlockKeysFwd; a.KB = (((n_tokens + a.nb - 1) / a.nb) + 31) & ~31; }
+    a.qtiles = (n_tokens + 127) / 128;
+    a.k_block_bytes = static_cast<size_t>(a.KB) * 32;
+    a.q_tile_bytes = 128 * 32;
+    a.per_image = a.nb * a.k_block_bytes + a.qtiles * a.q_tile_bytes;
+    return a;
+}
 int attention(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
-              float scale, cudaStream_t stream, int reverse = 0);
+              float scale, cudaStream_t stream, int reverse = 0, const void* aug = nullptr);
 // Attention + head mean of P (the rollout's input, predict.py:189-190) without a [B,H,N,N] fp32 round trip, any n_tokens the
 // fast kernel serves: it stores the bf16 exponentials it feeds to P V ("packed P", see attention_cs.cu) into `scratch`
 // (attention_mean_scratch_bytes), head_mean_packed reduces them over the heads into attn_mean [B,N,N].
@@ -62,7 +83,8 @@ inline int rollout_operand_ld(int n_tokens) { return (n_tokens + 2 + 7) / 8 * 8;
 int head_mean_packed_operand(const PackedP& packed, void* operand, int batch, int heads, int n_tokens, int ld, cudaStream_t stream);
 // attention_mean writing the rollout operand instead of (mean == nullptr) or next to the fp32 mean
 int attention_mean_operand(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn_mean, void* operand, void* scratch,
-                           size_t scratch_bytes, int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse = 0);
+                           size_t scratch_bytes, int batch, int n_tokens, int heads, float scale, cudaStream_t stream, int reverse = 0,
+                           const void* aug = nullptr);
 // fp32 [B,N,N] head mean -> rollout operand (the path of the full-P / fp32-mode / general-shape forwards)
 int rollout_operand_from_mean(const float* mean, void* operand, int batch, int n_tokens, cudaStream_t stream);
 // r <- e0^T A_{L-1} ... A_0 from `layers` rollout operands [layers,B,N,ldr]; row [B,N-1]
@@ -74,7 +96,7 @@ int attention_kv(const void* qkv, const float* key_bias, void* out, float* cls_r
 // column-split pipelined kernel (attention_cs.cu): the fast path when the full P is not requested, any n_tokens <= 2048
 // packed: optional packed-P output (row stride attention_packed_ld(N)) for attention_mean
 int attention_cs(const void* qkv, const float* key_bias, void* out, float* cls_rows, int batch, int n_tokens, int heads, float scale,
-                 cudaStream_t stream, int reverse = 0, const PackedP* packed = nullptr);
+                 cudaStream_t stream, int reverse = 0, const PackedP* packed = nullptr, const void* aug = nullptr);
 // general-shape path (attention_generic.cu): head_dim a multiple of 16 up to 128, n_tokens <= 320; same outputs as `attention`
 int attention_generic(const void* qkv, const float* key_bias, void* out, float* cls_rows, float* attn, int batch, int n_tokens, int heads,
                       int head_dim, float scale, cudaStream_t stream);
@@ -85,8 +107,11 @@ int cls_stat(const float* cls_rows, float* cls_map, float* gmax, int batch, int 
 int cls_mask(const float* cls_map, const float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
              float* key_bias, int batch, int n_tokens, cudaStream_t stream);
 // both in one launch (the forward); `ticket`: a zeroed unsigned int that the kernel leaves zeroed
+int cls_stat_mask_capacity();      // largest batch of the one-launch kernel on the current device
+// aug (optional): the attention mask operands of every image (attention_aug_layout), inv_scale = 1 / attention scale
 int cls_stat_mask(const float* cls_rows, float* cls_map, float* gmax, const uint8_t* forced_bg, float thresh, int per_image, uint8_t* bg,
-                  float* key_bias, unsigned int* ticket, int batch, int heads, int n_tokens, cudaStream_t stream);
+                  float* key_bias, unsigned int* ticket, int batch, int heads, int n_tokens, cudaStream_t stream, void* aug = nullptr,
+                  float inv_scale = 0.f);
 
 struct HeadParams {
     const float* norm_w; const float* norm_b;

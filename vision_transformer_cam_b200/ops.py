@@ -208,6 +208,35 @@ def cls_mask(cls_map: torch.Tensor, gmax: torch.Tensor, thresh: float = 0.25, pe
     return bg, kb
 
 
+def cls_stat_mask(cls_rows: torch.Tensor, thresh: float = 0.25, per_image: bool = False, forced_bg: Optional[torch.Tensor] = None,
+                  scale: Optional[float] = None):
+    """cls_stat + cls_mask in one launch (the forward's kernel): -> (cls_map [B,P], gmax [1], bg [B,P] u8, key_bias [B,N], mask
+    operands uint8 [B, bytes] of the fast attention kernel when `scale` (the attention scale) is given, else None)."""
+    B, H, N = cls_rows.shape
+    dev = cls_rows.device
+    cmap = torch.empty((B, N - 1), dtype=torch.float32, device=dev)
+    gmax = torch.zeros((1,), dtype=torch.float32, device=dev)
+    bg = torch.empty((B, N - 1), dtype=torch.uint8, device=dev)
+    kb = torch.empty((B, N), dtype=torch.float32, device=dev)
+    ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
+    aug = None
+    if scale is not None:
+        aug = torch.zeros((B, int(_lib.load().vtc_attention_mask_operand_bytes(N))), dtype=torch.uint8, device=dev)
+    _call("vtc_cls_stat_mask", _ptr(cls_rows, torch.float32, "cls_rows"), _ptr(cmap), _ptr(gmax), _ptr(forced_bg, torch.uint8), thresh, int(per_image),
+          _ptr(bg), _ptr(kb), _ptr(ticket), _ptr(aug), (1.0 / scale) if scale is not None else 0.0, B, H, N)
+    return cmap, gmax, bg, kb, aug
+
+
+def attention_masked(qkv: torch.Tensor, heads: int, scale: float, key_bias: torch.Tensor, mask_operands: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fast attention with the precomputed mask operands of `cls_stat_mask` (what the forward does): (out, cls_rows)."""
+    B, N, D3 = qkv.shape
+    out = torch.empty((B, N, D3 // 3), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device)
+    _call("vtc_attention_masked", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(key_bias, torch.float32, "key_bias"), _ptr(mask_operands, torch.uint8, "mask_operands"),
+          _ptr(out), _ptr(cls), B, N, heads, scale)
+    return out, cls
+
+
 def rollout(attn_mean: torch.Tensor) -> torch.Tensor:
     """attn_mean [L,B,N,N] fp32 -> un-normalised rollout row [B,N-1] (predict.py:215-232)."""
     L, B, N, _ = attn_mean.shape
