@@ -8,6 +8,15 @@ python -m vision_transformer_cam_b200.build > /dev/null
 mkdir -p tools/ab
 OBJS=$(ls vision_transformer_cam_b200/build/*.o | grep -v attention_cs.o)
 for k in "$@"; do
+  if [[ $k == g* ]]; then      # gN: GEMM ablation N (gemm.cu: VTC_GEMM_ABLATE), timed with VTC_LIB_PATH=... python tools/prof_gemm.py
+    n=${k#g}
+    GOBJS=$(ls vision_transformer_cam_b200/build/*.o | grep -v "/gemm.o")
+    /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
+        -DVTC_GEMM_ABLATE=$n -c vision_transformer_cam_b200/csrc/gemm.cu -o /tmp/gemm_ablate$n.o
+    /usr/local/cuda/bin/nvcc -shared -o tools/ab/libvtc_gemm_ablate$n.so $GOBJS /tmp/gemm_ablate$n.o -gencode arch=compute_100a,code=sm_100a -cudart static
+    echo built tools/ab/libvtc_gemm_ablate$n.so
+    continue
+  fi
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
       -DVTC_ACS_ABLATE=$((k % 100)) -DVTC_ACS_EARLY_QK=$(((k / 100) % 10)) -DVTC_ACS_TMA_OUT=$((1 - (k / 1000) % 10)) -DVTC_ACS_NO_PREAUG=$((k / 10000)) -c vision_transformer_cam_b200/csrc/attention_cs.cu -o /tmp/acs_ablate$k.o
   /usr/local/cuda/bin/nvcc -shared -o tools/ab/libvtc_ablate$k.so $OBJS /tmp/acs_ablate$k.o -gencode arch=compute_100a,code=sm_100a -cudart static

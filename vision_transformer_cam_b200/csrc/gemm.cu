@@ -229,6 +229,16 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const gem
 //   fp32 residual stream   cp.reduce.async.bulk.tensor .add of 128x32 boxes: out += acc + bias happens in L2, the SMs
 //                          never read the residual.
 namespace gemm2 {
+// Ablation switches for timing experiments (libraries built with -DVTC_GEMM_ABLATE=k, tools/build_ablate.sh gK; results WRONG by
+// construction): bit 0 = no GELU arithmetic in the fc1 epilogue, bit 1 = no staging + bulk store of the bf16 output tiles,
+// bit 2 = no tcgen05.ld of the accumulator in the bf16-output epilogues.  0 in every shipped build.  Measured (B = 256, us per
+// launch): qkv 141 whatever is removed (the epilogue is hidden: operand-feed / MMA bound); fc1 195-206 -> 182 without the GELU
+// arithmetic, 176 with the whole epilogue removed.  Sixteen instead of eight epilogue warps for fc1 (one 64-column group per
+// warp, 96 registers) did NOT recover that: 205-213 us.
+#ifndef VTC_GEMM_ABLATE
+#define VTC_GEMM_ABLATE 0
+#endif
+constexpr int ABLATE = VTC_GEMM_ABLATE;
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;
 constexpr int BK = 64;
@@ -539,9 +549,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 } else {
                     uint32_t r0[32], r1[32];
-                    tmem_ld_32x32b_x32(t_row + c * 64, r0);
-                    tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
-                    tmem_ld_wait();
+                    if constexpr ((ABLATE & 4) != 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) { r0[q] = __float_as_uint(static_cast<float>(q + lane)); r1[q] = r0[q]; }
+                    } else {
+                        tmem_ld_32x32b_x32(t_row + c * 64, r0);
+                        tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+                        tmem_ld_wait();
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 b4 = __ldg(bias4 + j);
@@ -562,7 +577,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             unpack2(add2(pack2u(r1[4 * j + 0], r1[4 * j + 1]), pack2(c4.x, c4.y)), w0, w1);
                             unpack2(add2(pack2u(r1[4 * j + 2], r1[4 * j + 3]), pack2(c4.z, c4.w)), w2, w3);
                         }
-                        if (EPI == VTC_EPI_BIAS_GELU) {
+                        if (EPI == VTC_EPI_BIAS_GELU && (ABLATE & 1) == 0) {
                             if (SPLIT) {      // fp32 mode: exact erf instead of the 4e-7 polynomial
                                 v0 = gelu_erf_exact(v0); v1 = gelu_erf_exact(v1); v2 = gelu_erf_exact(v2); v3 = gelu_erf_exact(v3);
                                 w0 = gelu_erf_exact(w0); w1 = gelu_erf_exact(w1); w2 = gelu_erf_exact(w2); w3 = gelu_erf_exact(w3);
@@ -611,7 +626,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     buf ^= 1;
                 };
-                stage_and_store(pk, n0 + col0);
+                if ((ABLATE & 2) == 0 || EPI == VTC_EPI_BIAS_RESIDUAL || EPI == EPI_PATCH) stage_and_store(pk, n0 + col0);
+                else if (pk[lane & 31] == 0x12345678u) stage_and_store(pk, n0 + col0);      // keep the values alive
                 if (EPI != VTC_EPI_BIAS_RESIDUAL && EPI != EPI_PATCH) {
                     if (SPLIT) stage_and_store(pl, p.N + n0 + col0);
                 }
