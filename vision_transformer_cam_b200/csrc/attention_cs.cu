@@ -159,14 +159,14 @@ __device__ __forceinline__ void rescale_f16(uint32_t taddr, float f) {
 
 // One 32-key chunk: cur = raw accumulator values of this thread's row.  t_p = TMEM address of this warp's P area of the
 // block, pc = index of the chunk inside that area (chunks [0, pc) are already stored there).
-template <bool DUMP>      // DUMP: store the chunk of the packed P as it is produced (multi-block sequences)
+template <bool DUMP, bool SHORT_TAIL>      // DUMP: store the chunk of the packed P as it is produced (multi-block sequences)
 __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nvalid, float sc, float& m, uint64_t& sum2, uint32_t t_p,
                                       float* cls_dst, bool cls_thread, __nv_bfloat16* edst, float* mdst) {
     float mc = -INFINITY;
     if (nvalid >= 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) mc = fmaxf(mc, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
-    } else if (nvalid <= 8) {
+    } else if (SHORT_TAIL && nvalid <= 8) {
         // short tail (197 tokens: 5 keys): eight columns, branch-free (the generic partial-chunk path below costs as much as a
         // full chunk, and this chunk sits on the critical path of the column part that owns it)
 #pragma unroll
@@ -208,7 +208,7 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
             pk[(j >> 1) + 1] = pack_bf16x2(e[j + 2], e[j + 3]);
         }
         sum2 = add2(sum2, add2(sa, sb));
-    } else if (nvalid <= 8) {
+    } else if (SHORT_TAIL && nvalid <= 8) {
         float e[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? ex2_approx(fmaf(__uint_as_float(cur[j]), sc, negm)) : 0.f;
@@ -527,7 +527,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             for (int q = 0; q < 32; ++q) cur[q] = __float_as_uint(static_cast<float>(q + lane) * 0.01f);
                         } else {
                             if (nvalid > 16) tmem_ld_32x32b_x32(t_s + c * 32, cur);
-                            else if (nvalid > 8) tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
+                            else if (nvalid > 8 || DUMP) tmem_ld_32x32b_x16(t_s + c * 32, reinterpret_cast<uint32_t(&)[16]>(cur));
                             else tmem_ld_32x32b_x8(t_s + c * 32, reinterpret_cast<uint32_t(&)[8]>(cur));
                             tmem_ld_wait();
                         }
@@ -538,7 +538,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             tmem_st_32x32b_x16(t_p + (c - c0) * 16, pk0);
                             sum2 = add2(sum2, pack2(1.0f, 1.0f));
                         } else {
-                            chunk<DUMP_LOOP>(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
+                            chunk<DUMP_LOOP, !DUMP>(cur, c - c0, nvalid, sc, m, sum2, t_p, cls_buf + j * KB + c * 32, cls_thread,
                                              (DUMP_LOOP && erow) ? erow + j * KB + c * 32 : nullptr, (DUMP_LOOP && mrow) ? mrow + ((j * KB) >> 5) + c : nullptr);
                         }
                     }
