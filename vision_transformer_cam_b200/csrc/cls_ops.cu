@@ -301,10 +301,24 @@ __global__ void topk_heads_kernel(const HeadParams hp, const float* __restrict__
         fin = feat;
         F = hp.rep;
     }
+    const bool vec4 = ((F | D | P) & 3) == 0;          // 16-byte loads: the weight rows and the shared-memory vectors are 16-byte aligned then
     for (int c = warp; c < C; c += nwarps) {
         float s = 0.f, s1 = 0.f;
-        for (int d = lane; d < F; d += 32) s += hp.head_w[static_cast<size_t>(c) * F + d] * fin[d];
-        for (int d = lane; d < D; d += 32) s1 += hp.head1_w[static_cast<size_t>(c) * D + d] * meanv[d];
+        if (vec4) {
+            const float4* w4 = reinterpret_cast<const float4*>(hp.head_w + static_cast<size_t>(c) * F);
+            const float4* v4 = reinterpret_cast<const float4*>(hp.head1_w + static_cast<size_t>(c) * D);
+            for (int d = lane; d < (F >> 2); d += 32) {
+                const float4 a = __ldg(w4 + d), x = reinterpret_cast<const float4*>(fin)[d];
+                s += (a.x * x.x + a.y * x.y) + (a.z * x.z + a.w * x.w);
+            }
+            for (int d = lane; d < (D >> 2); d += 32) {
+                const float4 a = __ldg(v4 + d), x = reinterpret_cast<const float4*>(meanv)[d];
+                s1 += (a.x * x.x + a.y * x.y) + (a.z * x.z + a.w * x.w);
+            }
+        } else {
+            for (int d = lane; d < F; d += 32) s += hp.head_w[static_cast<size_t>(c) * F + d] * fin[d];
+            for (int d = lane; d < D; d += 32) s1 += hp.head1_w[static_cast<size_t>(c) * D + d] * meanv[d];
+        }
         s = warp_sum(s);
         s1 = warp_sum(s1);
         if (lane == 0) {
