@@ -212,7 +212,9 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
         float e[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? ex2_approx(fmaf(__uint_as_float(cur[j]), sc, negm)) : 0.f;
-        sum2 = add2(sum2, add2(add2(pack2(e[0], e[1]), pack2(e[2], e[3])), add2(pack2(e[4], e[5]), pack2(e[6], e[7]))));
+        // pairs added one after the other, exactly like the generic partial-chunk path: the kernels with and without this path
+        // (plain / packed-P variants) stay bit-identical
+        sum2 = add2(add2(add2(add2(sum2, pack2(e[0], e[1])), pack2(e[2], e[3])), pack2(e[4], e[5])), pack2(e[6], e[7]));
 #pragma unroll
         for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
 #pragma unroll
