@@ -2,10 +2,12 @@
 // P[b,h,0,:], any sequence length up to 2048 tokens, bf16 operands.  (Full-P output and the split-bf16 fp32 mode
 // are served by attention_kv.cu.)
 //
-// What bounds this kernel is the TMEM read port: every score has to come out of TMEM once as fp32 (54 B/clk per SM
-// measured, tools/ubench/tmem.cu), and tcgen05.ld stalls the issuing warp for the whole transfer (303 clk per 32x32
-// block), so the MUFU / FMA work of a warp cannot overlap its own loads -- only other warps on the same sub-partition
-// can fill that time.  Hence the shape:
+// Every score has to come out of TMEM once as fp32 (54 B/clk per SM measured, tools/ubench/tmem.cu), and tcgen05.ld stalls
+// the issuing warp for the whole transfer (303 clk per 32x32 block), so the MUFU / FMA work of a warp cannot overlap its own
+// loads -- only other warps on the same sub-partition can fill that time.  (Round-2 ablation, DESIGN.md 3.1: with four
+// softmax warps per sub-partition the loads ARE hidden -- removing them changes nothing; what is exposed is the softmax
+// arithmetic, MUFU-bound while the two groups' softmax phases overlap, on top of a per-item chain of MMA round trips.)
+// Hence the shape:
 //   * one persistent CTA per SM runs TWO independent pipelines ("groups"), each on its own stream of work items
 //     (image, head, 128-query tile), with its own 256 TMEM columns, Q / K / V tiles, producer warp and MMA warp;
 //   * inside a group the 128 x KB score block is split by COLUMNS between two sets of four softmax warps (PARTS = 2):
