@@ -16,9 +16,12 @@ static int grid_cap(size_t blocks, int per_sm) {
 // ---- attention rollout ----------------------------------------------------------------------------------------
 // r <- r . A_l for l = L-1 .. 0, A_l = (Pbar_l + I) / rowsum(Pbar_l + I): only the CLS row of the product is consumed
 // (predict.py:229-232), so the dense N^3 chain collapses to a vector-matrix chain.  One CTA per image; each warp
-// streams whole rows (coalesced), gets the row sum by shuffle, and accumulates w_i * row into its private column
-// accumulators in shared memory; the matrix is read exactly once.
+// streams whole rows (coalesced, four rows in flight, the values kept in registers), gets the row sums by shuffle, and
+// accumulates w_i * row into its private column accumulators in shared memory; the matrix is read exactly once.  This is the
+// fp32 entry point (vtc_rollout, exact on fp32 head means); the forward's own rollout runs on bf16 operands (below).
 constexpr int ROLL_WARPS = 8;
+constexpr int ROLL_ROWS = 4;          // rows a warp keeps in flight (the kernel is latency-bound: one row per warp at a time took 4x longer)
+constexpr int ROLL_MAXV = 8;          // values per lane and row held in registers: n_tokens <= 256; longer rows take the two-pass path
 __global__ void __launch_bounds__(ROLL_WARPS * 32) rollout_kernel(const float* __restrict__ pbar, float* __restrict__ out, int L, int B, int N) {
     extern __shared__ float sm[];
     float* r = sm;                  // [N]
@@ -27,18 +30,53 @@ __global__ void __launch_bounds__(ROLL_WARPS * 32) rollout_kernel(const float* _
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = threadIdx.x; j < N; j += blockDim.x) r[j] = (j == 0) ? 1.0f : 0.0f;
     __syncthreads();
+    const bool in_regs = N <= 32 * ROLL_MAXV;
     for (int l = L - 1; l >= 0; --l) {
         const float* A = pbar + (static_cast<size_t>(l) * B + b) * N * N;
         float* my = acc + warp * N;
         for (int j = lane; j < N; j += 32) my[j] = 0.f;
-        for (int i = warp; i < N; i += ROLL_WARPS) {
-            const float ri = r[i];
-            if (ri == 0.0f) continue;            // exact zeros only (the first step has a single non-zero row)
-            const float* row = A + static_cast<size_t>(i) * N;
-            float s = 0.f;
-            for (int j = lane; j < N; j += 32) s += row[j];
-            const float w = ri / (warp_sum(s) + 1.0f);
-            for (int j = lane; j < N; j += 32) my[j] += w * row[j] + (j == i ? w : 0.f);   // second touch hits L1; + identity
+        if (in_regs) {
+            for (int i0 = warp * ROLL_ROWS; i0 < N; i0 += ROLL_WARPS * ROLL_ROWS) {
+                float v[ROLL_ROWS][ROLL_MAXV], s[ROLL_ROWS];
+#pragma unroll
+                for (int q = 0; q < ROLL_ROWS; ++q) {          // all loads of the four rows are issued before anything consumes them
+                    const int i = i0 + q;
+                    const bool live = i < N && r[i] != 0.0f;   // exact zeros only (the first step has a single non-zero row)
+                    const float* row = A + static_cast<size_t>(i < N ? i : 0) * N;
+#pragma unroll
+                    for (int k = 0; k < ROLL_MAXV; ++k) v[q][k] = (live && lane + 32 * k < N) ? __ldg(row + lane + 32 * k) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < ROLL_ROWS; ++q) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < ROLL_MAXV; ++k) t += v[q][k];          // same order as the one-row loop: bit-identical sums
+                    s[q] = warp_sum(t);
+                }
+#pragma unroll
+                for (int q = 0; q < ROLL_ROWS; ++q) {
+                    const int i = i0 + q;
+                    if (i >= N) break;
+                    const float ri = r[i];
+                    if (ri == 0.0f) continue;
+                    const float w = ri / (s[q] + 1.0f);
+#pragma unroll
+                    for (int k = 0; k < ROLL_MAXV; ++k) {
+                        const int j = lane + 32 * k;
+                        if (j < N) my[j] += w * v[q][k] + (j == i ? w : 0.f);          // + identity
+                    }
+                }
+            }
+        } else {
+            for (int i = warp; i < N; i += ROLL_WARPS) {
+                const float ri = r[i];
+                if (ri == 0.0f) continue;
+                const float* row = A + static_cast<size_t>(i) * N;
+                float s = 0.f;
+                for (int j = lane; j < N; j += 32) s += row[j];
+                const float w = ri / (warp_sum(s) + 1.0f);
+                for (int j = lane; j < N; j += 32) my[j] += w * row[j] + (j == i ? w : 0.f);   // second touch hits L1; + identity
+            }
         }
         __syncthreads();
         for (int j = threadIdx.x; j < N; j += blockDim.x) {
