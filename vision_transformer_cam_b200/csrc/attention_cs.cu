@@ -550,7 +550,9 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     // ---- the warps that share these rows agree on the row maximum (and, at the end, on the row sum)
                     float s0, s1;
                     unpack2(sum2, s0, s1);
-                    named_bar_sync(row_bar, 32 * PARTS);           // everybody is done with the previous block's exchange slots
+                    // (no barrier before the write: whoever still has to READ the previous block's exchange slots does so before it
+                    // arrives on p_full, and this warp only got here through s_full / o_full of a later MMA, which waited for all
+                    // eight arrivals)
                     xch[part * 128 + r_local] = make_float2(m, s0 + s1);
                     named_bar_sync(row_bar, 32 * PARTS);
                     stamp(3);
