@@ -27,6 +27,12 @@ for rep in range(3):
             e1.record()
             torch.cuda.synchronize()
             print(f"{path.split('/')[-1]:24s} bias={'yes' if bias is not None else 'no '}: {e0.elapsed_time(e1) * 100:.1f} us")
+outs = []
+for path, lib in libs:          # how far apart the builds' results are (max |difference| of O and of the CLS rows, against the first library)
+    assert lib.vtc_attention(qkv.data_ptr(), kb.data_ptr(), out.data_ptr(), cls.data_ptr(), None, B, N, H, 0.125, st) == 0
+    torch.cuda.synchronize()
+    outs.append((out.float().clone(), cls.clone()))
+    print(f"{path.split('/')[-1]:24s} vs first: O {float((outs[-1][0] - outs[0][0]).abs().max()):.2e}  cls rows {float((outs[-1][1] - outs[0][1]).abs().max()):.2e}")
 if os.environ.get("VTC_AB_PLAIN_ONLY") == "1":
     sys.exit(0)
 print("---- vtc_attention_mean (attention + packed P + head mean)")

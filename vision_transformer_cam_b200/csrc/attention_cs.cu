@@ -159,6 +159,30 @@ __device__ __forceinline__ void rescale_f16(uint32_t taddr, float f) {
     tmem_st_32x32b_x16(taddr, q);
 }
 
+// Experiment kept in the tree (off by default: measured no gain at 25-31 %, a loss at 50 %): exponentials on the
+// FMA pipe.  Every VTC_ACS_POLY-th PAIR of a full chunk takes 2^x = 2^n * p(r) (n = round(x), |r| <= 1/2, p = degree-3 minimax
+// fit of 2^r: relative error 9.6e-5, a twentieth of the bf16 rounding P gets anyway; 5 issue slots per element) instead of
+// MUFU.EX2 (8 clk per warp instruction).  0 = every exponential on MUFU.
+#ifndef VTC_ACS_POLY
+#define VTC_ACS_POLY 0
+#endif
+__device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));        // masked keys sit at ~ -144: keep the exponent field in range
+    const uint64_t t2 = add2(x2, pack2(12582912.0f, 12582912.0f));          // 1.5 * 2^23: the low mantissa bits of t are n
+    const uint64_t n2 = add2(t2, pack2(-12582912.0f, -12582912.0f));
+    const uint64_t r2 = fma2(n2, pack2(-1.0f, -1.0f), x2);
+    uint64_t q = fma2(pack2(0.054526202380657196f, 0.054526202380657196f), r2, pack2(0.2427794337272644f, 0.2427794337272644f));
+    q = fma2(q, r2, pack2(0.6933389902114868f, 0.6933389902114868f));
+    q = fma2(q, r2, pack2(0.9999109506607056f, 0.9999109506607056f));
+    float q0, q1, t0, t1;
+    unpack2(q, q0, q1);
+    unpack2(t2, t0, t1);
+    e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 // One 32-key chunk: cur = raw accumulator values of this thread's row.  t_p = TMEM address of this warp's P area of the
 // block, pc = index of the chunk inside that area (chunks [0, pc) are already stored there).
 template <bool DUMP, bool SHORT_TAIL>      // DUMP: store the chunk of the packed P as it is produced (multi-block sequences)
@@ -197,7 +221,12 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
             float x0, x1;
-            unpack2(fma2(pack2u(cur[j], cur[j + 1]), sc2, negm2), x0, x1);
+            const uint64_t x2 = fma2(pack2u(cur[j], cur[j + 1]), sc2, negm2);
+            if (VTC_ACS_POLY > 0 && ((j >> 1) % (VTC_ACS_POLY > 0 ? VTC_ACS_POLY : 1)) == (VTC_ACS_POLY > 0 ? VTC_ACS_POLY : 1) - 1) {
+                ex2_poly_pair(x2, e[j], e[j + 1]);
+                continue;
+            }
+            unpack2(x2, x0, x1);
             e[j] = ex2_approx(x0);
             e[j + 1] = ex2_approx(x1);
         }

@@ -468,28 +468,6 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 }
 
 
-// 2^x for two values on the FMA pipe (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-5 polynomial for 2^f
-// (max relative error 3.7e-7, tools/fit_exp2.py), exponent re-inserted with one integer multiply-add.  B200 retires
-// only ~8 MUFU.EX2 per clock per SM, which bounds the attention softmax; half of its exponentials take this path.
-__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
-    float x0, x1;
-    unpack2(x2, x0, x1);
-    x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
-    const uint64_t t2 = add2(x2, pack2(12582912.0f, 12582912.0f));
-    const uint64_t n2 = add2(t2, pack2(-12582912.0f, -12582912.0f));
-    const uint64_t f2 = fma2(n2, pack2(-1.0f, -1.0f), x2);
-    uint64_t q = fma2(pack2(0.0013395280111581087f, 0.0013395280111581087f), f2, pack2(0.009670763276517391f, 0.009670763276517391f));
-    q = fma2(q, f2, pack2(0.05550340563058853f, 0.05550340563058853f));
-    q = fma2(q, f2, pack2(0.24022211134433746f, 0.24022211134433746f));
-    q = fma2(q, f2, pack2(0.6931471824645996f, 0.6931471824645996f));
-    q = fma2(q, f2, pack2(1.0f, 1.0f));
-    float q0, q1, t0, t1;
-    unpack2(q, q0, q1);
-    unpack2(t2, t0, t1);
-    e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-    e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-}
-
 // erf-GELU of two values at once for the GEMM epilogue.
 //   gelu(x) = relu(x) - |x/2| * erfc(|x|/sqrt2),   erfc(|x|/sqrt2) = 2^P6(min(|x|, 6))
 // P6 = degree-6 polynomial fit of log2(erfc(a/sqrt2)) on [0,6] (tools/fit_gelu.py): |gelu error| <= 4.3e-7 absolute over
