@@ -166,9 +166,26 @@ __device__ __forceinline__ void rescale_f16(uint32_t taddr, float f) {
 #ifndef VTC_ACS_POLY
 #define VTC_ACS_POLY 0
 #endif
+#ifndef VTC_ACS_POLY_SCALAR
+#define VTC_ACS_POLY_SCALAR 0
+#endif
+__device__ __forceinline__ float ex2_poly_scalar(float x) {      // the same on scalar instructions with immediate operands
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;
+    const float r = x - (t - 12582912.0f);
+    float q = fmaf(0.054526202380657196f, r, 0.2427794337272644f);
+    q = fmaf(q, r, 0.6933389902114868f);
+    q = fmaf(q, r, 0.9999109506607056f);
+    return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& e0, float& e1) {
     float x0, x1;
     unpack2(x2, x0, x1);
+    if (VTC_ACS_POLY_SCALAR) {
+        e0 = ex2_poly_scalar(x0);
+        e1 = ex2_poly_scalar(x1);
+        return;
+    }
     x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));        // masked keys sit at ~ -144: keep the exponent field in range
     const uint64_t t2 = add2(x2, pack2(12582912.0f, 12582912.0f));          // 1.5 * 2^23: the low mantissa bits of t are n
     const uint64_t n2 = add2(t2, pack2(-12582912.0f, -12582912.0f));
