@@ -42,7 +42,8 @@ namespace vtc {
 namespace acs {
 // Ablation switches for timing experiments (tools/ab_attn_lib.py on libraries built with -DVTC_ACS_ABLATE=k; results are WRONG
 // by construction): bit 0 = no softmax arithmetic (a chunk is stored back as loaded), bit 1 = no tcgen05.ld of the scores,
-// bit 2 = one P V k-step instead of all, bit 3 = no tcgen05.ld of O in the epilogue.  0 in every shipped build.
+// bit 2 = one P V k-step instead of all, bit 3 = no tcgen05.ld of O in the epilogue, bit 4 = no MUFU.EX2 in full chunks (e = x),
+// bit 5 = no maximum pass over full chunks.  0 in every shipped build.
 #ifndef VTC_ACS_ABLATE
 #define VTC_ACS_ABLATE 0
 #endif
@@ -207,6 +208,8 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
                                       float* cls_dst, bool cls_thread, __nv_bfloat16* edst, float* mdst) {
     float mc = -INFINITY;
     if (nvalid >= 32) {
+        if constexpr ((ABLATE & 32) != 0) mc = __uint_as_float(cur[0]);
+        else
 #pragma unroll
         for (int j = 0; j < 32; j += 2) mc = fmaxf(mc, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
     } else if (SHORT_TAIL && nvalid <= 8) {
@@ -244,6 +247,11 @@ __device__ __forceinline__ void chunk(const uint32_t (&cur)[32], int pc, int nva
                 continue;
             }
             unpack2(x2, x0, x1);
+            if constexpr ((ABLATE & 16) != 0) {
+                e[j] = x0;
+                e[j + 1] = x1;
+                continue;
+            }
             e[j] = ex2_approx(x0);
             e[j + 1] = ex2_approx(x1);
         }
