@@ -3,7 +3,7 @@
 depth 6 in the mask-firing 'masked' regime: layers 0-4 run the plain attention kernel, layer 5 the masked one); range B = the
 kernels the forward does not reach in that configuration, through their C-ABI entry points, at the same batch.
 
-    python tools/kernel_zoo.py [batch]"""
+    python tools/kernel_zoo.py [batch]        (a small batch, e.g. 8, is what a compute-sanitizer pass uses)"""
 import os
 import sys
 
@@ -29,7 +29,8 @@ labels[torch.arange(B), torch.arange(B) % 20] = 1
 qkv = torch.randn((B, 197, 3 * 768), generator=g, device=dev).bfloat16()
 mean12 = torch.randn((12, B, 197, 197), generator=g, device=dev).softmax(-1)
 opnd = ops.rollout_operand_from_mean(mean12)
-gt = torch.randint(0, 21, (32, 375, 500), generator=g, device=dev, dtype=torch.uint8)
+n32 = min(B, 32)
+gt = torch.randint(0, 21, (n32, 375, 500), generator=g, device=dev, dtype=torch.uint8)
 
 
 def range_a():
@@ -40,7 +41,7 @@ def range_b(o):
     ops.attention_mean_operand(qkv, 12, 0.125)                       # attention_cs<packed P> + head_mean_packed<operand>
     ops.attention_mean(qkv, 12, 0.125)                               # ... + head_mean_packed<fp32>
     ops.rollout_operands(opnd, 197)                                  # streaming rollout
-    ops.rollout(mean12[:, :64].contiguous())                         # fp32 entry point
+    ops.rollout(mean12[:, :min(B, 64)].contiguous())                         # fp32 entry point
     ops.patchify_u8(u8, 16, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
     cam = CAM.classic_cam(o.tokens_last, model.head1.weight.data)    # cam_project
     CAM.cam_pseudo_label(cam, labels, hw)                            # cam_label (fused upsample + argmax)
@@ -49,7 +50,7 @@ def range_b(o):
     CAM.layer_maps(o.cls_rows)                                       # cls_layer_map
     seg = CAM.hwp_pseudo_seg(o, model.head1.weight.data, hw)         # hwp_cos_vote, cls_layer_map, hwp_seg
     cm = CAM.ConfusionMatrix(20, device=dev)
-    cm.update(gt, seg[:32])                                          # confmat
+    cm.update(gt, seg[:n32])                                          # confmat
     CAM.average_precision(labels, torch.sigmoid(o.hwp_logits))
     CAM.patch_similarity(o.tokens_last[:32])
     ops.normalize_max_(torch.rand((B, 196), device=dev))
