@@ -22,6 +22,10 @@ __global__ void k(float* out, int iters, unsigned long long* cyc) {
             if (OP == 4) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(a[i]) : "f"(0.999f));
             if (OP == 5) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(a[(i + 3) & 7]));
             if (OP == 6) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+            if (OP == 7) asm volatile("fma.rn.f32 %0, %0, %1, 0f3E800000;" : "+f"(a[i]) : "f"(a[(i + 3) & 7]));          // immediate addend (Horner step)
+            if (OP == 8) asm volatile("{.reg .b64 c; mov.b64 c, {0f3E800000, 0f3E800000}; fma.rn.f32x2 %0, %0, %1, c;}" : "+l"(p[i]) : "l"(p[(i + 3) & 7]));
+            if (OP == 9) asm volatile("add.rn.f32 %0, %0, 0f4B400000;" : "+f"(a[i]));
+            if (OP == 10) { uint32_t r = __float_as_uint(a[i]); asm volatile("mad.lo.u32 %0, %1, 8388608, %0;" : "+r"(r) : "r"(__float_as_uint(a[(i + 3) & 7]))); a[i] = __uint_as_float(r); }
         }
     }
     unsigned long long t1 = clock64();
@@ -55,5 +59,9 @@ int main() {
     run<3>("F2FP bf16x2 pack");
     run<4>("FFMA scalar");
     run<5>("FMNMX");
+    run<7>("FFMA scalar, imm addend");
+    run<8>("FFMA2, imm addend");
+    run<9>("FADD scalar, imm");
+    run<10>("IMAD imm");
     return 0;
 }
