@@ -90,6 +90,24 @@ def test_device_feeder_overlapped_ingest_equals_direct(env):
     assert torch.equal(out["cam"], ref["cam"]) and out["cam"].shape[0] == 20
 
 
+def test_host_drain_overlapped_read_back_equals_direct(env):
+    """Results read back through HostDrain (copy on a side stream, the device tensor dropped by the caller at once) equal a
+    synchronous .cpu() of the same step, for several steps into per-step pinned buffers; mismatched pairs are refused."""
+    from vision_transformer_cam_b200 import pipeline as PIPE
+    VF, dev, model = env["VF"], env["dev"], env["model"]
+    xs = [VF.make_images(4 * i, 4).to(dev) for i in range(4)]
+    direct = [model.forward_cam(x, mask_norm="image").logits.cpu() for x in xs]
+    drain = PIPE.HostDrain(dev)
+    hosts = [torch.empty((4, direct[0].shape[1])).pin_memory() for _ in xs]
+    for x, h in zip(xs, hosts):
+        drain.push(h, model.forward_cam(x, mask_norm="image").logits)        # the only reference to the device tensor dies here
+        torch.empty((1 << 20,), device=dev).fill_(7.0)                         # churn the caching allocator while the copy may still be pending
+    drain.wait(sync=True)
+    assert all(torch.equal(a, b) for a, b in zip(hosts, direct))
+    with pytest.raises(ValueError):
+        drain.push(torch.empty((3, 3)), xs[0])
+
+
 # ---- SURVEY 8(f)-3/4: VOC12 ingest and the utils.py callers ---------------------------------------------------------------
 @pytest.fixture(scope="module")
 def voc(tmp_path_factory):

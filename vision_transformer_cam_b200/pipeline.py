@@ -81,6 +81,39 @@ class DeviceFeeder:
                 self.free[k].record(compute)
 
 
+class HostDrain:
+    """Device -> host read-back overlapped with compute, the counterpart of `DeviceFeeder`: the copy of a step's results into
+    (pinned) host tensors runs on a side stream behind an event on the caller's stream, so the next step's kernels do not queue
+    behind it.
+
+        drain = HostDrain(device)
+        for x in batches:
+            o = model.forward_cam(x)
+            drain.push(cam_host, cam)          # returns at once; cam may be dropped by the caller
+        drain.wait()                           # the caller's stream (and the host, if sync=True) sees every copy finished
+
+    A host tensor handed to `push` must not be read before `wait()` (or `drain.done.synchronize()`)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.done = torch.cuda.Event()
+
+    def push(self, host: torch.Tensor, dev: torch.Tensor) -> None:
+        if tuple(host.shape) != tuple(dev.shape) or host.dtype != dev.dtype or host.is_cuda or not dev.is_cuda:
+            raise ValueError(f"HostDrain.push: host {tuple(host.shape)} {host.dtype} / device {tuple(dev.shape)} {dev.dtype} do not match")
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))       # the producer kernels of `dev`
+        with torch.cuda.stream(self.copy_stream):
+            host.copy_(dev, non_blocking=True)
+            self.done.record(self.copy_stream)
+        dev.record_stream(self.copy_stream)        # the allocator must not hand the block out again before the copy has read it
+
+    def wait(self, sync: bool = False) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.copy_stream)
+        if sync:
+            self.done.synchronize()
+
+
 @dataclass
 class Prediction:
     """predict.py outputs for a batch."""
