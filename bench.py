@@ -480,6 +480,17 @@ def main():
         drain.wait()                                # the closing event below is recorded behind the last read-back
 
     e2e_run(2)
+    # the host link of this box, measured alone (diagnostic: an e2e well below `value` on a box with a slow link is the link, not the path)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe = torch.empty_like(x_host, device=dev)
+    probe.copy_(x_host, non_blocking=True)
+    h0.record()
+    for _ in range(3):
+        probe.copy_(x_host, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * x_host.numel() * 4 / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    del probe
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -494,7 +505,7 @@ def main():
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_t)
     e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
-           "d2h_bytes_per_step": (cam_host.numel() + logit_host.numel()) * 4, "ms_per_step": ms_e2e / K,
+           "d2h_bytes_per_step": (cam_host.numel() + logit_host.numel()) * 4, "ms_per_step": ms_e2e / K, "h2d_link_gbps_alone": round(h2d_gbps, 1),
            "overlap": "H2D of step i+1 on a copy stream during step i (pipeline.DeviceFeeder, two device buffers); D2H of step i on a second copy stream (pipeline.HostDrain), all of it inside the timed region"}
 
     # ---- dominant kernel, timed live with CUDA events around every launch of the same workload

@@ -1,6 +1,9 @@
 """Timeline of the column-split attention kernel (debug): per (CTA, step, warp) %clock64 stamps (SM clocks).
 softmax warps 0-15, slots: 0 step top, 1 S ready, 2 chunks done, 3 row barrier passed, 4 p_full arrived, 5 O ready, 6 item done
-MMA threads (rows 16, 17), slots: 0 step top, 1 O region free, 2 K landed (QK issued), 3 QK committed, 4 P ready, 5 V landed (PV issued)"""
+MMA threads (rows 16, 17), slots: 0 step top, 1 O region free, 2 K landed (QK issued), 3 QK committed, 4 P ready, 5 V landed (PV issued)
+
+The stamps are compiled in only with -DVTC_ACS_TRACE=1:
+    tools/build_ablate.sh 10000000 && VTC_LIB_PATH=$PWD/tools/ab/libvtc_ablate10000000.so python tools/attn_trace_cs.py"""
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -82,9 +82,9 @@ class DeviceFeeder:
 
 
 class HostDrain:
-    """Device -> host read-back overlapped with compute, the counterpart of `DeviceFeeder`: the copy of a step's results into
-    (pinned) host tensors runs on a side stream behind an event on the caller's stream, so the next step's kernels do not queue
-    behind it.
+    """Device -> host read-back overlapped with compute, the counterpart of `DeviceFeeder`: a step's results are copied
+    device-to-device into a small staging ring on the caller's stream (a few microseconds) and from there into (pinned) host
+    tensors on a side stream, so the next step's kernels do not queue behind the PCIe transfer.
 
         drain = HostDrain(device)
         for x in batches:
@@ -92,21 +92,38 @@ class HostDrain:
             drain.push(cam_host, cam)          # returns at once; cam may be dropped by the caller
         drain.wait()                           # the caller's stream (and the host, if sync=True) sees every copy finished
 
-    A host tensor handed to `push` must not be read before `wait()` (or `drain.done.synchronize()`)."""
+    The staging ring (not `Tensor.record_stream`) is what keeps the device tensor alive: a block the caching allocator cannot
+    hand out again until a side-stream event has passed makes the next step's allocations fall through to cudaMalloc, which
+    synchronises the device.  A host tensor handed to `push` must not be read before `wait()`."""
 
-    def __init__(self, device):
+    def __init__(self, device, depth: int = 2):
         self.device = torch.device(device)
+        self.depth = depth
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.rings: dict = {}              # (shape, dtype) -> [buffers, staged events, drained events, pushes so far]
         self.done = torch.cuda.Event()
 
     def push(self, host: torch.Tensor, dev: torch.Tensor) -> None:
         if tuple(host.shape) != tuple(dev.shape) or host.dtype != dev.dtype or host.is_cuda or not dev.is_cuda:
             raise ValueError(f"HostDrain.push: host {tuple(host.shape)} {host.dtype} / device {tuple(dev.shape)} {dev.dtype} do not match")
-        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))       # the producer kernels of `dev`
+        key = (tuple(dev.shape), dev.dtype)
+        ring = self.rings.get(key)
+        if ring is None:
+            ring = self.rings[key] = [[torch.empty_like(dev) for _ in range(self.depth)], [torch.cuda.Event() for _ in range(self.depth)],
+                                      [torch.cuda.Event() for _ in range(self.depth)], 0]
+        bufs, staged, drained, n = ring
+        k = n % self.depth
+        ring[3] = n + 1
+        compute = torch.cuda.current_stream(self.device)
+        if n >= self.depth:
+            compute.wait_event(drained[k])         # the read-back that used this staging buffer two pushes ago
+        bufs[k].copy_(dev)                         # device to device, on the caller's stream
+        staged[k].record(compute)
         with torch.cuda.stream(self.copy_stream):
-            host.copy_(dev, non_blocking=True)
+            self.copy_stream.wait_event(staged[k])
+            host.copy_(bufs[k], non_blocking=True)
+            drained[k].record(self.copy_stream)
             self.done.record(self.copy_stream)
-        dev.record_stream(self.copy_stream)        # the allocator must not hand the block out again before the copy has read it
 
     def wait(self, sync: bool = False) -> None:
         torch.cuda.current_stream(self.device).wait_stream(self.copy_stream)
